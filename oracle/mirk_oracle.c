@@ -1,0 +1,847 @@
+/*
+ * mirk_oracle.c — CPU restatement of the MIRK4/MIRK6 collocation Newton path.
+ * TEST INFRASTRUCTURE ONLY (see mirk_oracle.h).  PARITY UNPINNED against a live Julia run.
+ *
+ * Every function cites the reference code it restates (paths relative to /root/reference,
+ * MIRK/ = lib/BoundaryValueDiffEqMIRK/src/, CORE/ = lib/BoundaryValueDiffEqCore/src/).
+ * The Newton loop and the linear solve live in third-party packages that are not vendored
+ * (NonlinearSolveFirstOrder "1.2, 2", LinearSolve, FastAlmostBandedMatrices "0.1.4",
+ * BandedMatrices "1.7.5"; compat ranges in lib/BoundaryValueDiffEqMIRK/Project.toml); their
+ * published algorithms are restated: Newton-Raphson with an |F|_inf <= abstol stop, and a
+ * row-pivoted LU elimination of the almost-block-diagonal matrix.
+ */
+#include "mirk_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* options / tableaus                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_default_options(orc_options *o) {
+    o->abstol = 1e-6;              /* MIRK/mirk.jl:50 */
+    o->adaptive = 1;
+    o->defect_threshold = 0.1;     /* CORE/calc_errors.jl:54-60 DefectControl() */
+    o->max_num_subintervals = 3000; /* MIRK/algorithms.jl:55-61 */
+    o->maxiters = 1000;
+    o->reinterp_inplace = 0; /* see DESIGN.md "Q3": 1 reproduces the reference's in-place hazard */
+    o->max_outer = 60;
+}
+
+/* MIRK/mirk_tableaus.jl:62-87 (MIRK4) and :120-152 (MIRK6).  Only 1:s of c,v,b is used. */
+int orc_tableau_get(int order, orc_tableau *T) {
+    memset(T, 0, sizeof(*T));
+    T->order = order;
+    if (order == 4) {
+        T->s = 3;
+        T->s_star = 4;
+        const double c[3] = {0.0, 1.0, 1.0 / 2.0};
+        const double v[3] = {0.0, 1.0, 1.0 / 2.0};
+        const double b[3] = {1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0};
+        for (int r = 0; r < 3; r++) { T->c[r] = c[r]; T->v[r] = v[r]; T->b[r] = b[r]; }
+        T->x[2][0] = 1.0 / 8.0;
+        T->x[2][1] = -1.0 / 8.0;
+        T->c_star[0] = 3.0 / 4.0;
+        T->v_star[0] = 27.0 / 32.0;
+        T->x_star[0][0] = 3.0 / 64.0;
+        T->x_star[0][1] = -9.0 / 64.0;
+        T->tau_star = 0.226;
+        return 0;
+    }
+    if (order == 6) {
+        T->s = 5;
+        T->s_star = 9;
+        const double c[5] = {0.0, 1.0, 1.0 / 4.0, 3.0 / 4.0, 1.0 / 2.0};
+        const double v[5] = {0.0, 1.0, 5.0 / 32.0, 27.0 / 32.0, 1.0 / 2.0};
+        const double b[5] = {7.0 / 90.0, 7.0 / 90.0, 16.0 / 45.0, 16.0 / 45.0, 2.0 / 15.0};
+        for (int r = 0; r < 5; r++) { T->c[r] = c[r]; T->v[r] = v[r]; T->b[r] = b[r]; }
+        T->x[2][0] = 9.0 / 64.0;  T->x[2][1] = -3.0 / 64.0;
+        T->x[3][0] = 3.0 / 64.0;  T->x[3][1] = -9.0 / 64.0;
+        T->x[4][0] = -5.0 / 24.0; T->x[4][1] = 5.0 / 24.0;
+        T->x[4][2] = 2.0 / 3.0;   T->x[4][3] = -2.0 / 3.0;
+        const double cs[4] = {7.0 / 16.0, 3.0 / 8.0, 9.0 / 16.0, 1.0 / 8.0};
+        for (int r = 0; r < 4; r++) { T->c_star[r] = cs[r]; T->v_star[r] = cs[r]; }
+        const double xs[4][9] = {
+            {1547.0 / 32768.0, -1225.0 / 32768.0, 749.0 / 4096.0, -287.0 / 2048.0,
+             -861.0 / 16384.0, 0, 0, 0, 0},
+            {83.0 / 1536.0, -13.0 / 384.0, 283.0 / 1536.0, -167.0 / 1536.0, -49.0 / 512.0, 0, 0, 0, 0},
+            {1225.0 / 32768.0, -1547.0 / 32768.0, 287.0 / 2048.0, -749.0 / 4096.0,
+             861.0 / 16384.0, 0, 0, 0, 0},
+            {233.0 / 3456.0, -19.0 / 1152.0, 0, 0, 0, -5.0 / 72.0, 7.0 / 72.0, -17.0 / 216.0, 0}};
+        memcpy(T->x_star, xs, sizeof(xs));
+        T->tau_star = 0.7156;
+        return 0;
+    }
+    return -1;
+}
+
+/* MIRK/interpolation.jl:481-499 (order 4) and :528-575 (order 6): weights w(tau), w'(tau). */
+void orc_interp_weights(int order, double tau, double *w, double *wp) {
+    const double t = tau;
+    if (order == 4) {
+        const double t2 = t * t, tm1 = t - 1.0, t4m3 = t * 4.0 - 3.0, t2m1 = t * 2.0 - 1.0;
+        w[0] = -t * (2.0 * t - 3.0) * (2.0 * t2 - 3.0 * t + 2.0) / 6.0;
+        w[1] = t2 * (12.0 * t2 - 20.0 * t + 9.0) / 6.0;
+        w[2] = 2.0 * t2 * (6.0 * t2 - 14.0 * t + 9.0) / 3.0;
+        w[3] = -16.0 * t2 * tm1 * tm1 / 3.0;
+        wp[0] = -tm1 * t4m3 * t2m1 / 3.0;
+        wp[1] = t * t2m1 * t4m3;
+        wp[2] = 4.0 * t * t4m3 * tm1;
+        wp[3] = -32.0 * t * t2m1 * tm1 / 3.0;
+        return;
+    }
+    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t, t6 = t3 * t3;
+    w[0] = t - 28607.0 / 7434.0 * t2 - 166210.0 / 33453.0 * t3 + 334780.0 / 11151.0 * t4 -
+           1911296.0 / 55755.0 * t5 + 406528.0 / 33453.0 * t6;
+    w[1] = 777.0 / 590.0 * t2 - 2534158.0 / 234171.0 * t3 + 2088580.0 / 78057.0 * t4 -
+           10479104.0 / 390285.0 * t5 + 11328512.0 / 1170855.0 * t6;
+    w[2] = -1008.0 / 59.0 * t2 + 222176.0 / 1593.0 * t3 - 180032.0 / 531.0 * t4 +
+           876544.0 / 2655.0 * t5 - 180224.0 / 1593.0 * t6;
+    w[3] = w[2];
+    w[4] = -378.0 / 59.0 * t2 + 27772.0 / 531.0 * t3 - 22504.0 / 177.0 * t4 +
+           109568.0 / 885.0 * t5 - 22528.0 / 531.0 * t6;
+    w[5] = -95232.0 / 413.0 * t2 + 62384128.0 / 33453.0 * t3 - 49429504.0 / 11151.0 * t4 +
+           46759936.0 / 11151.0 * t5 - 46661632.0 / 33453.0 * t6;
+    w[6] = 896.0 / 5.0 * t2 - 4352.0 / 3.0 * t3 + 3456.0 * t4 - 16384.0 / 5.0 * t5 +
+           16384.0 / 15.0 * t6;
+    w[7] = 50176.0 / 531.0 * t2 - 179554304.0 / 234171.0 * t3 + 143363072.0 / 78057.0 * t4 -
+           136675328.0 / 78057.0 * t5 + 137363456.0 / 234171.0 * t6;
+    w[8] = 16384.0 / 441.0 * t3 - 16384.0 / 147.0 * t4 + 16384.0 / 147.0 * t5 - 16384.0 / 441.0 * t6;
+    wp[0] = 1.0 - 28607.0 / 3717.0 * t - 166210.0 / 11151.0 * t2 + 1339120.0 / 11151.0 * t3 -
+            1911296.0 / 11151.0 * t4 + 813056.0 / 11151.0 * t5;
+    wp[1] = 777.0 / 295.0 * t - 2534158.0 / 78057.0 * t2 + 8354320.0 / 78057.0 * t3 -
+            10479104.0 / 78057.0 * t4 + 22657024.0 / 390285.0 * t5;
+    wp[2] = -2016.0 / 59.0 * t + 222176.0 / 531.0 * t2 - 720128.0 / 531.0 * t3 +
+            876544.0 / 531.0 * t4 - 360448.0 / 531.0 * t5;
+    wp[3] = wp[2];
+    wp[4] = -756.0 / 59.0 * t + 27772.0 / 177.0 * t2 - 90016.0 / 177.0 * t3 + 109568.0 / 177.0 * t4 -
+            45056.0 / 177.0 * t5;
+    wp[5] = -190464.0 / 413.0 * t + 62384128.0 / 11151.0 * t2 - 197718016.0 / 11151.0 * t3 +
+            233799680.0 / 11151.0 * t4 - 93323264.0 / 11151.0 * t5;
+    wp[6] = 1792.0 / 5.0 * t - 4352.0 * t2 + 13824.0 * t3 - 16384.0 * t4 + 32768.0 / 5.0 * t5;
+    wp[7] = 100352.0 / 531.0 * t - 179554304.0 / 78057.0 * t2 + 573452288.0 / 78057.0 * t3 -
+            683376640.0 / 78057.0 * t4 + 274726912.0 / 78057.0 * t5;
+    wp[8] = 16384.0 / 147.0 * t2 - 65536.0 / 147.0 * t3 + 81920.0 / 147.0 * t4 - 32768.0 / 147.0 * t5;
+}
+
+/* CORE/utils.jl:694 — collect(range(t0; stop=t1, length=nint+1)).  Julia's range is a
+ * twice-precision StepRangeLen, i.e. effectively correctly rounded; binary128 here. */
+void orc_mesh_uniform(double t0, double t1, int nint, double *mesh) {
+    const __float128 a = (__float128)t0, b = (__float128)t1;
+    for (int i = 0; i <= nint; i++)
+        mesh[i] = (double)(a + ((b - a) * (__float128)i) / (__float128)nint);
+    mesh[0] = t0;
+    mesh[nint] = t1;
+}
+
+/* CORE/utils.jl:119-121 — clamp(searchsortedfirst(mesh,t)-1, 1, N-1), returned 0-based. */
+int orc_interval(const double *mesh, int N, double t) {
+    int lo = 0, hi = N; /* first j with mesh[j] >= t */
+    while (lo < hi) {
+        int mid = (lo + hi) / 2;
+        if (mesh[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    int j = lo; /* == 1-based searchsortedfirst - 1 */
+    if (j < 1) j = 1;
+    if (j > N - 1) j = N - 1;
+    return j - 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* collocation residual  (MIRK/collocation.jl:44-72)                      */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_phi(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+             const double *y, double *Kd, double *phi) {
+    const int n = P->n, s = T->s;
+    double *tmp = (double *)malloc(sizeof(double) * n);
+    for (int i = 0; i < N - 1; i++) {
+        const double h = mesh[i + 1] - mesh[i];
+        const double *yi = y + (size_t)i * n, *yi1 = yi + n;
+        double *K = Kd + (size_t)i * s * n;
+        for (int r = 0; r < s; r++) {
+            for (int k = 0; k < n; k++) tmp[k] = (1.0 - T->v[r]) * yi[k] + T->v[r] * yi1[k];
+            /* __maybe_matmul!(tmp, K[:,1:r-1], x[r,1:r-1], h, 1): tmp += h * K_j * x_rj, j ascending */
+            for (int j = 0; j < r; j++)
+                for (int k = 0; k < n; k++) tmp[k] = h * K[j * n + k] * T->x[r][j] + tmp[k];
+            P->f(K + r * n, tmp, p, mesh[i] + T->c[r] * h, P->ctx);
+        }
+        double *res = phi + (size_t)i * n;
+        for (int k = 0; k < n; k++) res[k] = yi1[k] - yi[k];
+        for (int r = 0; r < s; r++)
+            for (int k = 0; k < n; k++) res[k] = -h * K[r * n + k] * T->b[r] + res[k];
+    }
+    free(tmp);
+}
+
+/* interpolation stages (MIRK/interpolation.jl:300-372; Appendix A.3) */
+void orc_interp_setup(const orc_problem *P, const orc_tableau *T, const double *p, int N,
+                      const double *mesh, const double *y, const double *Kd, double *Ki) {
+    const int n = P->n, s = T->s, si = T->s_star - T->s;
+    double *tmp = (double *)malloc(sizeof(double) * n);
+    for (int i = 0; i < N - 1; i++) {
+        const double h = mesh[i + 1] - mesh[i];
+        const double *yi = y + (size_t)i * n, *yi1 = yi + n;
+        const double *K = Kd + (size_t)i * s * n;
+        double *KI = Ki + (size_t)i * si * n;
+        for (int r = 0; r < si; r++) {
+            for (int k = 0; k < n; k++) tmp[k] = 0.0;
+            for (int j = 0; j < s; j++)
+                for (int k = 0; k < n; k++) tmp[k] += K[j * n + k] * T->x_star[r][j];
+            for (int j = 0; j < r; j++)
+                for (int k = 0; k < n; k++) tmp[k] += KI[j * n + k] * T->x_star[r][s + j];
+            for (int k = 0; k < n; k++)
+                tmp[k] = tmp[k] * h + (1.0 - T->v_star[r]) * yi[k] + T->v_star[r] * yi1[k];
+            P->f(KI + r * n, tmp, p, mesh[i] + T->c_star[r] * h, P->ctx);
+        }
+    }
+    free(tmp);
+}
+
+/* continuous extension (MIRK/interpolation.jl:98-126 for sol(t), :214-242 for the BC-time EvalSol;
+ * Appendix A.4).  bc_shortcut=1 reproduces EvalSol's endpoint short-circuit (:218-219). */
+void orc_eval_sol(const orc_problem *P, const orc_tableau *T, int N, const double *mesh,
+                  const double *y, const double *Kd, const double *Ki, double t, int deriv,
+                  int bc_shortcut, double *out) {
+    const int n = P->n, s = T->s, si = T->s_star - T->s;
+    if (bc_shortcut && deriv == 0) {
+        if (t == mesh[0]) { memcpy(out, y, sizeof(double) * n); return; }
+        if (t == mesh[N - 1]) { memcpy(out, y + (size_t)(N - 1) * n, sizeof(double) * n); return; }
+    }
+    const int i = orc_interval(mesh, N, t);
+    const double dt = mesh[i + 1] - mesh[i];
+    const double tau = (t - mesh[i]) / dt;
+    double w[ORC_MAX_SS], wp[ORC_MAX_SS];
+    orc_interp_weights(T->order, tau, w, wp);
+    const double *ww = deriv ? wp : w;
+    const double *K = Kd + (size_t)i * s * n, *KI = Ki + (size_t)i * si * n;
+    for (int k = 0; k < n; k++) out[k] = 0.0;
+    for (int r = 0; r < s; r++)
+        for (int k = 0; k < n; k++) out[k] += K[r * n + k] * ww[r];
+    for (int r = 0; r < si; r++)
+        for (int k = 0; k < n; k++) out[k] += KI[r * n + k] * ww[s + r];
+    if (!deriv)
+        for (int k = 0; k < n; k++) out[k] = out[k] * dt + y[(size_t)i * n + k];
+}
+
+/* gather U[k] = sol(times[k]) for the boundary condition */
+static int bc_gather(const orc_problem *P, const orc_tableau *T, const double *p, int N,
+                     const double *mesh, const double *y, const double *Kd, const double *Ki,
+                     double *times, double *U) {
+    const int n = P->n;
+    if (P->problem_type == 1) { /* TwoPoint: bca(res_a, y_1, p), bcb(res_b, y_N, p) CORE/utils.jl:157-199 */
+        memcpy(U, y, sizeof(double) * n);
+        memcpy(U + n, y + (size_t)(N - 1) * n, sizeof(double) * n);
+        times[0] = mesh[0];
+        times[1] = mesh[N - 1];
+        return 2;
+    }
+    const int m = P->bc_times(times, p, mesh[0], mesh[N - 1], P->ctx);
+    for (int k = 0; k < m; k++) orc_eval_sol(P, T, N, mesh, y, Kd, Ki, times[k], 0, 1, U + k * n);
+    return m;
+}
+
+/* full residual (MIRK/mirk.jl:471-534).  Standard: [bc; Phi_1..Phi_{N-1}] and interp_setup! on
+ * every call (quirk Q7, interpolation.jl:382-403); TwoPoint: [bc_a; Phi...; bc_b]
+ * (CORE/utils.jl:42-52). */
+void orc_loss(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+              const double *y, double *Kd, double *Ki, double *resid) {
+    const int n = P->n, L = P->n_bc;
+    double times[ORC_MAX_BC_PTS];
+    double *U = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * n);
+    double *bc = (double *)malloc(sizeof(double) * L);
+    if (P->problem_type == 0) {
+        orc_phi(P, T, p, N, mesh, y, Kd, resid + L);
+        orc_interp_setup(P, T, p, N, mesh, y, Kd, Ki);
+        bc_gather(P, T, p, N, mesh, y, Kd, Ki, times, U);
+        P->bc(bc, U, p, P->ctx);
+        memcpy(resid, bc, sizeof(double) * L);
+    } else {
+        const int La = P->n_bca;
+        orc_phi(P, T, p, N, mesh, y, Kd, resid + La);
+        bc_gather(P, T, p, N, mesh, y, Kd, Ki, times, U);
+        P->bc(bc, U, p, P->ctx);
+        memcpy(resid, bc, sizeof(double) * La);
+        memcpy(resid + La + (size_t)(N - 1) * n, bc + La, sizeof(double) * (L - La));
+    }
+    free(U);
+    free(bc);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* exact block Jacobian  (what sparse ForwardDiff of loss_collocation yields when the pattern  */
+/* is wide enough: MIRK/mirk.jl:810-838; Appendix A.2)                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+static void matmul_nn(int n, const double *A, const double *B, double *C) { /* C = A*B row-major */
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < n; k++) acc += A[i * n + k] * B[k * n + j];
+            C[i * n + j] = acc;
+        }
+}
+
+void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p, int N,
+                    const double *mesh, const double *y, double *Lb, double *Rb) {
+    const int n = P->n, s = T->s, nn = n * n;
+    double *tmp = (double *)malloc(sizeof(double) * n);
+    double *K = (double *)malloc(sizeof(double) * s * n);
+    double *J = (double *)malloc(sizeof(double) * nn);
+    double *M = (double *)malloc(sizeof(double) * nn);
+    double *A = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_i     */
+    double *B = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_{i+1} */
+    for (int i = 0; i < N - 1; i++) {
+        const double h = mesh[i + 1] - mesh[i];
+        const double *yi = y + (size_t)i * n, *yi1 = yi + n;
+        for (int r = 0; r < s; r++) {
+            for (int k = 0; k < n; k++) tmp[k] = (1.0 - T->v[r]) * yi[k] + T->v[r] * yi1[k];
+            for (int j = 0; j < r; j++)
+                for (int k = 0; k < n; k++) tmp[k] = h * K[j * n + k] * T->x[r][j] + tmp[k];
+            const double tt = mesh[i] + T->c[r] * h;
+            P->f(K + r * n, tmp, p, tt, P->ctx);
+            P->dfdu(J, tmp, p, tt, P->ctx);
+            /* A_r = J_r [(1-v_r) I + h sum_j x_rj A_j] */
+            for (int e = 0; e < nn; e++) M[e] = 0.0;
+            for (int k = 0; k < n; k++) M[k * n + k] = 1.0 - T->v[r];
+            for (int j = 0; j < r; j++)
+                if (T->x[r][j] != 0.0)
+                    for (int e = 0; e < nn; e++) M[e] += h * T->x[r][j] * A[j * nn + e];
+            matmul_nn(n, J, M, A + r * nn);
+            /* B_r = J_r [v_r I + h sum_j x_rj B_j] */
+            for (int e = 0; e < nn; e++) M[e] = 0.0;
+            for (int k = 0; k < n; k++) M[k * n + k] = T->v[r];
+            for (int j = 0; j < r; j++)
+                if (T->x[r][j] != 0.0)
+                    for (int e = 0; e < nn; e++) M[e] += h * T->x[r][j] * B[j * nn + e];
+            matmul_nn(n, J, M, B + r * nn);
+        }
+        double *Li = Lb + (size_t)i * nn, *Ri = Rb + (size_t)i * nn;
+        for (int e = 0; e < nn; e++) { Li[e] = 0.0; Ri[e] = 0.0; }
+        for (int k = 0; k < n; k++) { Li[k * n + k] = -1.0; Ri[k * n + k] = 1.0; }
+        for (int r = 0; r < s; r++)
+            for (int e = 0; e < nn; e++) {
+                Li[e] -= h * T->b[r] * A[r * nn + e];
+                Ri[e] -= h * T->b[r] * B[r * nn + e];
+            }
+    }
+    free(tmp); free(K); free(J); free(M); free(A); free(B);
+}
+
+/* BC Jacobian in the reference's pattern (quirk Q2): the interpolant inside loss_bc reads the
+ * Float64 stage buffers (MIRK/interpolation.jl:227), so d bc / d y lands only on the LEFT node of
+ * the interval that contains the evaluation time (identity through `z .* dt .+ u[ii]`, :239);
+ * endpoints short-circuit to y_1 / y_N (:218-219).  Returns m; nodes[k] is 0-based; B is
+ * m blocks of L×n row-major. */
+int orc_bc_jac(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+               const double *y, const double *Kd, const double *Ki, int *nodes, double *B) {
+    const int n = P->n, L = P->n_bc;
+    double times[ORC_MAX_BC_PTS];
+    double *U = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * n);
+    const int m = bc_gather(P, T, p, N, mesh, y, Kd, Ki, times, U);
+    double *d = (double *)malloc(sizeof(double) * L * m * n);
+    P->dbc(d, U, p, P->ctx);
+    for (int k = 0; k < m; k++) {
+        if (times[k] == mesh[0]) nodes[k] = 0;
+        else if (times[k] == mesh[N - 1]) nodes[k] = N - 1;
+        else nodes[k] = orc_interval(mesh, N, times[k]);
+        for (int r = 0; r < L; r++)
+            for (int c = 0; c < n; c++) B[((size_t)k * L + r) * n + c] = d[(size_t)r * m * n + k * n + c];
+    }
+    free(U);
+    free(d);
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* almost-block-diagonal solve: sequential row-pivoted LU with carried boundary rows           */
+/* (stands in for LinearSolve on AlmostBandedMatrix / BandedMatrix gbtrf; call site            */
+/* CORE/default_internal_solve.jl:107-110 -> NonlinearSolve)                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+int orc_abd_solve(int n, int N, int L, const double *Lb, const double *Rb, int m, const int *nodes,
+                  const double *B, const double *rhs_bc, const double *rhs_phi, double *delta) {
+    if (L != n) return -1;
+    /* unique sorted pinned nodes with accumulated blocks */
+    int Q = 0;
+    int *pn = (int *)malloc(sizeof(int) * (m > 0 ? m : 1));
+    for (int k = 0; k < m; k++) {
+        int found = 0;
+        for (int q = 0; q < Q; q++) if (pn[q] == nodes[k]) found = 1;
+        if (!found) pn[Q++] = nodes[k];
+    }
+    for (int a = 0; a < Q; a++)
+        for (int b = a + 1; b < Q; b++)
+            if (pn[b] < pn[a]) { int t = pn[a]; pn[a] = pn[b]; pn[b] = t; }
+    const int W = Q * n;            /* tail width */
+    const int RW = 2 * n + W + 1;   /* row width: cur | nxt | tail | rhs */
+    const int RA = L + n;           /* active rows */
+    double *act = (double *)calloc((size_t)RA * RW, sizeof(double));
+    double *piv = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n * RW);
+    int *slot_of = (int *)malloc(sizeof(int) * N);
+    for (int i = 0; i < N; i++) slot_of[i] = -1;
+    for (int q = 0; q < Q; q++) slot_of[pn[q]] = q;
+    int status = 0;
+
+    for (int r = 0; r < L; r++) {
+        double *row = act + (size_t)r * RW;
+        for (int k = 0; k < m; k++) {
+            const int q = slot_of[nodes[k]];
+            for (int c = 0; c < n; c++) row[2 * n + q * n + c] += B[((size_t)k * L + r) * n + c];
+        }
+        row[RW - 1] = rhs_bc[r];
+    }
+    for (int k = 0; k < N - 1 && !status; k++) {
+        if (slot_of[k] >= 0) {
+            const int q = slot_of[k];
+            for (int r = 0; r < L; r++) {
+                double *row = act + (size_t)r * RW;
+                for (int c = 0; c < n; c++) { row[c] += row[2 * n + q * n + c]; row[2 * n + q * n + c] = 0.0; }
+            }
+        }
+        for (int r = 0; r < n; r++) {
+            double *row = act + (size_t)(L + r) * RW;
+            memset(row, 0, sizeof(double) * RW);
+            for (int c = 0; c < n; c++) {
+                row[c] = Lb[((size_t)k * n + r) * n + c];
+                row[n + c] = Rb[((size_t)k * n + r) * n + c];
+            }
+            row[RW - 1] = rhs_phi[(size_t)k * n + r];
+        }
+        for (int j = 0; j < n; j++) {
+            int pr = j;
+            double best = fabs(act[(size_t)j * RW + j]);
+            for (int r = j + 1; r < RA; r++) {
+                const double a = fabs(act[(size_t)r * RW + j]);
+                if (a > best) { best = a; pr = r; }
+            }
+            if (!(best > 0.0) || !isfinite(best)) { status = 1; break; }
+            if (pr != j)
+                for (int c = 0; c < RW; c++) {
+                    const double t = act[(size_t)j * RW + c];
+                    act[(size_t)j * RW + c] = act[(size_t)pr * RW + c];
+                    act[(size_t)pr * RW + c] = t;
+                }
+            const double *prow = act + (size_t)j * RW;
+            for (int r = j + 1; r < RA; r++) {
+                double *row = act + (size_t)r * RW;
+                const double f = row[j] / prow[j];
+                if (f != 0.0) {
+                    row[j] = 0.0;
+                    for (int c = j + 1; c < RW; c++) row[c] -= f * prow[c];
+                }
+            }
+        }
+        if (status) break;
+        memcpy(piv + (size_t)k * n * RW, act, sizeof(double) * (size_t)n * RW);
+        for (int r = 0; r < L; r++) {
+            double *dst = act + (size_t)r * RW;
+            const double *src = act + (size_t)(n + r) * RW;
+            for (int c = 0; c < n; c++) { dst[c] = src[n + c]; dst[n + c] = 0.0; }
+            for (int c = 2 * n; c < RW; c++) dst[c] = src[c];
+        }
+    }
+    if (!status) {
+        const int k = N - 1;
+        if (slot_of[k] >= 0) {
+            const int q = slot_of[k];
+            for (int r = 0; r < L; r++) {
+                double *row = act + (size_t)r * RW;
+                for (int c = 0; c < n; c++) { row[c] += row[2 * n + q * n + c]; row[2 * n + q * n + c] = 0.0; }
+            }
+        }
+        for (int j = 0; j < n && !status; j++) {
+            int pr = j;
+            double best = fabs(act[(size_t)j * RW + j]);
+            for (int r = j + 1; r < L; r++) {
+                const double a = fabs(act[(size_t)r * RW + j]);
+                if (a > best) { best = a; pr = r; }
+            }
+            if (!(best > 0.0) || !isfinite(best)) { status = 1; break; }
+            if (pr != j)
+                for (int c = 0; c < RW; c++) {
+                    const double t = act[(size_t)j * RW + c];
+                    act[(size_t)j * RW + c] = act[(size_t)pr * RW + c];
+                    act[(size_t)pr * RW + c] = t;
+                }
+            const double *prow = act + (size_t)j * RW;
+            for (int r = j + 1; r < L; r++) {
+                double *row = act + (size_t)r * RW;
+                const double f = row[j] / prow[j];
+                row[j] = 0.0;
+                for (int c = j + 1; c < RW; c++) row[c] -= f * prow[c];
+            }
+        }
+        if (!status) {
+            double *dk = delta + (size_t)k * n;
+            for (int j = n - 1; j >= 0; j--) {
+                const double *row = act + (size_t)j * RW;
+                double acc = row[RW - 1];
+                for (int c = j + 1; c < n; c++) acc -= row[c] * dk[c];
+                dk[j] = acc / row[j];
+            }
+            for (int kk = N - 2; kk >= 0; kk--) {
+                double *d = delta + (size_t)kk * n;
+                const double *dn = d + n;
+                for (int j = n - 1; j >= 0; j--) {
+                    const double *row = piv + ((size_t)kk * n + j) * RW;
+                    double acc = row[RW - 1];
+                    for (int c = 0; c < n; c++) acc -= row[n + c] * dn[c];
+                    for (int q = 0; q < Q; q++)
+                        if (pn[q] > kk)
+                            for (int c = 0; c < n; c++)
+                                acc -= row[2 * n + q * n + c] * delta[(size_t)pn[q] * n + c];
+                    for (int c = j + 1; c < n; c++) acc -= row[c] * d[c];
+                    d[j] = acc / row[j];
+                }
+            }
+        }
+    }
+    free(pn); free(act); free(piv); free(slot_of);
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Newton-Raphson (NonlinearSolveFirstOrder NewtonRaphson, no line search; restated from its   */
+/* published algorithm: J(u) d = F(u); u <- u - d; stop when |F(u)|_inf <= abstol; non-finite   */
+/* norm => Unstable; the best iterate is what is returned (AbsNormSafeBest)).                   */
+/* ------------------------------------------------------------------------------------------ */
+
+static double norm_inf(const double *x, size_t len) {
+    double m = 0.0;
+    for (size_t i = 0; i < len; i++) {
+        const double a = fabs(x[i]);
+        if (!(a <= m)) m = a; /* propagates NaN */
+    }
+    return m;
+}
+
+int orc_newton(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+               double *y, double *Kd, double *Ki, double abstol, int maxiters, double *resid_norm,
+               int *iters) {
+    const int n = P->n, L = P->n_bc;
+    const size_t nu = (size_t)N * n, nr = (size_t)L + (size_t)(N - 1) * n;
+    double *fu = (double *)malloc(sizeof(double) * nr);
+    double *Lb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n * n);
+    double *Rb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n * n);
+    double *B = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * L * n);
+    double *delta = (double *)malloc(sizeof(double) * nu);
+    double *ybest = (double *)malloc(sizeof(double) * nu);
+    double *rhs_bc = (double *)malloc(sizeof(double) * L);
+    int nodes[ORC_MAX_BC_PTS];
+    int ret = ORC_MAXITERS, it = 0;
+    double best = INFINITY;
+    memcpy(ybest, y, sizeof(double) * nu);
+
+    orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
+    double nrm = norm_inf(fu, nr);
+    for (; it < maxiters;) {
+        orc_jac_blocks(P, T, p, N, mesh, y, Lb, Rb);
+        const int m = orc_bc_jac(P, T, p, N, mesh, y, Kd, Ki, nodes, B);
+        const double *rphi;
+        if (P->problem_type == 0) {
+            memcpy(rhs_bc, fu, sizeof(double) * L);
+            rphi = fu + L;
+        } else {
+            const int La = P->n_bca;
+            memcpy(rhs_bc, fu, sizeof(double) * La);
+            memcpy(rhs_bc + La, fu + La + (size_t)(N - 1) * n, sizeof(double) * (L - La));
+            rphi = fu + La;
+        }
+        if (orc_abd_solve(n, N, L, Lb, Rb, m, nodes, B, rhs_bc, rphi, delta)) { ret = ORC_FAILURE; break; }
+        for (size_t i = 0; i < nu; i++) y[i] -= delta[i];
+        it++;
+        orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
+        nrm = norm_inf(fu, nr);
+        if (!isfinite(nrm)) { ret = ORC_UNSTABLE; break; }
+        if (nrm < best) { best = nrm; memcpy(ybest, y, sizeof(double) * nu); }
+        if (nrm <= abstol) { ret = ORC_SUCCESS; break; }
+    }
+    if (ret != ORC_SUCCESS && it > 0 && isfinite(best)) {
+        /* SafeBest: hand back the best iterate seen and stages consistent with it */
+        memcpy(y, ybest, sizeof(double) * nu);
+        orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
+        nrm = norm_inf(fu, nr);
+    }
+    *resid_norm = nrm;
+    *iters = it;
+    free(fu); free(Lb); free(Rb); free(B); free(delta); free(ybest); free(rhs_bc);
+    return ret;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* defect estimate (MIRK/adaptivity.jl:370-415; Appendix A.5)                                  */
+/* ------------------------------------------------------------------------------------------ */
+
+double orc_defect(const orc_problem *P, const orc_tableau *T, const double *p, int N,
+                  const double *mesh, const double *y, const double *Kd, double *Ki, double *errors) {
+    const int n = P->n, s = T->s, si = T->s_star - T->s;
+    double w1[ORC_MAX_SS], w1p[ORC_MAX_SS], w2[ORC_MAX_SS], w2p[ORC_MAX_SS];
+    orc_interp_weights(T->order, T->tau_star, w1, w1p);
+    orc_interp_weights(T->order, 1.0 - T->tau_star, w2, w2p);
+    orc_interp_setup(P, T, p, N, mesh, y, Kd, Ki);
+    double *z = (double *)malloc(sizeof(double) * n), *zp = (double *)malloc(sizeof(double) * n);
+    double *d1 = (double *)malloc(sizeof(double) * n), *d2 = (double *)malloc(sizeof(double) * n);
+    double defect = 0.0;
+    for (int i = 0; i < N - 1; i++) {
+        const double dt = mesh[i + 1] - mesh[i];
+        const double *K = Kd + (size_t)i * s * n, *KI = Ki + (size_t)i * si * n;
+        double est[2];
+        for (int smp = 0; smp < 2; smp++) {
+            const double *w = smp ? w2 : w1, *wp = smp ? w2p : w1p;
+            double *d = smp ? d2 : d1;
+            for (int k = 0; k < n; k++) { z[k] = 0.0; zp[k] = 0.0; }
+            for (int r = 0; r < s; r++) for (int k = 0; k < n; k++) z[k] += K[r * n + k] * w[r];
+            for (int r = 0; r < si; r++) for (int k = 0; k < n; k++) z[k] += KI[r * n + k] * w[s + r];
+            for (int r = 0; r < s; r++) for (int k = 0; k < n; k++) zp[k] += K[r * n + k] * wp[r];
+            for (int r = 0; r < si; r++) for (int k = 0; k < n; k++) zp[k] += KI[r * n + k] * wp[s + r];
+            for (int k = 0; k < n; k++) z[k] = z[k] * dt + y[(size_t)i * n + k];
+            const double tau = smp ? (1.0 - T->tau_star) : T->tau_star;
+            P->f(d, z, p, mesh[i] + tau * dt, P->ctx);
+            double e = 0.0;
+            for (int k = 0; k < n; k++) {
+                d[k] = (zp[k] - d[k]) / (fabs(d[k]) + 1.0);
+                if (fabs(d[k]) > e) e = fabs(d[k]);
+            }
+            est[smp] = e;
+        }
+        const double *pick = est[0] > est[1] ? d1 : d2;
+        for (int k = 0; k < n; k++) {
+            errors[(size_t)i * n + k] = pick[k];
+            if (fabs(pick[k]) > defect) defect = fabs(pick[k]);
+            if (isnan(pick[k])) defect = NAN;
+        }
+    }
+    free(z); free(zp); free(d1); free(d2);
+    return defect;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* mesh selection (MIRK/adaptivity.jl:23-75, redistribute! :250-278, half_mesh! :287-304;       */
+/* Appendix A.6).  Returns ORC_SUCCESS / ORC_FAILURE; mesh_new must hold 4*(N-1)+1 doubles.     */
+/* ------------------------------------------------------------------------------------------ */
+
+int orc_mesh_select(int order, int n, int N, const double *mesh, const double *errors, double abstol,
+                    int max_num_subintervals, int *N_new, double *mesh_new) {
+    const int ni = N - 1;
+    double *sh = (double *)malloc(sizeof(double) * ni);
+    double r1 = 0.0, r2 = 0.0;
+    for (int i = 0; i < ni; i++) {
+        double e = 0.0;
+        for (int k = 0; k < n; k++) if (fabs(errors[(size_t)i * n + k]) > e) e = fabs(errors[(size_t)i * n + k]);
+        sh[i] = pow(e / abstol, 1.0 / (order + 1));
+        if (sh[i] > r1) r1 = sh[i];
+        r2 += sh[i];
+    }
+    const double r3 = r2 / ni;
+    long n_predict = (long)nearbyint(1.3 * r2 + 1.0); /* round(Int, .) is half-to-even */
+    const double n_ = 0.1 * ni;
+    if (fabs((double)(n_predict - ni)) < n_) n_predict = (long)nearbyint(ni + n_);
+    int info = ORC_SUCCESS;
+    if (r1 <= 1.0 * r3) { /* rho = 1.0 */
+        const int ns = 2 * ni;
+        if (ns > max_num_subintervals) {
+            info = ORC_FAILURE;
+            *N_new = N;
+            memcpy(mesh_new, mesh, sizeof(double) * N);
+        } else {
+            *N_new = ns + 1;
+            for (int i = 0; i < ni; i++) {
+                mesh_new[2 * i] = mesh[i];
+                mesh_new[2 * i + 1] = (mesh[i + 1] + mesh[i]) / 2.0;
+            }
+            mesh_new[2 * ni] = mesh[ni];
+        }
+    } else {
+        long lb = N / 2, ub = 4L * ni;
+        long ns = n_predict < lb ? lb : (n_predict > ub ? ub : n_predict);
+        if (ns > max_num_subintervals) {
+            info = ORC_FAILURE;
+            *N_new = N;
+            memcpy(mesh_new, mesh, sizeof(double) * N);
+        } else {
+            for (int i = 0; i < ni; i++) sh[i] /= (mesh[i + 1] - mesh[i]);
+            double tot = 0.0;
+            for (int i = 0; i < ni; i++) tot += sh[i] * (mesh[i + 1] - mesh[i]);
+            const double zeta = tot / (double)ns;
+            /* resize!(cache.mesh, ns+1) keeps the leading old entries; new tail entries are
+             * uninitialised in Julia, here they default to t_end */
+            for (long i = 0; i <= ns; i++) mesh_new[i] = (i < N) ? mesh[i] : mesh[ni];
+            int k = 0;
+            long i = 0;
+            mesh_new[0] = mesh[0];
+            double t = mesh[0], integral = 0.0;
+            while (k < ni) {
+                const double next_piece = sh[k] * (mesh[k + 1] - t);
+                const double int_next = integral + next_piece;
+                if (int_next > zeta) {
+                    const double tn = (zeta - integral) / sh[k] + t;
+                    if (i + 1 <= ns) mesh_new[i + 1] = tn;
+                    t = tn;
+                    i++;
+                    integral = 0.0;
+                } else {
+                    integral = int_next;
+                    t = mesh[k + 1];
+                    k++;
+                }
+            }
+            mesh_new[ns] = mesh[ni];
+            *N_new = (int)ns + 1;
+        }
+    }
+    free(sh);
+    return info;
+}
+
+/* new guess on the new mesh (MIRK/mirk.jl:364-372, adaptivity.jl:6-13,590-621; Appendix A.7).
+ * inplace_quirk=1 reproduces Q3: sum_stages! adds `cache.y0.u[i_old]`, the array being rewritten. */
+void orc_reinterp(const orc_problem *P, const orc_tableau *T, int N_old, const double *mesh_old,
+                  const double *y_old, const double *Kd, const double *Ki, int N_new,
+                  const double *mesh_new, double *y_new, int inplace_quirk) {
+    const int n = P->n, s = T->s, si = T->s_star - T->s;
+    const int NB = N_old > N_new ? N_old : N_new;
+    double *buf = (double *)calloc((size_t)NB * n, sizeof(double));
+    memcpy(buf, y_old, sizeof(double) * (size_t)N_old * n);
+    double w[ORC_MAX_SS], wp[ORC_MAX_SS];
+    for (int j = 0; j < N_new; j++) {
+        const double t = mesh_new[j];
+        const int i = orc_interval(mesh_old, N_old, t);
+        const double dt = mesh_old[i + 1] - mesh_old[i];
+        const double tau = (t - mesh_old[i]) / dt;
+        orc_interp_weights(T->order, tau, w, wp);
+        const double *K = Kd + (size_t)i * s * n, *KI = Ki + (size_t)i * si * n;
+        const double *base = inplace_quirk ? (buf + (size_t)i * n) : (y_old + (size_t)i * n);
+        for (int k = 0; k < n; k++) {
+            double acc = 0.0;
+            for (int r = 0; r < s; r++) acc += K[r * n + k] * w[r];
+            for (int r = 0; r < si; r++) acc += KI[r * n + k] * w[s + r];
+            y_new[(size_t)j * n + k] = acc * dt + base[k];
+        }
+        if (inplace_quirk) memcpy(buf + (size_t)j * n, y_new + (size_t)j * n, sizeof(double) * n);
+    }
+    free(buf);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* adaptive outer loop (MIRK/mirk.jl:286-388; Appendix A.8)                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+int orc_solve(const orc_problem *P, int order, const double *p, int N0, const double *mesh0,
+              const double *y0, const orc_options *opt, orc_result *out) {
+    orc_tableau T;
+    if (orc_tableau_get(order, &T)) return -1;
+    const int n = P->n, s = T.s, si = T.s_star - T.s;
+    int N = N0;
+    double *mesh = (double *)malloc(sizeof(double) * N);
+    double *y = (double *)malloc(sizeof(double) * (size_t)N * n);
+    memcpy(mesh, mesh0, sizeof(double) * N);
+    memcpy(y, y0, sizeof(double) * (size_t)N * n);
+    double *Kd = (double *)calloc((size_t)(N - 1) * s * n, sizeof(double));
+    double *Ki = (double *)calloc((size_t)(N - 1) * si * n, sizeof(double));
+    memset(out, 0, sizeof(*out));
+    int info = ORC_SUCCESS;
+    double error_norm = 2.0 * opt->abstol, resid_norm = 0.0;
+    do {
+        int iters = 0;
+        const int nret = orc_newton(P, &T, p, N, mesh, y, Kd, Ki, opt->abstol, opt->maxiters,
+                                    &resid_norm, &iters);
+        out->newton_iters += iters;
+        error_norm = 2.0 * opt->abstol;
+        info = nret;
+        const int h = out->n_hist < 64 ? out->n_hist : 63;
+        out->hist_N[h] = N;
+        out->hist_newton[h] = iters;
+        out->hist_defect[h] = NAN;
+        out->outer_iters++;
+        if (out->n_hist < 64) out->n_hist++;
+        if (!opt->adaptive) break;
+        if (info == ORC_SUCCESS) {
+            double *errors = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n);
+            error_norm = orc_defect(P, &T, p, N, mesh, y, Kd, Ki, errors);
+            out->hist_defect[h] = error_norm;
+            if (!(error_norm <= opt->defect_threshold)) info = ORC_FAILURE;
+            if (info == ORC_SUCCESS && error_norm > opt->abstol) {
+                int Nn = 0;
+                double *mesh_new = (double *)malloc(sizeof(double) * (4 * (size_t)(N - 1) + 1));
+                info = orc_mesh_select(order, n, N, mesh, errors, opt->abstol,
+                                       opt->max_num_subintervals, &Nn, mesh_new);
+                if (info == ORC_SUCCESS) {
+                    double *y_new = (double *)malloc(sizeof(double) * (size_t)Nn * n);
+                    orc_reinterp(P, &T, N, mesh, y, Kd, Ki, Nn, mesh_new, y_new, opt->reinterp_inplace);
+                    free(y); free(mesh); free(Kd); free(Ki);
+                    y = y_new; mesh = mesh_new; N = Nn;
+                    Kd = (double *)calloc((size_t)(N - 1) * s * n, sizeof(double));
+                    Ki = (double *)calloc((size_t)(N - 1) * si * n, sizeof(double));
+                } else {
+                    free(mesh_new);
+                }
+                free(errors);
+                continue;
+            }
+            free(errors);
+        }
+        if (info != ORC_SUCCESS) {
+            /* MIRK/mirk.jl:374-385: halve the mesh, ZERO the guess, force a restart (quirk Q4) */
+            if (2 * (N - 1) > opt->max_num_subintervals) {
+                info = ORC_FAILURE;
+            } else {
+                const int Nn = 2 * (N - 1) + 1;
+                double *mesh_new = (double *)malloc(sizeof(double) * Nn);
+                for (int i = 0; i < N - 1; i++) {
+                    mesh_new[2 * i] = mesh[i];
+                    mesh_new[2 * i + 1] = (mesh[i + 1] + mesh[i]) / 2.0;
+                }
+                mesh_new[Nn - 1] = mesh[N - 1];
+                free(mesh); free(y); free(Kd); free(Ki);
+                mesh = mesh_new; N = Nn;
+                y = (double *)calloc((size_t)N * n, sizeof(double));
+                Kd = (double *)calloc((size_t)(N - 1) * s * n, sizeof(double));
+                Ki = (double *)calloc((size_t)(N - 1) * si * n, sizeof(double));
+                info = ORC_SUCCESS;
+            }
+        }
+    } while (info == ORC_SUCCESS && error_norm > opt->abstol && out->outer_iters < opt->max_outer);
+    if (info == ORC_SUCCESS && opt->adaptive && error_norm > opt->abstol) info = ORC_MAXITERS;
+    out->N = N; out->mesh = mesh; out->y = y; out->Kd = Kd; out->Ki = Ki;
+    out->retcode = info; out->resid_norm = resid_norm; out->defect_norm = error_norm;
+    return 0;
+}
+
+void orc_result_free(orc_result *r) {
+    free(r->mesh); free(r->y); free(r->Kd); free(r->Ki);
+    r->mesh = r->y = r->Kd = r->Ki = NULL;
+}
+
+/* SciMLBase EnsembleProblem driver restated for the packed-parameter case
+ * (MIRK/test/Core/ensemble_tests.jl:20-38): prob_func only swaps p. */
+int orc_ensemble_solve(const orc_problem *P, int order, int ntraj, const double *p, const double *u0,
+                       double t0, double t1, int nint, const orc_options *opt, int nthreads,
+                       int *retcodes, int *N_final, double *y_first, int *newton_iters) {
+    const int n = P->n;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    for (int tr = 0; tr < ntraj; tr++) {
+        double *mesh = (double *)malloc(sizeof(double) * (nint + 1));
+        double *y = (double *)malloc(sizeof(double) * (size_t)(nint + 1) * n);
+        orc_mesh_uniform(t0, t1, nint, mesh);
+        for (int i = 0; i <= nint; i++) memcpy(y + (size_t)i * n, u0, sizeof(double) * n);
+        orc_result R;
+        orc_solve(P, order, p + (size_t)tr * P->n_p, nint + 1, mesh, y, opt, &R);
+        retcodes[tr] = R.retcode;
+        if (N_final) N_final[tr] = R.N;
+        if (y_first) memcpy(y_first + (size_t)tr * n, R.y, sizeof(double) * n);
+        if (newton_iters) newton_iters[tr] = R.newton_iters;
+        orc_result_free(&R);
+        free(mesh); free(y);
+    }
+    return 0;
+}
