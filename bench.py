@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py — MIRK Newton steps/s on BASELINE config C2 (MIRK6, n = 16 states, 20 000 mesh nodes, FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one Newton step of the collocation system on the fixed C2 mesh: residual Phi + boundary
+rows, all (N-1) Jacobian blocks [L_i R_i] + boundary blocks, the almost-block-diagonal solve, the
+update y -= delta, and |F|_inf (unit of work M1).  Every step starts from the same
+stored guess so each does identical work.
+
+  value    device-resident throughput: K steps timed with CUDA events on the solver's stream
+  e2e      the same step through the C ABI with HOST buffers: mesh + guess copied host->device from
+           pinned memory, one Newton step, solution and |F|_inf copied back, every step
+  roofline the dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM copy peak
+  cpu_baseline  the CPU oracle (a restatement of the reference's algorithm; the Julia reference
+           cannot run in this image) timed on this box's host cores, 1 thread like the reference
+
+N > 1 (torchrun, one rank per GPU): the Newton path of ONE problem this size does not need more than
+one GPU, so ranks run independent C2 problems (an ensemble of large BVPs: independent units, no
+data-path collective), weak scaling; the timed region is bracketed by barriers and the slowest rank
+counts.  `--impl reference` runs the CPU oracle on rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mirk_newton_steps_per_sec"
+UNIT = "newton_steps/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_steps(cfg, steps):
+    """K Newton steps of the CPU oracle on the full C2 problem (abstol = 0 so it never stops early)."""
+    from oracle import oracle as O
+    ws = O.Workspace(O.builtin(cfg.problem), cfg.order, cfg.p, cfg.mesh, cfg.y0)
+    t = time.perf_counter()
+    ret, it, nrm = ws.newton(abstol=0.0, maxiters=steps)
+    dt = time.perf_counter() - t
+    return it, dt, nrm
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.warmup > 0:
+        cpu_steps(cfg, min(args.warmup, 2))
+    it, dt, nrm = cpu_steps(cfg, args.steps)
+    value = it / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / it, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(cfg, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{it} full-size Newton steps (oracle/mirk_oracle.c orc_newton; the reference's "
+                                   "hot path is single-threaded and Julia is absent from this image)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(cfg, n_gpus):
+    return {"workload": f"C2: {cfg.desc}; Newton step = residual + ABD Jacobian + block-cyclic-reduction solve + update",
+            "problem": cfg.problem, "order": cfg.order, "n_states": cfg.n, "mesh_nodes": cfg.N,
+            "unknowns": cfg.N * cfg.n, "problems_per_gpu": 1, "parallelism": f"independent problems x{n_gpus}",
+            "l2_policy": "per-step working set (Jacobian blocks + elimination factors, ~4 x 82 MB) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nint", type=int, default=19999, help="mesh intervals (default: C2's 19 999)")
+    ap.add_argument("--chunk", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    import numpy as np
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import configs
+
+    cfg = configs.c2_chain8(args.nint)
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, N = cfg.n, cfg.N
+    mesh_pinned = torch.empty(N, dtype=torch.float64).pin_memory()
+    y_pinned = torch.empty(N, n, dtype=torch.float64).pin_memory()
+    out_t = torch.empty(N, dtype=torch.float64).pin_memory()
+    out_y = torch.empty(N, n, dtype=torch.float64).pin_memory()
+    mesh_pinned.numpy()[:] = cfg.mesh
+    y_pinned.numpy()[:] = cfg.y0
+
+    cache = M.init(M.BVProblem(cfg.problem, y_pinned.numpy(), cfg.tspan, p=cfg.p, mesh=mesh_pinned.numpy()),
+                   M.MIRK6(), adaptive=False, device=local, chunk=args.chunk)
+    # ---- device-resident timing ------------------------------------------------------------------
+    st, _, _, _ = cache.bench_newton_steps(args.warmup)
+    assert st == 0, "warm-up Newton step failed"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    st, total_ms, phases, launches = cache.bench_newton_steps(args.steps)
+    barrier()
+    assert st == 0
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    import ctypes as C
+    from boundaryvaluediffeq_jl_b200 import _lib as B
+    L = B.lib()
+    dptr = lambda tns: C.cast(tns.data_ptr(), B.dp)  # noqa: E731
+    nrm = C.c_double(0)
+
+    def e2e_step():
+        B.check(L.mirk_set_mesh_guess(cache._h, N, dptr(mesh_pinned), dptr(y_pinned)))
+        B.check(L.mirk_newton_step(cache._h, C.byref(nrm)))
+        B.check(L.mirk_get_solution(cache._h, dptr(out_t), dptr(out_y)))
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel -------------------------------------------------------
+        names = ["residual", "jacobian_blocks", "abd_reduce_level0", "abd_reduce_upper", "abd_closing_solve",
+                 "abd_backsub", "update"]
+        per_step_ms = [p / args.steps for p in phases[:7]]
+        k = int(np.argmax(per_step_ms))
+        nn, ni = n * n, N - 1
+        s = 5 if cfg.order == 6 else 3
+        alg_bytes = {
+            "residual": 8 * (n * N + N + (s + 1) * n * ni),
+            "jacobian_blocks": 8 * (n * N + N + 2 * nn * ni),
+            # reads L_i, R_i, Phi_i; writes the elimination factors of every eliminated node and the
+            # collapsed relations: together again (2 n^2 + n) doubles per interval
+            "abd_reduce_level0": 8 * 2 * (2 * nn + n) * ni,
+            "abd_reduce_upper": 8 * 2 * (2 * nn + n) * ni // 7,
+            "abd_closing_solve": 8 * (2 * nn + n) * 2,
+            "abd_backsub": 8 * ((2 * nn + n) * ni + n * N),
+            "update": 8 * 3 * n * N,
+        }
+        hbm_peak, peak_src = _peaks()
+        achieved = alg_bytes[names[k]] / (per_step_ms[k] * 1e-3) * 1e-9
+        step_bytes = 8 * (2 * n * N + N + 2 * 2 * nn * ni)  # B = 32 n^2 N + 16 n N
+        # ---- CPU baseline (bounded sample: a few full-size steps, ~1 s each) ---------------------------
+        cpu = None
+        if world == 1:
+            it, dt, _ = cpu_steps(cfg, 8)
+            cpu = {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{it} full-size C2 Newton steps of the CPU oracle (restatement of the reference "
+                             "algorithm, single thread like the reference's hot path; Julia is absent here)"}
+        fp64, hbm_live = C.c_double(0), C.c_double(0)
+        B.check(L.mirk_measure_peaks(local, C.byref(fp64), C.byref(hbm_live)))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(cfg, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (N + N * n),
+                    "d2h_bytes_per_step": 8 * (N + N * n) + 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": names[k], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes[names[k]], "kernel_ms": per_step_ms[k],
+                         "whole_step": {"algorithmic_bytes": step_bytes,
+                                        "achieved_gbs": step_bytes / (total_ms_max / args.steps * 1e-3) * 1e-9},
+                         "live_peaks": {"fp64_fma_tflops": fp64.value, "hbm_copy_gbs": hbm_live.value}},
+            "phases_ms_per_step": dict(zip(names, per_step_ms)),
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    cache.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

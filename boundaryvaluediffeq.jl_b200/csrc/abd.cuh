@@ -1,0 +1,248 @@
+// abd.cuh — parallel solve of the almost-block-diagonal Newton system
+//
+//     [ B_k ... (boundary rows, any pinned nodes) ] [d_1]   [bc ]
+//     [ L_1 R_1                                   ] [d_2] = [Phi]
+//     [     L_2 R_2  ...                          ] [ : ]
+//
+// The reference hands this matrix to LinearSolve (almost-banded QR / banded LU, one core;
+// call site lib/BoundaryValueDiffEqCore/src/default_internal_solve.jl:107-110).  Here it is a
+// stable block cyclic reduction in the style of Wright's structured elimination: a *relation*
+// Lc d_a + Rc d_b = rc couples two nodes; a group of consecutive relations is collapsed to one by
+// eliminating its interior nodes with row-pivoted Gauss-Jordan on the stacked 2n x n block
+// (pivoting between the two stacked halves is what keeps dichotomic problems stable); the
+// eliminated node c keeps   d_c = rt - TL d_a - TR d_right   for the back substitution.  Nodes the
+// boundary condition touches are never eliminated; the few that survive are closed with the
+// boundary rows in one small dense solve.
+//
+// This file holds the size-generic path (any n): working matrix in shared memory when
+// 2n(3n+1) doubles fit, otherwise in a global scratch slab.  The register-resident warp path for
+// n <= 16 is in abd_warp.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mirk {
+
+// warp argmax of (value, index); lower index wins ties
+__device__ __forceinline__ void warp_argmax(double& v, int& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+// Row-pivoted Gauss-Jordan on the first `ne` columns of W (rows x cols, pitch `ld`), restricted
+// to rows with elig[r] != 0; on return pivrow[q] is the row that owns unit column q.
+// All threads of the block call this.  Returns false (uniformly) on a zero / non-finite pivot.
+__device__ bool block_gauss_jordan(double* W, int rows, int cols, int ld, int ne, int* elig,
+                                   int* pivrow, double* mult, double* prow, int* s_p) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int q = 0; q < ne; q++) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = 0x7fffffff;
+            for (int r = tid; r < rows; r += 32) {
+                if (elig[r]) {
+                    const double a = fabs(W[(size_t)r * ld + q]);
+                    if (a > best || !(a == a)) { best = (a == a) ? a : INFINITY; bi = r; }
+                }
+            }
+            warp_argmax(best, bi);
+            if (tid == 0) *s_p = (best > 0.0 && best < INFINITY) ? bi : -1;
+        }
+        __syncthreads();
+        const int pr = *s_p;
+        if (pr < 0) return false;
+        const double inv = 1.0 / W[(size_t)pr * ld + q];
+        for (int r = tid; r < rows; r += T) mult[r] = W[(size_t)r * ld + q];
+        for (int c = q + tid; c < cols; c += T) prow[c] = W[(size_t)pr * ld + c] * inv;
+        __syncthreads();
+        const int nc = cols - q;  // columns q..cols-1
+        for (int e = tid; e < rows * nc; e += T) {
+            const int r = e / nc, c = q + e % nc;
+            double* w = &W[(size_t)r * ld + c];
+            if (r == pr) *w = prow[c];
+            else *w = (c == q) ? 0.0 : (*w - mult[r] * prow[c]);
+        }
+        if (tid == 0) { elig[pr] = 0; pivrow[q] = pr; }
+        __syncthreads();
+    }
+    return true;
+}
+
+// One level of the reduction.  Block g collapses relations [gs[g], gs[g+1]) of the input level.
+// Relation storage: L[k][n][n], R[k][n][n] row-major, r[k][n].  nodes[k], nodes[k+1] are the
+// global node ids relation k couples.
+__global__ void __launch_bounds__(256)
+k_reduce_generic(int n, const double* __restrict__ inL, const double* __restrict__ inR,
+                 const double* __restrict__ inr, double* __restrict__ outL, double* __restrict__ outR,
+                 double* __restrict__ outr, const int* __restrict__ nodes, const int* __restrict__ gs,
+                 double* __restrict__ TL, double* __restrict__ TR, double* __restrict__ rt,
+                 double* __restrict__ scratch, int use_smem, int* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int g = blockIdx.x, k0 = gs[g], k1 = gs[g + 1];
+    const int rows = 2 * n, cols = 3 * n + 1, ld = cols;
+    const size_t nn = (size_t)n * n;
+    if (k1 - k0 == 1) {  // nothing to eliminate: pass the relation through
+        for (int e = tid; e < (int)nn; e += T) {
+            outL[g * nn + e] = inL[k0 * nn + e];
+            outR[g * nn + e] = inR[k0 * nn + e];
+        }
+        for (int e = tid; e < n; e += T) outr[(size_t)g * n + e] = inr[(size_t)k0 * n + e];
+        return;
+    }
+    double* W = use_smem ? smem : scratch + (size_t)g * rows * ld;
+    double* mult = use_smem ? smem + (size_t)rows * ld : smem;
+    double* prow = mult + rows;
+    int* elig = (int*)(prow + cols);
+    int* pivrow = elig + rows;
+    int* rowlist = pivrow + n;   // rows that receive the next relation
+    int* s_p = rowlist + n;
+
+    // carried rows <- relation k0 :  [E | A | B | rhs] = [R | L | 0 | r]
+    for (int e = tid; e < n * cols; e += T) {
+        const int q = e / cols, c = e % cols;
+        double v;
+        if (c < n) v = inR[k0 * nn + (size_t)q * n + c];
+        else if (c < 2 * n) v = inL[k0 * nn + (size_t)q * n + (c - n)];
+        else if (c < 3 * n) v = 0.0;
+        else v = inr[(size_t)k0 * n + q];
+        W[(size_t)q * ld + c] = v;
+    }
+    for (int q = tid; q < n; q += T) rowlist[q] = n + q;
+    __syncthreads();
+    for (int j = k0 + 1; j < k1; j++) {
+        // incoming relation j into the free rows: [E | A | B | rhs] = [L | 0 | R | r]
+        for (int e = tid; e < n * cols; e += T) {
+            const int q = e / cols, c = e % cols;
+            double v;
+            if (c < n) v = inL[j * nn + (size_t)q * n + c];
+            else if (c < 2 * n) v = 0.0;
+            else if (c < 3 * n) v = inR[j * nn + (size_t)q * n + (c - 2 * n)];
+            else v = inr[(size_t)j * n + q];
+            W[(size_t)rowlist[q] * ld + c] = v;
+        }
+        for (int r = tid; r < rows; r += T) elig[r] = 1;
+        __syncthreads();
+        if (!block_gauss_jordan(W, rows, cols, ld, n, elig, pivrow, mult, prow, s_p)) {
+            if (tid == 0) atomicExch(status, 1);
+            return;
+        }
+        // factors of the eliminated node: d_c = rt - TL d_a - TR d_right
+        const int c_node = nodes[j];
+        for (int e = tid; e < (int)nn; e += T) {
+            const int q = e / n, c = e % n;
+            const double* row = W + (size_t)pivrow[q] * ld;
+            TL[(size_t)c_node * nn + e] = row[n + c];
+            TR[(size_t)c_node * nn + e] = row[2 * n + c];
+        }
+        for (int q = tid; q < n; q += T) rt[(size_t)c_node * n + q] = W[(size_t)pivrow[q] * ld + 3 * n];
+        __syncthreads();
+        // survivors: E <- B, B <- 0 ; pivot rows become the free rows of the next merge
+        for (int e = tid; e < rows * n; e += T) {
+            const int r = e / n, c = e % n;
+            if (elig[r]) {
+                W[(size_t)r * ld + c] = W[(size_t)r * ld + 2 * n + c];
+                W[(size_t)r * ld + 2 * n + c] = 0.0;
+            }
+        }
+        for (int q = tid; q < n; q += T) rowlist[q] = pivrow[q];
+        __syncthreads();
+    }
+    // emit the collapsed relation from the n surviving rows (rows not in rowlist)
+    if (tid == 0) {
+        for (int r = 0; r < rows; r++) elig[r] = 1;
+        for (int q = 0; q < n; q++) elig[rowlist[q]] = 0;
+        int cnt = 0;
+        for (int r = 0; r < rows; r++) if (elig[r]) pivrow[cnt++] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < (int)nn; e += T) {
+        const int q = e / n, c = e % n;
+        const double* row = W + (size_t)pivrow[q] * ld;
+        outR[g * nn + e] = row[c];
+        outL[g * nn + e] = row[n + c];
+    }
+    for (int q = tid; q < n; q += T) outr[(size_t)g * n + q] = W[(size_t)pivrow[q] * ld + 3 * n];
+}
+
+// Back substitution of one level: block g recovers the interior nodes of its group right to left.
+__global__ void __launch_bounds__(256)
+k_backsub_generic(int n, const int* __restrict__ nodes, const int* __restrict__ gs,
+                  const double* __restrict__ TL, const double* __restrict__ TR,
+                  const double* __restrict__ rt, double* __restrict__ delta) {
+    const int g = blockIdx.x, k0 = gs[g], k1 = gs[g + 1];
+    if (k1 - k0 == 1) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const size_t nn = (size_t)n * n;
+    const double* da = delta + (size_t)nodes[k0] * n;
+    for (int j = k1 - 1; j > k0; j--) {
+        const int c = nodes[j];
+        const double* dr = delta + (size_t)nodes[j + 1] * n;
+        for (int q = warp; q < n; q += nw) {
+            const double* tl = TL + (size_t)c * nn + (size_t)q * n;
+            const double* tr = TR + (size_t)c * nn + (size_t)q * n;
+            double acc = 0.0;
+            for (int k = lane; k < n; k += 32) acc += tl[k] * da[k] + tr[k] * dr[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) delta[(size_t)c * n + q] = rt[(size_t)c * n + q] - acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Closing solve on the surviving nodes kept[0..Q): Q-1 relations + L boundary rows, dense
+// Gauss-Jordan with row pivoting in a global scratch matrix M (D x (D+1), D = Q n).  One block.
+__global__ void __launch_bounds__(1024)
+k_final_solve(int n, int Q, const int* __restrict__ kept, const double* __restrict__ relL,
+              const double* __restrict__ relR, const double* __restrict__ relr, int L, int La,
+              const int* __restrict__ m_ptr, const int* __restrict__ bc_nodes,
+              const double* __restrict__ Bc, const double* __restrict__ resid, size_t tail_off,
+              double* M, double* __restrict__ delta, int* __restrict__ status) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int D = Q * n, cols = D + 1, ld = cols;
+    const size_t nn = (size_t)n * n;
+    double* mult = smem;
+    double* prow = mult + D;
+    int* elig = (int*)(prow + cols);
+    int* pivrow = elig + D;
+    int* s_p = pivrow + D;
+    if (!M) M = (double*)(s_p + 4);  // the closing matrix fits in shared memory
+    for (int e = tid; e < D * cols; e += T) M[e] = 0.0;
+    __syncthreads();
+    // boundary rows first (the reference's row order), accumulated per pinned node
+    const int m = *m_ptr;
+    if (tid < L) {
+        const int q = tid;
+        for (int k = 0; k < m; k++) {
+            int slot = -1;
+            for (int s = 0; s < Q; s++) if (kept[s] == bc_nodes[k]) slot = s;
+            if (slot < 0) { atomicExch(status, 2); continue; }
+            for (int c = 0; c < n; c++) M[(size_t)q * ld + slot * n + c] += Bc[((size_t)k * L + q) * n + c];
+        }
+        M[(size_t)q * ld + D] = q < La ? resid[q] : resid[tail_off + (q - La)];
+    }
+    for (int e = tid; e < (Q - 1) * (int)nn; e += T) {
+        const int g = e / (int)nn, q = (e % (int)nn) / n, c = e % n;
+        double* row = M + (size_t)(L + g * n + q) * ld;
+        row[g * n + c] = relL[e];
+        row[(g + 1) * n + c] = relR[e];
+    }
+    for (int e = tid; e < (Q - 1) * n; e += T) M[(size_t)(L + e) * ld + D] = relr[e];
+    for (int r = tid; r < D; r += T) elig[r] = 1;
+    __syncthreads();
+    if (!block_gauss_jordan(M, D, cols, ld, D, elig, pivrow, mult, prow, s_p)) {
+        if (tid == 0) atomicExch(status, 1);
+        return;
+    }
+    for (int e = tid; e < D; e += T) {
+        const int s = e / n, c = e % n;
+        delta[(size_t)kept[s] * n + c] = M[(size_t)pivrow[e] * ld + D];
+    }
+}
+
+}  // namespace mirk

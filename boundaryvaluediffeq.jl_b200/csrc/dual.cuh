@@ -1,0 +1,81 @@
+// dual.cuh — forward-mode dual numbers (value + ONE directional derivative) for the per-interval
+// Jacobian kernels.  The reference differentiates the whole collocation loss with coloured
+// ForwardDiff sweeps (lib/BoundaryValueDiffEqMIRK/src/mirk.jl:810-838); here every thread carries
+// one seed direction through the s stages of ONE interval, so a column of [L_i R_i] costs one
+// dual evaluation of Phi_i and never touches the other N-2 intervals.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mirk {
+
+struct Dual {
+    double v, d;
+    __host__ __device__ __forceinline__ Dual() : v(0.0), d(0.0) {}
+    __host__ __device__ __forceinline__ Dual(double v_) : v(v_), d(0.0) {}
+    __host__ __device__ __forceinline__ Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+
+#define MIRK_OP __host__ __device__ __forceinline__
+MIRK_OP Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+MIRK_OP Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+MIRK_OP Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+MIRK_OP Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+MIRK_OP Dual operator/(Dual a, Dual b) {
+    const double q = a.v / b.v;
+    return Dual(q, (a.d - q * b.d) / b.v);
+}
+MIRK_OP Dual operator+(Dual a, double b) { return Dual(a.v + b, a.d); }
+MIRK_OP Dual operator+(double a, Dual b) { return Dual(a + b.v, b.d); }
+MIRK_OP Dual operator-(Dual a, double b) { return Dual(a.v - b, a.d); }
+MIRK_OP Dual operator-(double a, Dual b) { return Dual(a - b.v, -b.d); }
+MIRK_OP Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
+MIRK_OP Dual operator*(double a, Dual b) { return Dual(a * b.v, a * b.d); }
+MIRK_OP Dual operator/(Dual a, double b) { return Dual(a.v / b, a.d / b); }
+MIRK_OP Dual operator/(double a, Dual b) {
+    const double q = a / b.v;
+    return Dual(q, -q * b.d / b.v);
+}
+MIRK_OP Dual& operator+=(Dual& a, Dual b) { a.v += b.v; a.d += b.d; return a; }
+MIRK_OP Dual& operator-=(Dual& a, Dual b) { a.v -= b.v; a.d -= b.d; return a; }
+MIRK_OP Dual& operator*=(Dual& a, Dual b) { a = a * b; return a; }
+MIRK_OP Dual& operator+=(Dual& a, double b) { a.v += b; return a; }
+MIRK_OP Dual& operator*=(Dual& a, double b) { a.v *= b; a.d *= b; return a; }
+
+// elementary functions usable on both scalar types from templated RHS code: `using namespace mirk::fn;`
+namespace fn {
+MIRK_OP double sin(double x) { return ::sin(x); }
+MIRK_OP double cos(double x) { return ::cos(x); }
+MIRK_OP double exp(double x) { return ::exp(x); }
+MIRK_OP double log(double x) { return ::log(x); }
+MIRK_OP double sqrt(double x) { return ::sqrt(x); }
+MIRK_OP double tanh(double x) { return ::tanh(x); }
+MIRK_OP double square(double x) { return x * x; }
+MIRK_OP double value(double x) { return x; }
+MIRK_OP Dual sin(Dual a) {
+    double s, c;
+#ifdef __CUDA_ARCH__
+    ::sincos(a.v, &s, &c);
+#else
+    s = ::sin(a.v); c = ::cos(a.v);
+#endif
+    return Dual(s, c * a.d);
+}
+MIRK_OP Dual cos(Dual a) {
+    double s, c;
+#ifdef __CUDA_ARCH__
+    ::sincos(a.v, &s, &c);
+#else
+    s = ::sin(a.v); c = ::cos(a.v);
+#endif
+    return Dual(c, -s * a.d);
+}
+MIRK_OP Dual exp(Dual a) { const double e = ::exp(a.v); return Dual(e, e * a.d); }
+MIRK_OP Dual log(Dual a) { return Dual(::log(a.v), a.d / a.v); }
+MIRK_OP Dual sqrt(Dual a) { const double r = ::sqrt(a.v); return Dual(r, a.d / (2.0 * r)); }
+MIRK_OP Dual tanh(Dual a) { const double t = ::tanh(a.v); return Dual(t, (1.0 - t * t) * a.d); }
+MIRK_OP Dual square(Dual a) { return Dual(a.v * a.v, 2.0 * a.v * a.d); }
+MIRK_OP double value(Dual a) { return a.v; }
+}  // namespace fn
+
+}  // namespace mirk

@@ -1,0 +1,996 @@
+// mirk_b200.cu — host driver and C ABI (include/mirk_b200.h) of the B200-native MIRK path.
+//
+// Mirrors, on the host side, what the reference's MIRKCache / solve! do around the hot loops
+// (lib/BoundaryValueDiffEqMIRK/src/mirk.jl:49-265 __init, :286-388 solve!/__perform_mirk_iteration)
+// and what NonlinearSolve's NewtonRaphson does around loss/jac/linear-solve (call site
+// lib/BoundaryValueDiffEqCore/src/default_internal_solve.jl:107-110).  All numerics run in the
+// CUDA kernels of kernels.cuh / abd.cuh / abd_warp.cuh; the host only sequences launches, reads
+// back 8-byte norms / status words, and decides sizes.  There is no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "abd.cuh"
+#include "abd_warp.cuh"
+#include "generic_kernels.cuh"
+#include "mirk_b200.h"
+#include "ops.cuh"
+
+using namespace mirk;
+
+// ---- errors -------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(MIRK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CKS(call)                       \
+    do {                                \
+        int s_ = (call);                \
+        if (s_ != MIRK_OK) return s_;   \
+    } while (0)
+
+// ---- registry -----------------------------------------------------------------------------------
+static const char* kBuiltinNames[problems::kNumBuiltin] = {
+    "pendulum", "linear2", "linear2_tp", "swirling", "lotka", "torus", "layer", "chain8", "chain16",
+    "bratu64"};
+
+struct Plugin {
+    std::string name;
+    void* dl;
+    const ProblemOps* (*get)(int order);
+};
+static std::vector<Plugin> g_plugins;
+static std::mutex g_plugin_mu;
+static const int kPluginBase = 1000;
+
+static const ProblemOps* find_ops(int id, int order) {
+    using namespace problems;
+    if (id >= 0 && id <= kLayer) return ops_small(id, order);
+    if (id == kChain8) return ops_chain8(order);
+    if (id == kChain16) return ops_chain16(order);
+    if (id == kBratu64) return ops_bratu64(order);
+    std::lock_guard<std::mutex> lk(g_plugin_mu);
+    if (id >= kPluginBase && id - kPluginBase < (int)g_plugins.size()) return g_plugins[id - kPluginBase].get(order);
+    return nullptr;
+}
+
+// ---- device arena helpers -----------------------------------------------------------------------
+template <class T> static cudaError_t dalloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+template <class T> static void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static const int kMaxLev = 40;
+
+struct Plan {
+    int nlev = 0;
+    int R[kMaxLev + 1];  // relations entering level l; R[nlev] = relations of the closing system
+    int G[kMaxLev];      // groups (= relations leaving) of level l
+    int Q = 0;           // nodes of the closing system
+    int* d_int = nullptr;     // arena: nodes_l and gs_l of every level
+    double* d_rel = nullptr;  // arena: output relations of every level
+    size_t int_cap = 0, rel_cap = 0;
+    int* d_nodes[kMaxLev + 1];
+    int* d_gs[kMaxLev];
+    double *relL[kMaxLev + 1], *relR[kMaxLev + 1], *relr[kMaxLev + 1];
+    std::vector<int> pinned;  // the pinned nodes the plan was built for
+    int N = 0, chunk = 0;
+    bool valid = false;
+};
+
+struct mirk_solver_s {
+    mirk_desc desc;
+    const ProblemOps* ops = nullptr;
+    int n = 0, L = 0, La = 0, s = 0, si = 0;
+    cudaStream_t st = nullptr;
+    int N = 0, Ncap = 0;
+    bool have_guess = false;
+    std::vector<double> h_mesh, h_p;
+    // device state (all FP64, node-major)
+    double *mesh = nullptr, *mesh_new = nullptr, *y = nullptr, *y_new = nullptr, *y_guess = nullptr,
+           *y_best = nullptr, *Kd = nullptr, *Ki = nullptr, *resid = nullptr, *errors = nullptr,
+           *est = nullptr, *Lb = nullptr, *Rb = nullptr, *TL = nullptr, *TR = nullptr, *rt = nullptr,
+           *delta = nullptr, *p = nullptr, *Bc = nullptr, *scratch = nullptr, *Mfinal = nullptr,
+           *tbuf = nullptr, *obuf = nullptr;
+    int *bc_nodes = nullptr, *m_dev = nullptr, *iold = nullptr, *sel_out = nullptr;
+    size_t scratch_cap = 0, Mfinal_cap = 0, tbuf_cap = 0;
+    // host-visible words: [0] residual norm bits, [1] defect bits, [2] status
+    unsigned long long* words = nullptr;  // device
+    unsigned long long* h_words = nullptr;  // pinned host
+    Plan plan;
+    int64_t launches = 0;
+    bool jac_valid = false, resid_valid = false;
+    double last_resid_norm = NAN;
+};
+
+static double bits_to_double(unsigned long long b) {
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+// ---- buffers ------------------------------------------------------------------------------------
+static void free_buffers(mirk_solver_s* S) {
+    dfree(S->mesh); dfree(S->mesh_new); dfree(S->y); dfree(S->y_new); dfree(S->y_guess); dfree(S->y_best);
+    dfree(S->Kd); dfree(S->Ki); dfree(S->resid); dfree(S->errors); dfree(S->est); dfree(S->Lb); dfree(S->Rb);
+    dfree(S->TL); dfree(S->TR); dfree(S->rt); dfree(S->delta); dfree(S->iold);
+    S->Ncap = 0;
+}
+
+static int ensure_capacity(mirk_solver_s* S, int Nneed) {
+    if (Nneed <= S->Ncap) return MIRK_OK;
+    free_buffers(S);
+    const size_t N = (size_t)Nneed, n = S->n, nn = n * n;
+    CK(dalloc(&S->mesh, N)); CK(dalloc(&S->mesh_new, N));
+    CK(dalloc(&S->y, N * n)); CK(dalloc(&S->y_new, N * n)); CK(dalloc(&S->y_guess, N * n));
+    CK(dalloc(&S->y_best, N * n));
+    CK(dalloc(&S->Kd, N * S->s * n)); CK(dalloc(&S->Ki, N * S->si * n));
+    CK(dalloc(&S->resid, (N + 1) * n)); CK(dalloc(&S->errors, N * n)); CK(dalloc(&S->est, N));
+    CK(dalloc(&S->Lb, N * nn)); CK(dalloc(&S->Rb, N * nn));
+    CK(dalloc(&S->TL, N * nn)); CK(dalloc(&S->TR, N * nn)); CK(dalloc(&S->rt, N * n));
+    CK(dalloc(&S->delta, N * n)); CK(dalloc(&S->iold, N));
+    S->Ncap = Nneed;
+    S->plan.valid = false;
+    return MIRK_OK;
+}
+
+// ---- reduction plan -----------------------------------------------------------------------------
+static int reduce_smem_bytes(int n) {
+    const int rows = 2 * n, cols = 3 * n + 1;
+    return (int)(sizeof(double) * ((size_t)rows * cols + rows + cols) + sizeof(int) * (rows + 2 * n + 4));
+}
+static int reduce_small_smem_bytes(int n) {  // only mult/prow/ints when W lives in global scratch
+    const int rows = 2 * n, cols = 3 * n + 1;
+    return (int)(sizeof(double) * (rows + cols) + sizeof(int) * (rows + 2 * n + 4));
+}
+static const int kSmemLimit = 200 * 1024;
+
+static int build_plan(mirk_solver_s* S) {
+    Plan& P = S->plan;
+    const int N = S->N, n = S->n;
+    int bcn[16];
+    const int m = S->ops->bc_nodes_host(N, S->h_mesh.data(), S->h_p.data(), bcn);
+    std::vector<int> pinned(bcn, bcn + m);
+    std::sort(pinned.begin(), pinned.end());
+    pinned.erase(std::unique(pinned.begin(), pinned.end()), pinned.end());
+    const int chunk = S->desc.chunk >= 2 ? S->desc.chunk : 8;
+    if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
+
+    std::vector<char> is_pinned(N, 0);
+    for (int v : pinned) is_pinned[v] = 1;
+    std::vector<std::vector<int>> nodes_l, gs_l;
+    std::vector<int> nodes(N);
+    for (int i = 0; i < N; i++) nodes[i] = i;
+    while ((int)nodes_l.size() < kMaxLev) {
+        const int R = (int)nodes.size() - 1;
+        std::vector<int> gs;
+        gs.push_back(0);
+        int k = 0;
+        while (k < R) {
+            int e = k + 1;
+            while (e < R && e - k < chunk && !is_pinned[nodes[e]]) e++;
+            gs.push_back(e);
+            k = e;
+        }
+        const int G = (int)gs.size() - 1;
+        if (G == R) break;
+        std::vector<int> next(G + 1);
+        for (int g = 0; g < G; g++) next[g] = nodes[gs[g]];
+        next[G] = nodes[R];
+        nodes_l.push_back(nodes);
+        gs_l.push_back(gs);
+        nodes.swap(next);
+    }
+    P.nlev = (int)nodes_l.size();
+    P.Q = (int)nodes.size();
+    size_t ints = 0, rels = 0;
+    for (int l = 0; l < P.nlev; l++) {
+        P.R[l] = (int)nodes_l[l].size() - 1;
+        P.G[l] = (int)gs_l[l].size() - 1;
+        ints += nodes_l[l].size() + gs_l[l].size();
+        rels += (size_t)P.G[l];
+    }
+    P.R[P.nlev] = P.Q - 1;
+    ints += nodes.size();
+    if (ints > P.int_cap) {
+        dfree(P.d_int);
+        CK(dalloc(&P.d_int, ints));
+        P.int_cap = ints;
+    }
+    const size_t per_rel = (size_t)2 * n * n + n;
+    if (rels * per_rel > P.rel_cap) {
+        dfree(P.d_rel);
+        CK(dalloc(&P.d_rel, rels * per_rel));
+        P.rel_cap = rels * per_rel;
+    }
+    std::vector<int> hint(ints);
+    size_t io = 0, ro = 0;
+    P.relL[0] = S->Lb;
+    P.relR[0] = S->Rb;
+    P.relr[0] = S->resid + S->La;  // Phi rows start after the leading boundary rows
+    for (int l = 0; l < P.nlev; l++) {
+        P.d_nodes[l] = P.d_int + io;
+        std::copy(nodes_l[l].begin(), nodes_l[l].end(), hint.begin() + io);
+        io += nodes_l[l].size();
+        P.d_gs[l] = P.d_int + io;
+        std::copy(gs_l[l].begin(), gs_l[l].end(), hint.begin() + io);
+        io += gs_l[l].size();
+        double* base = P.d_rel + ro * per_rel;
+        const size_t G = (size_t)P.G[l];
+        P.relL[l + 1] = base;
+        P.relR[l + 1] = base + G * n * n;
+        P.relr[l + 1] = base + 2 * G * n * n;
+        ro += G;
+    }
+    P.d_nodes[P.nlev] = P.d_int + io;
+    std::copy(nodes.begin(), nodes.end(), hint.begin() + io);
+    CK(cudaMemcpyAsync(P.d_int, hint.data(), ints * sizeof(int), cudaMemcpyHostToDevice, S->st));
+    CK(cudaStreamSynchronize(S->st));  // hint goes out of scope
+
+    // scratch for the generic reduction when the working matrix does not fit in shared memory
+    if (reduce_smem_bytes(n) > kSmemLimit && P.nlev > 0) {
+        const size_t need = (size_t)P.G[0] * (2 * n) * (3 * n + 1);
+        if (need > S->scratch_cap) {
+            dfree(S->scratch);
+            CK(dalloc(&S->scratch, need));
+            S->scratch_cap = need;
+        }
+    }
+    const size_t D = (size_t)P.Q * n, mneed = D * (D + 1);
+    if (mneed > S->Mfinal_cap) {
+        dfree(S->Mfinal);
+        CK(dalloc(&S->Mfinal, mneed));
+        S->Mfinal_cap = mneed;
+    }
+    P.pinned = pinned;
+    P.N = N;
+    P.chunk = chunk;
+    P.valid = true;
+    return MIRK_OK;
+}
+
+// ---- pieces of a Newton step ---------------------------------------------------------------------
+static int launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MIRK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return MIRK_OK;
+}
+
+// F(y): Phi rows, boundary rows, |F|_inf bits into words[0]
+static int eval_residual(mirk_solver_s* S) {
+    CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
+    S->ops->residual(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words);
+    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
+               S->words, 0);
+    S->launches += 2;
+    S->resid_valid = true;
+    return launch_check("residual");
+}
+
+static int eval_jacobian(mirk_solver_s* S) {
+    S->ops->jac_blocks(S->st, S->N, S->mesh, S->y, S->p, S->Lb, S->Rb);
+    // boundary blocks (reference pattern); rewrites the same boundary residual values
+    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
+               S->words + 3, 1);
+    S->launches += 2;
+    S->jac_valid = true;
+    return launch_check("jacobian");
+}
+
+static int abd_reduce(mirk_solver_s* S, int l_begin = 0, int l_end = kMaxLev) {
+    Plan& P = S->plan;
+    const int n = S->n;
+    const bool smem_ok = reduce_smem_bytes(n) <= kSmemLimit;
+    for (int l = l_begin; l < P.nlev && l < l_end; l++) {
+        if (warp_reduce_supported(n)) {
+            launch_warp_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
+                               P.relr[l + 1], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt,
+                               (int*)(S->words + 2));
+        } else {
+            const int smem = smem_ok ? reduce_smem_bytes(n) : reduce_small_smem_bytes(n);
+            k_reduce_generic<<<P.G[l], 256, smem, S->st>>>(n, P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1],
+                                                            P.relR[l + 1], P.relr[l + 1], P.d_nodes[l],
+                                                            P.d_gs[l], S->TL, S->TR, S->rt, S->scratch,
+                                                            smem_ok ? 1 : 0, (int*)(S->words + 2));
+        }
+        S->launches++;
+    }
+    return launch_check("abd_reduce");
+}
+
+static int final_smem_bytes(int D, bool m_in_smem) {
+    size_t b = sizeof(double) * ((size_t)D + D + 1) + sizeof(int) * (2 * (size_t)D + 4);
+    if (m_in_smem) b += sizeof(double) * (size_t)D * (D + 1);
+    return (int)b;
+}
+
+static int abd_final(mirk_solver_s* S) {
+    Plan& P = S->plan;
+    const int n = S->n, D = P.Q * n;
+    const bool m_in_smem = final_smem_bytes(D, true) <= kSmemLimit;
+    const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n;
+    const int threads = D * (D + 1) >= 4096 ? 1024 : 256;
+    k_final_solve<<<1, threads, final_smem_bytes(D, m_in_smem), S->st>>>(
+        n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, S->m_dev,
+        S->bc_nodes, S->Bc, S->resid, tail_off, m_in_smem ? nullptr : S->Mfinal, S->delta,
+        (int*)(S->words + 2));
+    S->launches++;
+    return launch_check("abd_final");
+}
+
+static int abd_backsub(mirk_solver_s* S) {
+    Plan& P = S->plan;
+    const int n = S->n;
+    for (int l = P.nlev - 1; l >= 0; l--) {
+        if (warp_reduce_supported(n))
+            launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt, S->delta);
+        else
+            k_backsub_generic<<<P.G[l], 256, 0, S->st>>>(n, P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt, S->delta);
+        S->launches++;
+    }
+    return launch_check("abd_backsub");
+}
+
+static int linear_solve(mirk_solver_s* S) {
+    CKS(build_plan(S));
+    CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
+    CKS(abd_reduce(S));
+    CKS(abd_final(S));
+    CKS(abd_backsub(S));
+    return MIRK_OK;
+}
+
+static int apply_update(mirk_solver_s* S) {
+    const size_t len = (size_t)S->N * S->n;
+    k_axpy_neg<<<(unsigned)((len + 255) / 256), 256, 0, S->st>>>(len, S->y, S->delta);
+    S->launches++;
+    S->jac_valid = false;
+    return launch_check("update");
+}
+
+// copy words to the host and wait: the single host sync of a Newton iteration
+static int read_words(mirk_solver_s* S) {
+    CK(cudaMemcpyAsync(S->h_words, S->words, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+// NewtonRaphson with |F|_inf <= abstol termination and best-iterate bookkeeping; same control flow
+// as oracle/mirk_oracle.c orc_newton (from-memory restatement of NonlinearSolve).
+static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* ret_out) {
+    const size_t ybytes = (size_t)S->N * S->n * sizeof(double);
+    const double abstol = S->desc.abstol;
+    const int maxiters = S->desc.maxiters;
+    int ret = MIRK_RET_MAXITERS, it = 0;
+    double best = INFINITY;
+    bool have_best = false;
+    CKS(eval_residual(S));
+    CKS(read_words(S));
+    double nrm = bits_to_double(S->h_words[0]);
+    while (it < maxiters) {
+        CKS(eval_jacobian(S));
+        CKS(linear_solve(S));
+        CKS(apply_update(S));
+        it++;
+        CKS(eval_residual(S));
+        CKS(read_words(S));
+        if (S->h_words[2] != 0ull) {  // singular block met by the elimination
+            ret = MIRK_RET_FAILURE;
+            nrm = bits_to_double(S->h_words[0]);
+            break;
+        }
+        nrm = bits_to_double(S->h_words[0]);
+        if (!std::isfinite(nrm)) { ret = MIRK_RET_UNSTABLE; break; }
+        if (nrm < best) {
+            best = nrm;
+            have_best = true;
+            CK(cudaMemcpyAsync(S->y_best, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        }
+        if (nrm <= abstol) { ret = MIRK_RET_SUCCESS; break; }
+    }
+    if (ret != MIRK_RET_SUCCESS && it > 0 && have_best && ret != MIRK_RET_FAILURE) {
+        CK(cudaMemcpyAsync(S->y, S->y_best, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        CKS(eval_residual(S));
+        CKS(read_words(S));
+        nrm = bits_to_double(S->h_words[0]);
+    }
+    S->last_resid_norm = nrm;
+    *iters_out = it;
+    *nrm_out = nrm;
+    *ret_out = ret;
+    return MIRK_OK;
+}
+
+static int eval_defect(mirk_solver_s* S, double* defect_norm) {
+    CK(cudaMemsetAsync(S->words + 1, 0, sizeof(unsigned long long), S->st));
+    S->ops->defect(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->errors, S->est, S->words + 1);
+    S->launches++;
+    CKS(launch_check("defect"));
+    CKS(read_words(S));
+    *defect_norm = bits_to_double(S->h_words[1]);
+    return MIRK_OK;
+}
+
+template <int ORDER>
+static void launch_interp(mirk_solver_s* S, int N, const double* mesh, const double* y, int nt, const double* ts,
+                          int deriv, int add_base, double* out, int* iold) {
+    const long long tot = (long long)nt * S->n;
+    k_interp<ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, S->st>>>(S->n, N, mesh, y, S->Kd, S->Ki, nt, ts, deriv,
+                                                                     add_base, out, iold);
+}
+static int do_interp(mirk_solver_s* S, int N, const double* mesh, const double* y, int nt, const double* ts, int deriv,
+                     int add_base, double* out, int* iold) {
+    if (S->desc.order == 4) launch_interp<4>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold);
+    else launch_interp<6>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold);
+    S->launches++;
+    return launch_check("interp");
+}
+
+static int sync_host_mesh(mirk_solver_s* S) {
+    S->h_mesh.resize(S->N);
+    CK(cudaMemcpyAsync(S->h_mesh.data(), S->mesh, sizeof(double) * S->N, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+// mesh_selector! + interp_eval! + __expand_cache!  (MIRK/adaptivity.jl:23-75, mirk.jl:364-372)
+static int refine_mesh(mirk_solver_s* S, int* info_out, int* Nnew_out) {
+    const int N = S->N, n = S->n;
+    const int smem_needed = (int)(sizeof(double) * 2 * (size_t)N);
+    const int use_smem = smem_needed <= kSmemLimit;
+    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0, S->st>>>(S->desc.order, N, S->mesh, S->est, S->desc.abstol,
+                                                                  S->desc.max_num_subintervals, S->Ncap, S->mesh_new,
+                                                                  S->sel_out, use_smem);
+    S->launches++;
+    CKS(launch_check("mesh_select"));
+    int out[2];
+    CK(cudaMemcpyAsync(out, S->sel_out, sizeof(out), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    *info_out = out[1];
+    *Nnew_out = out[0];
+    if (out[1] != MIRK_RET_SUCCESS) return MIRK_OK;
+    const int Nn = out[0];
+    if (Nn > S->Ncap) return fail(MIRK_ERR_STATE, "refined mesh exceeds the allocated capacity");
+    // new guess = old interpolant at the new nodes
+    if (S->desc.reinterp_inplace) {
+        CKS(do_interp(S, N, S->mesh, S->y, Nn, S->mesh_new, 0, 0, S->delta, S->iold));
+        k_reinterp_inplace_chain<<<1, ((n + 31) / 32) * 32, 0, S->st>>>(n, N, Nn, S->y, S->delta, S->iold, S->y_new);
+        S->launches++;
+    } else {
+        CKS(do_interp(S, N, S->mesh, S->y, Nn, S->mesh_new, 0, 1, S->y_new, nullptr));
+    }
+    std::swap(S->mesh, S->mesh_new);
+    std::swap(S->y, S->y_new);
+    S->N = Nn;
+    CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(Nn - 1) * S->s * n, S->st));
+    CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(Nn - 1) * S->si * n, S->st));
+    S->jac_valid = S->resid_valid = false;
+    S->plan.valid = false;
+    return sync_host_mesh(S);
+}
+
+// MIRK/mirk.jl:374-385: halve the mesh and restart from an all-zero guess (quirk Q4)
+static int halve_and_zero(mirk_solver_s* S) {
+    const int N = S->N, n = S->n, Nn = 2 * (N - 1) + 1;
+    if (Nn > S->Ncap) return fail(MIRK_ERR_STATE, "halved mesh exceeds the allocated capacity");
+    k_half_mesh<<<(N + 255) / 256, 256, 0, S->st>>>(N, S->mesh, S->mesh_new);
+    S->launches++;
+    std::swap(S->mesh, S->mesh_new);
+    S->N = Nn;
+    CK(cudaMemsetAsync(S->y, 0, sizeof(double) * (size_t)Nn * n, S->st));
+    CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(Nn - 1) * S->s * n, S->st));
+    CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(Nn - 1) * S->si * n, S->st));
+    S->jac_valid = S->resid_valid = false;
+    S->plan.valid = false;
+    return sync_host_mesh(S);
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+extern "C" void mirk_mesh_uniform_fill(double t0, double t1, int32_t nint, double* mesh);
+
+extern "C" {
+
+int mirk_version(void) { return 100; }
+const char* mirk_last_error(void) { return g_err.c_str(); }
+
+int mirk_device_count(int32_t* count) {
+    if (!count) return fail(MIRK_ERR_ARG, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(MIRK_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    return MIRK_OK;
+}
+
+int mirk_problem_lookup(const char* name, int32_t* problem_id) {
+    if (!name || !problem_id) return fail(MIRK_ERR_ARG, "NULL argument");
+    for (int i = 0; i < problems::kNumBuiltin; i++)
+        if (!strcmp(name, kBuiltinNames[i])) { *problem_id = i; return MIRK_OK; }
+    std::lock_guard<std::mutex> lk(g_plugin_mu);
+    for (size_t i = 0; i < g_plugins.size(); i++)
+        if (g_plugins[i].name == name) { *problem_id = kPluginBase + (int)i; return MIRK_OK; }
+    return fail(MIRK_ERR_UNSUPPORTED, std::string("unknown problem '") + name + "'");
+}
+
+int mirk_problem_info_get(int32_t problem_id, mirk_problem_info* info) {
+    if (!info) return fail(MIRK_ERR_ARG, "info is NULL");
+    const ProblemOps* o = find_ops(problem_id, 4);
+    if (!o) return fail(MIRK_ERR_UNSUPPORTED, "unknown problem id");
+    info->n = o->n; info->n_params = o->np; info->problem_type = o->problem_type;
+    info->n_bc = o->n_bc; info->n_bca = o->n_bca; info->max_bc_pts = o->max_bc_pts;
+    return MIRK_OK;
+}
+
+// A plugin is a shared object built from a user functor with plugin_template.cu: it exports
+// `const mirk::ProblemOps* mirk_plugin_ops(int order)`.
+int mirk_problem_register_plugin(const char* name, const char* so_path, int32_t* problem_id) {
+    if (!name || !so_path || !problem_id) return fail(MIRK_ERR_ARG, "NULL argument");
+    void* dl = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return fail(MIRK_ERR_ARG, std::string("dlopen: ") + dlerror());
+    auto get = (const ProblemOps* (*)(int))dlsym(dl, "mirk_plugin_ops");
+    if (!get) { dlclose(dl); return fail(MIRK_ERR_ARG, "plugin lacks mirk_plugin_ops"); }
+    std::lock_guard<std::mutex> lk(g_plugin_mu);
+    g_plugins.push_back(Plugin{name, dl, get});
+    *problem_id = kPluginBase + (int)g_plugins.size() - 1;
+    return MIRK_OK;
+}
+
+int mirk_mesh_uniform(double t0, double t1, int32_t nint, double* mesh) {
+    if (!mesh || nint < 1) return fail(MIRK_ERR_ARG, "bad mesh request");
+    mirk_mesh_uniform_fill(t0, t1, nint, mesh);  // binary128, host_util.cpp
+    return MIRK_OK;
+}
+
+int mirk_destroy(mirk_handle S) {
+    if (!S) return MIRK_OK;
+    cudaSetDevice(S->desc.device);
+    if (S->st) cudaStreamSynchronize(S->st);
+    free_buffers(S);
+    dfree(S->p); dfree(S->Bc); dfree(S->scratch); dfree(S->Mfinal); dfree(S->tbuf); dfree(S->obuf);
+    dfree(S->bc_nodes); dfree(S->m_dev); dfree(S->sel_out); dfree(S->words);
+    dfree(S->plan.d_int); dfree(S->plan.d_rel);
+    if (S->h_words) cudaFreeHost(S->h_words);
+    if (S->st) cudaStreamDestroy(S->st);
+    delete S;
+    return MIRK_OK;
+}
+
+int mirk_create(const mirk_desc* desc, mirk_handle* out) {
+    if (!desc || !out) return fail(MIRK_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (desc->order != 4 && desc->order != 6) return fail(MIRK_ERR_UNSUPPORTED, "order must be 4 (MIRK4) or 6 (MIRK6)");
+    const ProblemOps* ops = find_ops(desc->problem_id, desc->order);
+    if (!ops) return fail(MIRK_ERR_UNSUPPORTED, "unknown problem id");
+    if (desc->n_params < ops->np) return fail(MIRK_ERR_ARG, "too few parameters for this problem");
+    if (ops->np > 0 && !desc->params) return fail(MIRK_ERR_ARG, "params is NULL");
+    if (!(desc->abstol > 0)) return fail(MIRK_ERR_ARG, "abstol must be positive");
+    if (ops->n_bc != ops->n) return fail(MIRK_ERR_UNSUPPORTED, "boundary rows must equal states (NLLS is out of scope)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MIRK_ERR_NO_DEVICE, "no CUDA device: libmirkb200 has no CPU fallback");
+    }
+    if (desc->device < 0 || desc->device >= count) return fail(MIRK_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(desc->device));
+    mirk_solver_s* S = new mirk_solver_s();
+    S->desc = *desc;
+    S->desc.params = nullptr;
+    if (S->desc.maxiters < 0) S->desc.maxiters = 0;
+    S->ops = ops;
+    S->n = ops->n; S->L = ops->n_bc; S->s = ops->s; S->si = ops->s_star - ops->s;
+    S->La = ops->problem_type == 1 ? ops->n_bca : ops->n_bc;
+    S->h_p.assign(std::max(desc->n_params, 1), 0.0);
+    for (int i = 0; i < desc->n_params; i++) S->h_p[i] = desc->params[i];
+#define CKD(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e2 = (call);                                                        \
+        if (e2 != cudaSuccess) {                                                        \
+            mirk_destroy(S);                                                            \
+            return fail(MIRK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2)); \
+        }                                                                               \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+    CKD(dalloc(&S->p, S->h_p.size()));
+    CKD(cudaMemcpy(S->p, S->h_p.data(), S->h_p.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CKD(dalloc(&S->Bc, (size_t)ops->max_bc_pts * S->L * S->n));
+    CKD(dalloc(&S->bc_nodes, 16));
+    CKD(dalloc(&S->m_dev, 1));
+    CKD(dalloc(&S->sel_out, 2));
+    CKD(dalloc(&S->words, 4));
+    CKD(cudaMemset(S->words, 0, 4 * sizeof(unsigned long long)));
+    CKD(cudaMallocHost((void**)&S->h_words, 4 * sizeof(unsigned long long)));
+#undef CKD
+    // opt in to large dynamic shared memory once per process (idempotent)
+    cudaFuncSetAttribute(k_reduce_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(k_final_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(k_mesh_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    *out = S;
+    return MIRK_OK;
+}
+
+int mirk_set_params(mirk_handle S, const double* params, int32_t n_params) {
+    if (!S || (n_params > 0 && !params)) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (n_params < S->ops->np) return fail(MIRK_ERR_ARG, "too few parameters for this problem");
+    CK(cudaSetDevice(S->desc.device));
+    for (int i = 0; i < n_params && i < (int)S->h_p.size(); i++) S->h_p[i] = params[i];
+    CK(cudaMemcpyAsync(S->p, S->h_p.data(), S->h_p.size() * sizeof(double), cudaMemcpyHostToDevice, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    S->jac_valid = S->resid_valid = false;
+    S->plan.valid = false;
+    return MIRK_OK;
+}
+
+int mirk_set_mesh_guess(mirk_handle S, int32_t n_mesh, const double* mesh, const double* y) {
+    if (!S || !mesh || !y) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (n_mesh < 2) return fail(MIRK_ERR_ARG, "a mesh needs at least two nodes");
+    for (int i = 1; i < n_mesh; i++)
+        if (!(mesh[i] > mesh[i - 1])) return fail(MIRK_ERR_ARG, "mesh must be strictly increasing");
+    CK(cudaSetDevice(S->desc.device));
+    const int cap = S->desc.adaptive ? std::max(n_mesh, S->desc.max_num_subintervals + 1) : n_mesh;
+    CKS(ensure_capacity(S, cap));
+    S->N = n_mesh;
+    S->h_mesh.assign(mesh, mesh + n_mesh);
+    const size_t yb = sizeof(double) * (size_t)n_mesh * S->n;
+    CK(cudaMemcpyAsync(S->mesh, mesh, sizeof(double) * n_mesh, cudaMemcpyHostToDevice, S->st));
+    CK(cudaMemcpyAsync(S->y, y, yb, cudaMemcpyHostToDevice, S->st));
+    CK(cudaMemcpyAsync(S->y_guess, S->y, yb, cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->s * S->n, S->st));
+    CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->si * S->n, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    S->have_guess = true;
+    S->jac_valid = S->resid_valid = false;
+    S->plan.valid = false;
+    return MIRK_OK;
+}
+
+int mirk_set_uniform_guess(mirk_handle S, double t0, double t1, double dt, const double* u0) {
+    if (!S || !u0) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (!(dt > 0)) return fail(MIRK_ERR_ARG, "dt must be positive");
+    if (!(t1 > t0)) return fail(MIRK_ERR_ARG, "tspan must be increasing");
+    const int nint = (int)ceil((t1 - t0) / dt);  // cld(t1 - t0, dt), CORE/utils.jl:362
+    std::vector<double> mesh(nint + 1), y((size_t)(nint + 1) * S->n);
+    mirk_mesh_uniform(t0, t1, nint, mesh.data());
+    for (int i = 0; i <= nint; i++)
+        for (int k = 0; k < S->n; k++) y[(size_t)i * S->n + k] = u0[k];
+    return mirk_set_mesh_guess(S, nint + 1, mesh.data(), y.data());
+}
+
+#define NEED_GUESS(S)                                                          \
+    do {                                                                       \
+        if (!(S)) return fail(MIRK_ERR_ARG, "NULL handle");                    \
+        if (!(S)->have_guess) return fail(MIRK_ERR_STATE, "no mesh/guess set"); \
+        CK(cudaSetDevice((S)->desc.device));                                   \
+    } while (0)
+
+int mirk_residual(mirk_handle S, double* resid, double* resid_norm) {
+    NEED_GUESS(S);
+    CKS(eval_residual(S));
+    CKS(read_words(S));
+    if (resid_norm) *resid_norm = bits_to_double(S->h_words[0]);
+    if (resid) {
+        CK(cudaMemcpyAsync(resid, S->resid, sizeof(double) * ((size_t)S->L + (size_t)(S->N - 1) * S->n),
+                           cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+    }
+    return MIRK_OK;
+}
+
+int mirk_jacobian_blocks(mirk_handle S, double* Lb, double* Rb, int32_t* bc_nodes, double* Bc, int32_t* m) {
+    NEED_GUESS(S);
+    if (!S->resid_valid) CKS(eval_residual(S));  // the boundary blocks read the discrete stages
+    CKS(eval_jacobian(S));
+    const size_t nb = sizeof(double) * (size_t)(S->N - 1) * S->n * S->n;
+    if (Lb) CK(cudaMemcpyAsync(Lb, S->Lb, nb, cudaMemcpyDeviceToHost, S->st));
+    if (Rb) CK(cudaMemcpyAsync(Rb, S->Rb, nb, cudaMemcpyDeviceToHost, S->st));
+    int mh = 0;
+    CK(cudaMemcpyAsync(&mh, S->m_dev, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    if (m) *m = mh;
+    if (bc_nodes) CK(cudaMemcpy(bc_nodes, S->bc_nodes, sizeof(int) * mh, cudaMemcpyDeviceToHost));
+    if (Bc) CK(cudaMemcpy(Bc, S->Bc, sizeof(double) * (size_t)mh * S->L * S->n, cudaMemcpyDeviceToHost));
+    return MIRK_OK;
+}
+
+int mirk_linear_solve(mirk_handle S, double* delta) {
+    NEED_GUESS(S);
+    if (!S->resid_valid) CKS(eval_residual(S));
+    if (!S->jac_valid) CKS(eval_jacobian(S));
+    CKS(linear_solve(S));
+    CKS(read_words(S));
+    if (delta) {
+        CK(cudaMemcpyAsync(delta, S->delta, sizeof(double) * (size_t)S->N * S->n, cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+    }
+    return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
+}
+
+int mirk_newton_step(mirk_handle S, double* resid_norm) {
+    NEED_GUESS(S);
+    if (!S->resid_valid) CKS(eval_residual(S));
+    CKS(eval_jacobian(S));
+    CKS(linear_solve(S));
+    CKS(apply_update(S));
+    CKS(eval_residual(S));
+    CKS(read_words(S));
+    if (resid_norm) *resid_norm = bits_to_double(S->h_words[0]);
+    return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
+}
+
+int mirk_newton_solve(mirk_handle S, int32_t* iters, double* resid_norm) {
+    NEED_GUESS(S);
+    int it = 0, ret = 0;
+    double nrm = 0;
+    CKS(newton_solve(S, &it, &nrm, &ret));
+    if (iters) *iters = it;
+    if (resid_norm) *resid_norm = nrm;
+    return ret;
+}
+
+int mirk_defect(mirk_handle S, double* errors, double* defect_norm) {
+    NEED_GUESS(S);
+    if (!S->resid_valid) CKS(eval_residual(S));
+    double d = 0;
+    CKS(eval_defect(S, &d));
+    if (defect_norm) *defect_norm = d;
+    if (errors) {
+        CK(cudaMemcpyAsync(errors, S->errors, sizeof(double) * (size_t)(S->N - 1) * S->n, cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+    }
+    return MIRK_OK;
+}
+
+int mirk_refine_mesh(mirk_handle S, int32_t* n_mesh_new) {
+    NEED_GUESS(S);
+    int info = 0, Nn = 0;
+    CKS(refine_mesh(S, &info, &Nn));
+    if (n_mesh_new) *n_mesh_new = S->N;
+    return info;
+}
+
+int mirk_solve(mirk_handle S, mirk_result* out) {
+    NEED_GUESS(S);
+    if (!out) return fail(MIRK_ERR_ARG, "result is NULL");
+    memset(out, 0, sizeof(*out));
+    const double abstol = S->desc.abstol;
+    int info = MIRK_RET_SUCCESS;
+    double error_norm = 2.0 * abstol, resid_norm = 0.0;
+    const int max_outer = 100;
+    do {
+        int iters = 0, nret = 0;
+        CKS(newton_solve(S, &iters, &resid_norm, &nret));
+        out->newton_iters += iters;
+        error_norm = 2.0 * abstol;
+        info = nret;
+        const int h = out->n_hist < 64 ? out->n_hist : 63;
+        out->hist_n_mesh[h] = S->N;
+        out->hist_newton[h] = iters;
+        out->hist_defect[h] = NAN;
+        out->outer_iters++;
+        if (out->n_hist < 64) out->n_hist++;
+        if (!S->desc.adaptive) {
+            // Standard problems leave all interpolation stages filled (interp_setup! runs inside every
+            // loss call, interpolation.jl:382-403); two-point ones leave them zero (quirk Q7)
+            if (S->ops->problem_type == 0) {
+                S->ops->interp_setup(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki);
+                S->launches++;
+            }
+            break;
+        }
+        if (info == MIRK_RET_SUCCESS) {
+            CKS(eval_defect(S, &error_norm));
+            out->hist_defect[h] = error_norm;
+            if (!(error_norm <= S->desc.defect_threshold)) info = MIRK_RET_FAILURE;
+            if (info == MIRK_RET_SUCCESS && error_norm > abstol) {
+                int Nn = 0;
+                CKS(refine_mesh(S, &info, &Nn));
+                continue;
+            }
+        }
+        if (info != MIRK_RET_SUCCESS) {
+            if (2 * (S->N - 1) > S->desc.max_num_subintervals) {
+                info = MIRK_RET_FAILURE;
+            } else {
+                CKS(halve_and_zero(S));
+                info = MIRK_RET_SUCCESS;
+            }
+        }
+    } while (info == MIRK_RET_SUCCESS && error_norm > abstol && out->outer_iters < max_outer);
+    if (info == MIRK_RET_SUCCESS && S->desc.adaptive && error_norm > abstol) info = MIRK_RET_MAXITERS;
+    CK(cudaStreamSynchronize(S->st));
+    out->retcode = info;
+    out->n_mesh = S->N;
+    out->resid_norm = resid_norm;
+    out->defect_norm = error_norm;
+    return MIRK_OK;
+}
+
+int mirk_get_mesh_size(mirk_handle S, int32_t* n_mesh) {
+    if (!S || !n_mesh) return fail(MIRK_ERR_ARG, "NULL argument");
+    *n_mesh = S->N;
+    return MIRK_OK;
+}
+
+int mirk_get_solution(mirk_handle S, double* mesh, double* y) {
+    NEED_GUESS(S);
+    if (mesh) CK(cudaMemcpyAsync(mesh, S->mesh, sizeof(double) * S->N, cudaMemcpyDeviceToHost, S->st));
+    if (y) CK(cudaMemcpyAsync(y, S->y, sizeof(double) * (size_t)S->N * S->n, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+int mirk_get_stages(mirk_handle S, double* Kd, double* Ki) {
+    NEED_GUESS(S);
+    const size_t per = (size_t)(S->N - 1) * S->n;
+    if (Kd) CK(cudaMemcpyAsync(Kd, S->Kd, sizeof(double) * per * S->s, cudaMemcpyDeviceToHost, S->st));
+    if (Ki) CK(cudaMemcpyAsync(Ki, S->Ki, sizeof(double) * per * S->si, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+int mirk_get_residual(mirk_handle S, double* resid) {
+    NEED_GUESS(S);
+    if (!resid) return fail(MIRK_ERR_ARG, "resid is NULL");
+    CK(cudaMemcpyAsync(resid, S->resid, sizeof(double) * ((size_t)S->L + (size_t)(S->N - 1) * S->n),
+                       cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+int mirk_interp(mirk_handle S, const double* t, int32_t m, int32_t deriv, double* out) {
+    NEED_GUESS(S);
+    if (!t || !out || m < 0) return fail(MIRK_ERR_ARG, "bad argument");
+    if (deriv != 0 && deriv != 1) return fail(MIRK_ERR_ARG, "deriv must be 0 or 1");
+    if (m == 0) return MIRK_OK;
+    if ((size_t)m * (S->n + 1) > S->tbuf_cap) {
+        dfree(S->tbuf);
+        CK(dalloc(&S->tbuf, (size_t)m * (S->n + 1)));
+        S->tbuf_cap = (size_t)m * (S->n + 1);
+    }
+    double* dout = S->tbuf + m;
+    CK(cudaMemcpyAsync(S->tbuf, t, sizeof(double) * m, cudaMemcpyHostToDevice, S->st));
+    CKS(do_interp(S, S->N, S->mesh, S->y, m, S->tbuf, deriv, 1, dout, nullptr));
+    CK(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)m * S->n, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return MIRK_OK;
+}
+
+// FP64 FMA peak (dependent-chain-free DFMA loop over all SMs) and HBM copy bandwidth, measured on
+// this device: the denominators of the roofline fractions bench.py reports.
+__global__ void k_peak_dfma(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678) out[0] = r;
+}
+__global__ void k_peak_copy(const double2* __restrict__ a, double2* __restrict__ b, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(MIRK_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double* out = nullptr;
+    CK(dalloc(&out, 1));
+    float best = 1e30f, ms = 0;
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0));
+        k_peak_dfma<<<blocks, threads>>>(out, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (fp64_tflops) *fp64_tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) * 1e-12;
+    dfree(out);
+    const size_t n2 = (size_t)1 << 26;  // 1 GiB each way
+    double2 *a = nullptr, *b = nullptr;
+    CK(dalloc(&a, n2));
+    CK(dalloc(&b, n2));
+    CK(cudaMemset(a, 0, n2 * sizeof(double2)));
+    best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        k_peak_copy<<<prop.multiProcessorCount * 16, 512>>>(a, b, n2);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (hbm_gbs) *hbm_gbs = 2.0 * n2 * sizeof(double2) / (best * 1e-3) * 1e-9;
+    dfree(a);
+    dfree(b);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MIRK_OK;
+}
+
+int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float* phase_ms, int64_t* launches) {
+    NEED_GUESS(S);
+    if (steps < 1) return fail(MIRK_ERR_ARG, "steps must be >= 1");
+    CKS(build_plan(S));
+    const size_t yb = sizeof(double) * (size_t)S->N * S->n;
+    const int NE = 9;
+    std::vector<cudaEvent_t> ev((size_t)steps * NE);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    const int64_t l0 = S->launches;
+    for (int it = 0; it < steps; it++) {
+        cudaEvent_t* e = &ev[(size_t)it * NE];
+        CK(cudaMemcpyAsync(S->y, S->y_guess, yb, cudaMemcpyDeviceToDevice, S->st));
+        CK(cudaEventRecord(e[0], S->st));
+        CKS(eval_residual(S));
+        CK(cudaEventRecord(e[1], S->st));
+        CKS(eval_jacobian(S));
+        CK(cudaEventRecord(e[2], S->st));
+        CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
+        CKS(abd_reduce(S, 0, 1));
+        CK(cudaEventRecord(e[3], S->st));
+        CKS(abd_reduce(S, 1, kMaxLev));
+        CK(cudaEventRecord(e[4], S->st));
+        CKS(abd_final(S));
+        CK(cudaEventRecord(e[5], S->st));
+        CKS(abd_backsub(S));
+        CK(cudaEventRecord(e[6], S->st));
+        CKS(apply_update(S));
+        CK(cudaEventRecord(e[7], S->st));
+        CK(cudaEventRecord(e[8], S->st));
+    }
+    CK(cudaStreamSynchronize(S->st));
+    float ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tot = 0;
+    for (int it = 0; it < steps; it++) {
+        cudaEvent_t* e = &ev[(size_t)it * NE];
+        for (int k = 0; k < 7; k++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+            ph[k] += ms;
+        }
+    }
+    // the whole timed region: first step's start to last step's end (includes the y resets between steps)
+    CK(cudaEventElapsedTime(&tot, ev[0], ev[(size_t)(steps - 1) * NE + 7]));
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (total_ms) *total_ms = tot;
+    if (phase_ms) for (int k = 0; k < 8; k++) phase_ms[k] = ph[k];
+    if (launches) *launches = S->launches - l0;
+    CKS(read_words(S));
+    return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
+}
+
+}  // extern "C"

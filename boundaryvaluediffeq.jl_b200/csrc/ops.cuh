@@ -1,0 +1,78 @@
+// ops.cuh — per-(problem, order) launch table.  The host driver (mirk_b200.cu) only sees this
+// table, so ahead-of-time instantiations (the built-in registry) and, later, NVRTC-compiled user
+// functors plug in the same way.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "problems.cuh"
+
+namespace mirk {
+
+struct ProblemOps {
+    const char* name;
+    int order, n, np, n_bc, n_bca, problem_type, max_bc_pts, s, s_star;
+    void (*residual)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
+                     double* Kd, double* phi_out, unsigned long long* norm_bits);
+    void (*bc)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
+               const double* Kd, double* Ki, double* resid, int* bc_nodes, double* Bc, int* m_out,
+               unsigned long long* norm_bits, int want_jac);
+    void (*jac_blocks)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
+                       double* Lb, double* Rb);
+    void (*defect)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
+                   const double* Kd, double* Ki, double* errors, double* est,
+                   unsigned long long* defect_bits);
+    void (*interp_setup)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
+                         const double* Kd, double* Ki);
+    // host twin of k_bc's node selection: the nodes the boundary rows touch (never eliminated)
+    int (*bc_nodes_host)(int N, const double* mesh, const double* p, int* nodes);
+};
+
+template <class P, int ORDER> struct OpsImpl {
+    static void residual(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
+                         double* Kd, double* phi_out, unsigned long long* nb) {
+        const int nb_ = (N - 1 + 127) / 128;
+        k_residual<P, ORDER><<<nb_, 128, 0, st>>>(N, mesh, y, p, Kd, phi_out, nb);
+    }
+    static void bc(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
+                   const double* Kd, double* Ki, double* resid, int* bc_nodes, double* Bc, int* m_out,
+                   unsigned long long* nb, int want_jac) {
+        k_bc<P, ORDER><<<1, 256, 0, st>>>(N, mesh, y, p, Kd, Ki, resid, bc_nodes, Bc, m_out, nb, want_jac);
+    }
+    static void jac_blocks(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
+                           double* Lb, double* Rb) {
+        const long long tot = (long long)(N - 1) * 2 * P::n;
+        k_jac_blocks<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Lb, Rb);
+    }
+    static void defect(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
+                       const double* Kd, double* Ki, double* errors, double* est,
+                       unsigned long long* db) {
+        k_defect<P, ORDER><<<(N - 1 + 127) / 128, 128, 0, st>>>(N, mesh, y, p, Kd, Ki, errors, est, db);
+    }
+    static void interp_setup(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
+                             const double* Kd, double* Ki) {
+        k_interp_setup<P, ORDER><<<(N - 1 + 127) / 128, 128, 0, st>>>(N, mesh, y, p, Kd, Ki);
+    }
+    static int bc_nodes_host(int N, const double* mesh, const double* p, int* nodes) {
+        if (P::problem_type == 1) { nodes[0] = 0; nodes[1] = N - 1; return 2; }
+        double tm[P::max_bc_pts];
+        const int m = P::bc_times(tm, p, mesh[0], mesh[N - 1]);
+        for (int k = 0; k < m; k++)
+            nodes[k] = tm[k] == mesh[0] ? 0 : tm[k] == mesh[N - 1] ? N - 1 : interval_of(mesh, N, tm[k]);
+        return m;
+    }
+    static ProblemOps make(const char* name) {
+        using TB = Tableau<ORDER>;
+        return ProblemOps{name, ORDER, P::n, P::np, P::n_bc, P::n_bca, P::problem_type, P::max_bc_pts,
+                          TB::s, TB::s_star, &residual, &bc, &jac_blocks, &defect, &interp_setup,
+                          &bc_nodes_host};
+    }
+};
+
+// defined one per translation unit group (ops_*.cu) so the registry compiles in parallel
+const ProblemOps* ops_small(int id, int order);
+const ProblemOps* ops_chain8(int order);
+const ProblemOps* ops_chain16(int order);
+const ProblemOps* ops_bratu64(int order);
+
+}  // namespace mirk

@@ -1,0 +1,116 @@
+// tableau.cuh — MIRK4 / MIRK6 coefficient tables and continuous-extension weights as
+// compile-time constants, so every stage loop in the kernels unrolls to straight-line FP64.
+//
+// Restates (not copied; the reference stores them as runtime Julia arrays built from rationals):
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:62-87   (MIRK4: s=3, s*=4, tau*=0.226)
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:120-152 (MIRK6: s=5, s*=9, tau*=0.7156)
+//   lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:481-499, 528-575 (weights w, w')
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mirk {
+
+#define MIRK_HD __host__ __device__ __forceinline__
+
+template <int ORDER> struct Tableau;
+
+template <> struct Tableau<4> {
+    static constexpr int order = 4, s = 3, s_star = 4, si = 1;
+    MIRK_HD static constexpr double c(int r) { return r == 0 ? 0.0 : r == 1 ? 1.0 : 0.5; }
+    MIRK_HD static constexpr double v(int r) { return r == 0 ? 0.0 : r == 1 ? 1.0 : 0.5; }
+    MIRK_HD static constexpr double b(int r) { return r == 2 ? 2.0 / 3.0 : 1.0 / 6.0; }
+    MIRK_HD static constexpr double x(int r, int j) {
+        return (r == 2 && j == 0) ? 1.0 / 8.0 : (r == 2 && j == 1) ? -1.0 / 8.0 : 0.0;
+    }
+    MIRK_HD static constexpr double c_star(int) { return 3.0 / 4.0; }
+    MIRK_HD static constexpr double v_star(int) { return 27.0 / 32.0; }
+    MIRK_HD static constexpr double x_star(int, int j) {
+        return j == 0 ? 3.0 / 64.0 : j == 1 ? -9.0 / 64.0 : 0.0;
+    }
+    MIRK_HD static constexpr double tau_star() { return 0.226; }
+    // w[0..s*), wp[0..s*)
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        const double t2 = t * t, tm1 = t - 1.0, t4m3 = t * 4.0 - 3.0, t2m1 = t * 2.0 - 1.0;
+        w[0] = -t * (2.0 * t - 3.0) * (2.0 * t2 - 3.0 * t + 2.0) / 6.0;
+        w[1] = t2 * (12.0 * t2 - 20.0 * t + 9.0) / 6.0;
+        w[2] = 2.0 * t2 * (6.0 * t2 - 14.0 * t + 9.0) / 3.0;
+        w[3] = -16.0 * t2 * tm1 * tm1 / 3.0;
+        wp[0] = -tm1 * t4m3 * t2m1 / 3.0;
+        wp[1] = t * t2m1 * t4m3;
+        wp[2] = 4.0 * t * t4m3 * tm1;
+        wp[3] = -32.0 * t * t2m1 * tm1 / 3.0;
+    }
+};
+
+template <> struct Tableau<6> {
+    static constexpr int order = 6, s = 5, s_star = 9, si = 4;
+    MIRK_HD static constexpr double c(int r) {
+        return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 0.25 : r == 3 ? 0.75 : 0.5;
+    }
+    MIRK_HD static constexpr double v(int r) {
+        return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 5.0 / 32.0 : r == 3 ? 27.0 / 32.0 : 0.5;
+    }
+    MIRK_HD static constexpr double b(int r) {
+        return r < 2 ? 7.0 / 90.0 : r < 4 ? 16.0 / 45.0 : 2.0 / 15.0;
+    }
+    MIRK_HD static constexpr double x(int r, int j) {
+        return r == 2 ? (j == 0 ? 9.0 / 64.0 : j == 1 ? -3.0 / 64.0 : 0.0)
+             : r == 3 ? (j == 0 ? 3.0 / 64.0 : j == 1 ? -9.0 / 64.0 : 0.0)
+             : r == 4 ? (j == 0 ? -5.0 / 24.0 : j == 1 ? 5.0 / 24.0 : j == 2 ? 2.0 / 3.0
+                                                       : j == 3 ? -2.0 / 3.0 : 0.0)
+                      : 0.0;
+    }
+    MIRK_HD static constexpr double c_star(int r) {
+        return r == 0 ? 7.0 / 16.0 : r == 1 ? 3.0 / 8.0 : r == 2 ? 9.0 / 16.0 : 1.0 / 8.0;
+    }
+    MIRK_HD static constexpr double v_star(int r) { return c_star(r); }
+    MIRK_HD static constexpr double x_star(int r, int j) {
+        return r == 0 ? (j == 0 ? 1547.0 / 32768.0 : j == 1 ? -1225.0 / 32768.0 : j == 2 ? 749.0 / 4096.0
+                         : j == 3 ? -287.0 / 2048.0 : j == 4 ? -861.0 / 16384.0 : 0.0)
+             : r == 1 ? (j == 0 ? 83.0 / 1536.0 : j == 1 ? -13.0 / 384.0 : j == 2 ? 283.0 / 1536.0
+                         : j == 3 ? -167.0 / 1536.0 : j == 4 ? -49.0 / 512.0 : 0.0)
+             : r == 2 ? (j == 0 ? 1225.0 / 32768.0 : j == 1 ? -1547.0 / 32768.0 : j == 2 ? 287.0 / 2048.0
+                         : j == 3 ? -749.0 / 4096.0 : j == 4 ? 861.0 / 16384.0 : 0.0)
+                      : (j == 0 ? 233.0 / 3456.0 : j == 1 ? -19.0 / 1152.0 : j == 5 ? -5.0 / 72.0
+                         : j == 6 ? 7.0 / 72.0 : j == 7 ? -17.0 / 216.0 : 0.0);
+    }
+    MIRK_HD static constexpr double tau_star() { return 0.7156; }
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t, t6 = t3 * t3;
+        w[0] = t - 28607.0 / 7434.0 * t2 - 166210.0 / 33453.0 * t3 + 334780.0 / 11151.0 * t4 -
+               1911296.0 / 55755.0 * t5 + 406528.0 / 33453.0 * t6;
+        w[1] = 777.0 / 590.0 * t2 - 2534158.0 / 234171.0 * t3 + 2088580.0 / 78057.0 * t4 -
+               10479104.0 / 390285.0 * t5 + 11328512.0 / 1170855.0 * t6;
+        w[2] = -1008.0 / 59.0 * t2 + 222176.0 / 1593.0 * t3 - 180032.0 / 531.0 * t4 +
+               876544.0 / 2655.0 * t5 - 180224.0 / 1593.0 * t6;
+        w[3] = w[2];
+        w[4] = -378.0 / 59.0 * t2 + 27772.0 / 531.0 * t3 - 22504.0 / 177.0 * t4 +
+               109568.0 / 885.0 * t5 - 22528.0 / 531.0 * t6;
+        w[5] = -95232.0 / 413.0 * t2 + 62384128.0 / 33453.0 * t3 - 49429504.0 / 11151.0 * t4 +
+               46759936.0 / 11151.0 * t5 - 46661632.0 / 33453.0 * t6;
+        w[6] = 896.0 / 5.0 * t2 - 4352.0 / 3.0 * t3 + 3456.0 * t4 - 16384.0 / 5.0 * t5 +
+               16384.0 / 15.0 * t6;
+        w[7] = 50176.0 / 531.0 * t2 - 179554304.0 / 234171.0 * t3 + 143363072.0 / 78057.0 * t4 -
+               136675328.0 / 78057.0 * t5 + 137363456.0 / 234171.0 * t6;
+        w[8] = 16384.0 / 441.0 * t3 - 16384.0 / 147.0 * t4 + 16384.0 / 147.0 * t5 -
+               16384.0 / 441.0 * t6;
+        wp[0] = 1.0 - 28607.0 / 3717.0 * t - 166210.0 / 11151.0 * t2 + 1339120.0 / 11151.0 * t3 -
+                1911296.0 / 11151.0 * t4 + 813056.0 / 11151.0 * t5;
+        wp[1] = 777.0 / 295.0 * t - 2534158.0 / 78057.0 * t2 + 8354320.0 / 78057.0 * t3 -
+                10479104.0 / 78057.0 * t4 + 22657024.0 / 390285.0 * t5;
+        wp[2] = -2016.0 / 59.0 * t + 222176.0 / 531.0 * t2 - 720128.0 / 531.0 * t3 +
+                876544.0 / 531.0 * t4 - 360448.0 / 531.0 * t5;
+        wp[3] = wp[2];
+        wp[4] = -756.0 / 59.0 * t + 27772.0 / 177.0 * t2 - 90016.0 / 177.0 * t3 +
+                109568.0 / 177.0 * t4 - 45056.0 / 177.0 * t5;
+        wp[5] = -190464.0 / 413.0 * t + 62384128.0 / 11151.0 * t2 - 197718016.0 / 11151.0 * t3 +
+                233799680.0 / 11151.0 * t4 - 93323264.0 / 11151.0 * t5;
+        wp[6] = 1792.0 / 5.0 * t - 4352.0 * t2 + 13824.0 * t3 - 16384.0 * t4 + 32768.0 / 5.0 * t5;
+        wp[7] = 100352.0 / 531.0 * t - 179554304.0 / 78057.0 * t2 + 573452288.0 / 78057.0 * t3 -
+                683376640.0 / 78057.0 * t4 + 274726912.0 / 78057.0 * t5;
+        wp[8] = 16384.0 / 147.0 * t2 - 65536.0 / 147.0 * t3 + 81920.0 / 147.0 * t4 -
+                32768.0 / 147.0 * t5;
+    }
+};
+
+}  // namespace mirk

@@ -1,0 +1,147 @@
+/*
+ * mirk_b200.h — C ABI of libmirkb200.so: the B200-native MIRK4/MIRK6 collocation Newton path.
+ *
+ * Drop-in boundary for the hot path of SciML/BoundaryValueDiffEq.jl (reference paths relative to
+ * /root/reference; MIRK/ = lib/BoundaryValueDiffEqMIRK/src, CORE/ = lib/BoundaryValueDiffEqCore/src).
+ * A Julia `BoundaryValueDiffEqMIRK` backend binds these with `ccall` (INTEGRATION.md shows the
+ * stubs); the tests and bench bind them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every HOST buffer is owned by the caller, every device
+ *     buffer by the library; one CUDA stream per handle; handles are independent and re-entrant
+ *     (the reference allows concurrent solves on Julia threads, MIRK/BoundaryValueDiffEqMIRK.jl:106-109)
+ *   - every entry point returns an int status: 0 ok, < 0 argument / environment error, > 0 a
+ *     numerical outcome mirroring SciMLBase.ReturnCode; nothing throws or aborts.
+ *     mirk_last_error() gives the message of the calling thread's last failure
+ *   - there is NO CPU fallback: without a CUDA device mirk_create fails with MIRK_ERR_NO_DEVICE
+ *   - unknowns are node-major `y[N][n]` exactly like the reference's flat vector
+ *     (CORE/utils.jl:59-66); residual order is the reference's: Standard `[bc; Phi_1..Phi_{N-1}]`
+ *     (MIRK/mirk.jl:471-482), TwoPoint `[bc_a; Phi...; bc_b]` (CORE/utils.jl:42-52)
+ */
+#ifndef MIRK_B200_H
+#define MIRK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* argument / environment errors */
+#define MIRK_OK 0
+#define MIRK_ERR_ARG (-1)         /* bad argument, e.g. dt <= 0 ("dt must be positive", CORE/utils.jl:354) */
+#define MIRK_ERR_NO_DEVICE (-2)   /* no CUDA device: the product path has no CPU fallback */
+#define MIRK_ERR_CUDA (-3)        /* a CUDA runtime call failed */
+#define MIRK_ERR_UNSUPPORTED (-4) /* unknown problem id / order */
+#define MIRK_ERR_STATE (-5)       /* call sequence error (e.g. no mesh set) */
+/* numerical outcomes (SciMLBase.ReturnCode as far as this path produces them) */
+#define MIRK_RET_SUCCESS 0
+#define MIRK_RET_FAILURE 1
+#define MIRK_RET_MAXITERS 2
+#define MIRK_RET_UNSTABLE 3
+#define MIRK_RET_STALLED 4
+
+typedef struct mirk_solver_s* mirk_handle;
+
+/* Replaces the BVProblem + algorithm + solve kwargs a `__init(prob, alg; ...)` call receives
+ * (MIRK/mirk.jl:49-53, MIRK/algorithms.jl:55-61). */
+typedef struct {
+    int32_t problem_id;            /* device functor: id from mirk_problem_lookup()             */
+    int32_t order;                 /* 4 = MIRK4(), 6 = MIRK6()                                  */
+    double abstol;                 /* 1e-6                                                      */
+    int32_t adaptive;              /* 1                                                         */
+    double defect_threshold;       /* DefectControl().defect_threshold = 0.1                    */
+    int32_t max_num_subintervals;  /* 3000                                                      */
+    int32_t maxiters;              /* nlsolve_kwargs maxiters, 1000                             */
+    int32_t reinterp_inplace;      /* 0; 1 reproduces the reference's in-place hazard (Q3)      */
+    int32_t chunk;                 /* relations collapsed per group and level of the ABD solve  */
+    int32_t device;                /* CUDA device ordinal                                       */
+    int32_t n_params;              /* length of params                                          */
+    const double* params;          /* prob.p (host)                                             */
+} mirk_desc;
+
+typedef struct {
+    int32_t n, n_params, problem_type /* 0 Standard, 1 TwoPoint */, n_bc, n_bca, max_bc_pts;
+} mirk_problem_info;
+
+/* What `solve!` returns (MIRK/mirk.jl:286-332): sizes and scalars; arrays via mirk_get_*. */
+typedef struct {
+    int32_t retcode;       /* MIRK_RET_*                                                        */
+    int32_t n_mesh;        /* nodes of the final mesh (length of sol.t)                         */
+    int32_t outer_iters;   /* calls of __perform_mirk_iteration                                  */
+    int32_t newton_iters;  /* Newton steps over all outer iterations                             */
+    double resid_norm;     /* |sol.resid|_inf of the last Newton solve                           */
+    double defect_norm;    /* last defect estimate (2 abstol when adaptive = false)              */
+    int32_t n_hist;        /* entries used below                                                 */
+    int32_t hist_n_mesh[64];
+    int32_t hist_newton[64];
+    double hist_defect[64];
+} mirk_result;
+
+/* -- library ----------------------------------------------------------------------------------- */
+int mirk_version(void);
+const char* mirk_last_error(void);
+int mirk_device_count(int32_t* count);
+
+/* -- device-function registry (replaces prob.f / prob.f.bc closures, MIRK/mirk.jl:71-116) ------- */
+int mirk_problem_lookup(const char* name, int32_t* problem_id);
+int mirk_problem_info_get(int32_t problem_id, mirk_problem_info* info);
+/* register a user functor compiled to a shared object from csrc/plugin template (the CUDA-side twin of
+ * passing Julia closures f!/bc! to BVProblem); see INTEGRATION.md */
+int mirk_problem_register_plugin(const char* name, const char* so_path, int32_t* problem_id);
+
+/* collect(range(t0; stop = t1, length = nint + 1)) — CORE/utils.jl:694 (host helper) */
+int mirk_mesh_uniform(double t0, double t1, int32_t nint, double* mesh);
+
+/* -- cache life cycle: SciMLBase.__init / finalizer (MIRK/mirk.jl:49-265) ------------------------ */
+int mirk_create(const mirk_desc* desc, mirk_handle* out);
+int mirk_destroy(mirk_handle h);
+int mirk_set_params(mirk_handle h, const double* params, int32_t n_params);
+/* mesh + initial guess: __extract_mesh / __initial_guess_on_mesh (CORE/utils.jl:694,750-773) */
+int mirk_set_mesh_guess(mirk_handle h, int32_t n_mesh, const double* mesh, const double* y);
+/* uniform mesh of cld(t1 - t0, dt) intervals with u0 copied to every node (CORE/utils.jl:349-363,766-769) */
+int mirk_set_uniform_guess(mirk_handle h, double t0, double t1, double dt, const double* u0);
+
+/* -- pieces of one Newton step (parity tests and the Newton-steps/s metric) ---------------------- */
+/* loss(du,u,p): __mirk_loss! (MIRK/mirk.jl:471-534); resid may be NULL */
+int mirk_residual(mirk_handle h, double* resid, double* resid_norm);
+/* jac(J,u,p): __mirk_mpoint_jacobian! / __mirk_2point_jacobian! (MIRK/mirk.jl:810-862,994-1002) in
+ * block form: Lb,Rb are (N-1) row-major n×n blocks; bc_nodes[m] 0-based pinned nodes and Bc[m][n_bc][n]
+ * the boundary rows (reference pattern).  Any pointer may be NULL. */
+int mirk_jacobian_blocks(mirk_handle h, double* Lb, double* Rb, int32_t* bc_nodes, double* Bc, int32_t* m);
+/* J \ F for the current iterate (stands in for LinearSolve inside NonlinearSolve); delta is N×n, may be NULL.
+ * Requires mirk_residual + mirk_jacobian_blocks state; leaves y untouched. */
+int mirk_linear_solve(mirk_handle h, double* delta);
+/* one NewtonRaphson iteration: J d = F, y -= d, F(y) ; returns the new |F|_inf */
+int mirk_newton_step(mirk_handle h, double* resid_norm);
+/* __internal_solve(nlprob, NewtonRaphson; abstol, maxiters) (CORE/default_internal_solve.jl:107-110) */
+int mirk_newton_solve(mirk_handle h, int32_t* iters, double* resid_norm);
+/* error_estimate!(cache, DefectControl, ...) (MIRK/adaptivity.jl:370-415); errors is (N-1)×n, may be NULL */
+int mirk_defect(mirk_handle h, double* errors, double* defect_norm);
+/* mesh_selector! + interp_eval! + __expand_cache! (MIRK/adaptivity.jl:23-75, mirk.jl:364-372);
+ * returns MIRK_RET_SUCCESS / MIRK_RET_FAILURE and the new node count */
+int mirk_refine_mesh(mirk_handle h, int32_t* n_mesh_new);
+
+/* -- SciMLBase.solve!(cache) (MIRK/mirk.jl:286-388) ---------------------------------------------- */
+int mirk_solve(mirk_handle h, mirk_result* result);
+
+/* -- solution access: sol.t, sol.u, sol(t), sol(t, Val{1}) (MIRK/interpolation.jl:17-204) -------- */
+int mirk_get_mesh_size(mirk_handle h, int32_t* n_mesh);
+int mirk_get_solution(mirk_handle h, double* mesh, double* y);
+int mirk_get_stages(mirk_handle h, double* Kd, double* Ki);
+int mirk_get_residual(mirk_handle h, double* resid);
+int mirk_interp(mirk_handle h, const double* t, int32_t m, int32_t deriv, double* out);
+
+/* -- measurement helpers (bench.py): device-timed Newton steps with inputs resident in HBM ------- */
+/* runs `steps` full Newton steps (residual + Jacobian + ABD solve + update) from the stored guess,
+ * resetting y to the guess before each step so every step does identical work; CUDA-event time of the
+ * whole region in ms, per-phase sums (residual, jacobian, reduce level 0, upper reduce levels, closing
+ * solve, back substitution, update, unused) in phase_ms[8], kernels launched in *launches. */
+int mirk_bench_newton_steps(mirk_handle h, int32_t steps, float* total_ms, float* phase_ms, int64_t* launches);
+/* roofline denominators measured on the device: FP64 FMA TFLOP/s and HBM copy GB/s */
+int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

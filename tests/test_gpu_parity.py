@@ -1,0 +1,262 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (FP64): residual / stages 1e-13 relative, Jacobian blocks 1e-12, Newton update 1e-9,
+solution values 1e-10 relative (the north-star tolerance), iteration counts and mesh sizes exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mirk_b200 as m
+    return m
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+
+PENDULUM_U0 = [math.pi / 2, math.pi / 2]
+PENDULUM_T = (0.0, math.pi / 2)
+LIN_P = [1.0, 0.0, 5.0, 5.0, 0.0, 0, 0]
+
+
+def _perturbed_case(M, O, name, order, p, tspan, nint, seed, u_base=None, mesh_jitter=True):
+    """A non-trivial iterate on a non-uniform mesh, shared by both sides."""
+    rng = np.random.default_rng(seed)
+    P = O.builtin(name)
+    n = P.n
+    mesh = np.asarray(O.mesh_uniform(tspan[0], tspan[1], nint))
+    if mesh_jitter:
+        h = (tspan[1] - tspan[0]) / nint
+        mesh[1:-1] += rng.uniform(-0.3, 0.3, nint - 1) * h
+    base = np.zeros(n) if u_base is None else np.asarray(u_base, dtype=float)
+    y = base[None, :] + 0.3 * rng.standard_normal((nint + 1, n))
+    ws = O.Workspace(P, order, p, mesh, y)
+    prob = M.BVProblem(name, y, tspan, p=p, mesh=mesh)
+    alg = M.MIRK4() if order == 4 else M.MIRK6()
+    cache = M.init(prob, alg, adaptive=False)
+    return ws, cache
+
+
+CASES = [
+    ("pendulum", 4, [9.81], PENDULUM_T, 32), ("pendulum", 6, [9.81], PENDULUM_T, 32),
+    ("linear2", 4, LIN_P, (0.0, 5.0), 25), ("linear2_tp", 6, [1.0, 5.0, 0.0], (0.0, 5.0), 17),
+    ("swirling", 4, [0.01], (0.0, 1.0), 40), ("swirling", 6, [0.01], (0.0, 1.0), 23),
+    ("lotka", 6, [7.5, 4.0, 8.5, 5.0], (0.0, 10.0), 50), ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 30),
+    ("layer", 6, [0.1], (-1.0, 1.0), 64), ("chain8", 6, None, (0.0, 0.5), 100), ("chain8", 4, None, (0.0, 0.5), 37),
+    ("chain16", 6, None, (0.0, 0.5), 41), ("bratu64", 4, [1.0], (0.0, 1.0), 19),
+]
+
+
+def _params(name, p):
+    if p is not None:
+        return p
+    npend = 8 if name == "chain8" else 16
+    rng = np.random.default_rng(5)
+    return np.concatenate([[9.81, 4.0], rng.uniform(-1, 1, 2 * npend)])
+
+
+@pytest.mark.parametrize("name,order,p,tspan,nint", CASES)
+def test_residual_jacobian_and_update_match_oracle(M, oracle, name, order, p, tspan, nint):
+    O = oracle
+    p = _params(name, p)
+    scale = 0.05 if name == "bratu64" else 1.0
+    ws, cache = _perturbed_case(M, O, name, order, p, tspan, nint, seed=nint)
+    if scale != 1.0:
+        ws.y *= scale
+        cache.close()
+        cache = M.init(M.BVProblem(name, ws.y, tspan, p=p, mesh=ws.mesh), M.MIRK4() if order == 4 else M.MIRK6(),
+                       adaptive=False)
+    # residual and stages
+    r_ref = ws.loss()
+    r_gpu, nrm = cache.residual()
+    assert _rel(r_gpu, r_ref) < 1e-13
+    assert nrm == pytest.approx(np.max(np.abs(r_ref)), rel=1e-13)
+    Kd, _ = cache.stages()
+    assert _rel(Kd, ws.Kd) < 1e-13
+    # Jacobian blocks and boundary blocks (reference pattern, quirk Q2)
+    Lb_ref, Rb_ref = ws.jac_blocks()
+    nodes_ref, B_ref = ws.bc_jac()
+    Lb, Rb, nodes, Bc = cache.jacobian_blocks()
+    assert _rel(Lb, Lb_ref) < 1e-12 and _rel(Rb, Rb_ref) < 1e-12
+    assert list(nodes) == list(nodes_ref)
+    assert _rel(Bc, B_ref) < 1e-12
+    # Newton update: J delta = F against a dense solve of the oracle's global Jacobian
+    st, delta = cache.linear_solve()
+    assert st == 0
+    J = ws.dense_jacobian()
+    d_ref = np.linalg.solve(J, r_ref).reshape(delta.shape)
+    cond_slack = 1e-9 if name not in ("swirling", "bratu64") else 1e-7
+    assert _rel(delta, d_ref) < cond_slack
+    # and as a property: the oracle Jacobian applied to the GPU update reproduces F
+    assert _rel(J @ delta.ravel(), r_ref) < 1e-8
+    cache.close()
+
+
+@pytest.mark.parametrize("chunk", [2, 3, 8, 64])
+def test_update_is_independent_of_reduction_chunking(M, oracle, chunk):
+    O = oracle
+    p = _params("chain8", None)
+    ws, cache = _perturbed_case(M, O, "chain8", 6, p, (0.0, 0.5), 203, seed=1)
+    cache.close()
+    cache = M.init(M.BVProblem("chain8", ws.y, (0.0, 0.5), p=p, mesh=ws.mesh), M.MIRK6(), adaptive=False, chunk=chunk)
+    st, delta = cache.linear_solve()
+    assert st == 0
+    d_ref = np.linalg.solve(ws.dense_jacobian(), ws.loss()).reshape(delta.shape)
+    assert _rel(delta, d_ref) < 1e-9
+    cache.close()
+
+
+def test_abd_solve_stable_on_dichotomic_problem(M, oracle):
+    """u'' = 400 u has e^{+-20 t} modes; elimination without row exchanges between the stacked
+    blocks overflows here, the pivoted reduction must not (same check the oracle's solver passes)."""
+    O = oracle
+    p = [-400.0, 1.0, 0.0]
+    nint = 200
+    mesh = O.mesh_uniform(0.0, 5.0, nint)
+    y = np.zeros((nint + 1, 2))
+    ws = O.Workspace(O.builtin("linear2_tp"), 4, p, mesh, y)
+    cache = M.init(M.BVProblem("linear2_tp", y, (0.0, 5.0), p=p, mesh=mesh), M.MIRK4(), adaptive=False)
+    ret, it, nrm = cache.newton_solve()
+    rret, rit, rnrm = ws.newton()
+    assert (ret, it) == (rret, rit) == (0, 1)
+    _, u = cache.solution()
+    assert _rel(u, ws.y) < 1e-10
+    cache.close()
+
+
+SOLVES = [
+    # name, order, p, u0, tspan, dt, kwargs
+    ("pendulum", 4, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {}),                    # BASELINE config C1
+    ("pendulum", 6, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {}),
+    ("linear2", 4, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),                          # mirk_basic_tests.jl:16-33
+    ("linear2", 6, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),
+    ("linear2_tp", 4, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.2, {}),
+    ("linear2_tp", 6, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.5, {"adaptive": False}),
+    ("swirling", 4, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),           # :315-344
+    ("swirling", 6, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),
+    ("lotka", 4, [7.5, 4.0, 8.5, 5.0], [1.0, 2.0], (0.0, 10.0), 0.1, {}),             # :438-455 (big defect)
+    ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05, {}),
+    ("layer", 4, [0.01], [0.0, 0.0], (-1.0, 1.0), 0.05, {}),                          # test/misc/adaptivity_tests.jl
+    ("layer", 6, [0.001], [0.0, 0.0], (-1.0, 1.0), 0.05, {}),
+]
+
+
+@pytest.mark.parametrize("name,order,p,u0,tspan,dt,kw", SOLVES)
+def test_full_solve_matches_oracle(M, oracle, name, order, p, u0, tspan, dt, kw):
+    """Same Newton iteration counts per outer iteration, same mesh sizes, same final mesh, solution
+    within 1e-10 relative — the north-star parity statement, against the oracle."""
+    O = oracle
+    ref = O.solve_dt(O.builtin(name), order, p, u0, tspan, dt, **kw)
+    alg = M.MIRK4() if order == 4 else M.MIRK6()
+    sol = M.solve(M.BVProblem(name, u0, tspan, p=p), alg, dt=dt, **kw)
+    assert sol.retcode == ref.retcode
+    assert sol.original["hist_n_mesh"] == ref.hist_N
+    assert sol.original["hist_newton"] == ref.hist_newton
+    assert len(sol.t) == ref.N
+    assert _rel(sol.t, ref.t) < 1e-12
+    assert _rel(sol.u, ref.u) < 1e-10
+    if ref.retcode == 0:
+        assert np.max(np.abs(sol.resid)) <= kw.get("abstol", 1e-6)
+        # dense output and its derivative (interpolation.jl:17-204)
+        ts = np.linspace(tspan[0], tspan[1], 37)
+        for deriv in (0, 1):
+            got = sol(ts, deriv=deriv)
+            want = np.stack([ref(t, deriv) for t in ts])
+            assert _rel(got, want) < 1e-9
+
+
+def test_defect_and_mesh_selection_match_oracle(M, oracle):
+    O = oracle
+    P = O.builtin("layer")
+    p = [0.01]
+    mesh = O.mesh_uniform(-1.0, 1.0, 40)
+    ws = O.Workspace(P, 4, p, mesh, np.zeros((41, 2)))
+    assert ws.newton()[0] == 0
+    cache = M.init(M.BVProblem("layer", np.zeros((41, 2)), (-1.0, 1.0), p=p), M.MIRK4())
+    assert cache.newton_solve()[0] == 0
+    d_ref, err_ref = ws.defect()
+    d, err = cache.defect()
+    assert d == pytest.approx(d_ref, rel=1e-9)
+    assert _rel(err, err_ref) < 1e-9
+    info_ref, mesh_ref = O.mesh_select(4, mesh, err_ref)
+    y_ref = O.reinterp(ws, mesh_ref, inplace_quirk=False)
+    info, Nn = cache.refine_mesh()
+    assert info == info_ref and Nn == len(mesh_ref)
+    t, u = cache.solution()
+    assert _rel(t, mesh_ref) < 1e-12
+    assert _rel(u, y_ref) < 1e-9
+    cache.close()
+
+
+def test_reinterp_inplace_quirk_Q3_matches_oracle(M, oracle):
+    O = oracle
+    args = ("layer", 4, [0.01], [0.0, 0.0], (-1.0, 1.0), 0.05)
+    ref = O.solve_dt(O.builtin(args[0]), args[1], args[2], args[3], args[4], args[5], reinterp_inplace=1)
+    sol = M.solve(M.BVProblem(args[0], args[3], args[4], p=args[2]), M.MIRK4(), dt=args[5], reinterp_inplace=True)
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+    assert _rel(sol.u, ref.u) < 1e-10
+
+
+def test_dt_must_be_positive(M):
+    prob = M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[9.81])
+    with pytest.raises(ValueError, match="dt must be positive"):   # CORE/utils.jl:354
+        M.solve(prob, M.MIRK4(), dt=0.0)
+    with pytest.raises(ValueError, match="dt must be positive"):
+        M.solve(prob, M.MIRK4(), dt=-0.1)
+
+
+def test_maxiters_zero_returns_guess_untouched(M):
+    """mirk_basic_tests.jl:678-720: with maxiters = 0 sol.u == the guess, and prob.u0 is not mutated"""
+    rng = np.random.default_rng(0)
+    guess = rng.standard_normal((11, 2))
+    keep = guess.copy()
+    prob = M.BVProblem("linear2", guess, (0.0, 5.0), p=LIN_P)
+    sol = M.solve(prob, M.MIRK4(), adaptive=False, nlsolve_kwargs={"maxiters": 0})
+    assert np.array_equal(sol.u, keep) and np.array_equal(prob.u0, keep)
+
+
+def test_convergence_order_on_gpu(M):
+    """mirk_basic_tests.jl:122-139: observed order on u'' = -u with the analytic solution"""
+    def exact(t):
+        return 5.0 * (np.cos(t) - np.sin(t) / np.tan(5.0))
+
+    for alg, order in ((M.MIRK4(), 4), (M.MIRK6(), 6)):
+        errs = []
+        for dt in (0.5, 0.25, 0.125):
+            sol = M.solve(M.BVProblem("linear2", [5.0, -3.5], (0.0, 5.0), p=LIN_P), alg, dt=dt, adaptive=False,
+                          nlsolve_kwargs={"abstol": 1e-13})
+            errs.append(np.max(np.abs(sol.u[:, 0] - exact(sol.t))))
+        rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+        assert abs(np.mean(rates) - order) < 0.5
+
+
+def test_headline_config_newton_properties_at_full_size(M):
+    """BASELINE config C2 at its full size (n = 16, 20 000 nodes, MIRK6): too large for a dense
+    cross-check, so size-independent properties — Newton converges quadratically from the linear
+    guess, and the update satisfies the block equations L_i d_i + R_i d_{i+1} = Phi_i."""
+    from boundaryvaluediffeq_jl_b200 import configs
+    c = configs.c2_chain8()
+    cache = M.init(M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh), M.MIRK6(), adaptive=False)
+    r, nrm0 = cache.residual()
+    Lb, Rb, nodes, Bc = cache.jacobian_blocks()
+    st, d = cache.linear_solve()
+    assert st == 0
+    phi = r[8:8 + (c.N - 1) * 16].reshape(c.N - 1, 16)
+    lhs = np.einsum("ijk,ik->ij", Lb, d[:-1]) + np.einsum("ijk,ik->ij", Rb, d[1:])
+    assert np.max(np.abs(lhs - phi)) < 1e-9 * max(1.0, np.max(np.abs(phi)))
+    assert np.max(np.abs(d[0, :8] - r[:8])) < 1e-12 and np.max(np.abs(d[-1, :8] - r[-8:])) < 1e-12
+    norms = [nrm0]
+    for _ in range(3):
+        st, nrm = cache.newton_step()
+        assert st == 0
+        norms.append(nrm)
+    assert norms[-1] < 1e-8 and norms[2] < norms[1] ** 1.5
+    cache.close()
