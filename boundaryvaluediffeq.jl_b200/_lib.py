@@ -53,6 +53,7 @@ class EnsembleDesc(C.Structure):
 
 
 Handle = C.c_void_p
+i64 = C.c_int64
 
 # every symbol include/mirk_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -83,6 +84,13 @@ SYMBOLS = {
     "mirk_interp": (C.c_int, [Handle, dp, C.c_int32, C.c_int32, dp]),
     "mirk_bench_newton_steps": (C.c_int, [Handle, C.c_int32, fp, fp, C.POINTER(C.c_int64)]),
     "mirk_measure_peaks": (C.c_int, [C.c_int32, dp, dp]),
+    "mirk_ensemble_create": (C.c_int, [C.POINTER(EnsembleDesc), C.c_int64, C.POINTER(Handle)]),
+    "mirk_ensemble_destroy": (C.c_int, [Handle]),
+    "mirk_ensemble_set_inputs": (C.c_int, [Handle, dp, dp, C.c_int32]),
+    "mirk_ensemble_run": (C.c_int, [Handle, fp]),
+    "mirk_ensemble_get_results": (C.c_int, [Handle, ip, ip, ip, ip, dp, dp, dp]),
+    "mirk_ensemble_get_trajectory": (C.c_int, [Handle, C.c_int64, ip, dp, dp]),
+    "mirk_ensemble_solve": (C.c_int, [C.POINTER(EnsembleDesc), C.c_int64, dp, dp, C.c_int32, ip, ip, ip, dp]),
 }
 
 _lib = None

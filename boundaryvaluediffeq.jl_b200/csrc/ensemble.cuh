@@ -1,0 +1,623 @@
+// ensemble.cuh — K6: thousands of independent small BVPs, ONE THREAD PER TRAJECTORY, each running
+// the complete adaptive solve!  loop of lib/BoundaryValueDiffEqMIRK/src/mirk.jl:286-388 (Newton solve
+// -> defect estimate -> mesh selection -> re-interpolation, halving + zero guess on failure) with
+// exactly the control flow of the single-problem host driver in mirk_b200.cu.
+//
+// The reference runs an EnsembleProblem as a CPU-thread loop of full solves (SciMLBase; usage
+// lib/BoundaryValueDiffEqMIRK/test/Core/ensemble_tests.jl:20-38).  Here a trajectory's whole state
+// lives in a strided slab of HBM laid out trajectory-minor ("slot s of trajectory t" at
+// work[s * stride + t]), so the 32 lanes of a warp — 32 different BVPs walking their meshes in step —
+// read and write consecutive doubles.  Per Newton iteration a lane makes two sweeps over its mesh:
+// a residual sweep (Phi, stages, |F|_inf) and a Jacobian sweep that builds [L_i R_i] by dual numbers
+// in registers and merges it straight into the running almost-block-diagonal elimination (same
+// row-pivoted stacked elimination as abd.cuh, one group per segment between pinned nodes), so the
+// Jacobian blocks never touch memory; only the elimination factors (2 n^2 + n per node) do.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace mirk {
+
+// SciMLBase.ReturnCode values (same numbers as MIRK_RET_* in include/mirk_b200.h)
+constexpr int MIRK_RET_SUCCESS_ = 0, MIRK_RET_FAILURE_ = 1, MIRK_RET_MAXITERS_ = 2, MIRK_RET_UNSTABLE_ = 3;
+
+struct EnsArgs {
+    long long ntraj;
+    long long stride;      // >= ntraj, trajectories per slot row
+    int NC;                // node capacity per trajectory
+    int N0;                // initial nodes
+    const double* mesh0;   // [N0] shared initial mesh
+    const double* params;  // [ntraj][np]
+    const double* u0;      // [n] or [ntraj][n]
+    int u0_per_traj;
+    double abstol, defect_threshold;
+    int adaptive, max_sub, maxiters, reinterp_inplace, max_outer;
+    double* work;
+    // per-trajectory results
+    int* retcode;
+    int* n_mesh;
+    int* newton_iters;
+    int* outer_iters;
+    double* resid_norm;
+    double* defect_norm;
+};
+
+template <class P, int ORDER> struct EnsLayout {
+    using TB = Tableau<ORDER>;
+    static constexpr int n = P::n, s = TB::s, si = TB::si;
+    // slot offsets as multiples of NC
+    static constexpr int oMESH = 0, oMESH2 = 1, oY = 2, oY2 = oY + n, oYB = oY2 + n, oKD = oYB + n,
+                         oKI = oKD + s * n, oEST = oKI + si * n, oPHI = oEST + 1, oTL = oPHI + n,
+                         oTR = oTL + n * n, oRT = oTR + n * n, oEND = oRT + n;
+    static constexpr int slots_per_node = oEND;
+};
+
+// NaN-propagating max of |x|
+__device__ __forceinline__ double nmax(double m, double x) {
+    const double a = fabs(x);
+    return !(a <= m) ? a : m;
+}
+
+constexpr int ens_unroll(int n) { return n <= 2 ? 64 : 1; }
+
+template <class P, int ORDER> struct EnsSolver {
+    using TB = Tableau<ORDER>;
+    using LY = EnsLayout<P, ORDER>;
+    static constexpr int n = P::n, s = TB::s, si = TB::si, L = P::n_bc, rows = 2 * n, cols = 3 * n + 1;
+    static constexpr int QMAX = P::max_bc_pts + 2, DMAX = QMAX * n;
+    static constexpr int UF = ens_unroll(P::n);
+
+    double* B;
+    size_t st;
+    int NC, N;
+    double p[P::np > 0 ? P::np : 1];
+
+#define SLOT(off, idx) B[((size_t)(off) * NC + (size_t)(idx)) * st]
+#define MESH(i) SLOT(LY::oMESH, i)
+#define MESH2(i) SLOT(LY::oMESH2, i)
+#define Y(i, k) SLOT(LY::oY + (k), i)
+#define Y2(i, k) SLOT(LY::oY2 + (k), i)
+#define YB(i, k) SLOT(LY::oYB + (k), i)
+#define KD(i, r, k) SLOT(LY::oKD + (r) * n + (k), i)
+#define KI(i, r, k) SLOT(LY::oKI + (r) * n + (k), i)
+#define EST(i) SLOT(LY::oEST, i)
+#define PHI(i, k) SLOT(LY::oPHI + (k), i)
+#define TLF(i, q, k) SLOT(LY::oTL + (q) * n + (k), i)
+#define TRF(i, q, k) SLOT(LY::oTR + (q) * n + (k), i)
+#define RTF(i, q) SLOT(LY::oRT + (q), i)
+
+    __device__ int interval_strided(double t) const {
+        int lo = 0, hi = N;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (MESH(mid) < t) lo = mid + 1; else hi = mid;
+        }
+        int j = lo;
+        if (j < 1) j = 1;
+        if (j > N - 1) j = N - 1;
+        return j - 1;
+    }
+    // interpolation stages of interval i from the stored discrete stages (Appendix A.3)
+    __device__ __noinline__ void interp_stages_at(int i, double* Kl /*[s*n]*/, double* KIl /*[si*n]*/, double* yi,
+                                                  double* yi1, double& ti, double& h) const {
+        ti = MESH(i);
+        h = MESH(i + 1) - ti;
+#pragma unroll
+        for (int k = 0; k < n; k++) { yi[k] = Y(i, k); yi1[k] = Y(i + 1, k); }
+#pragma unroll
+        for (int r = 0; r < s; r++)
+#pragma unroll
+            for (int k = 0; k < n; k++) Kl[r * n + k] = KD(i, r, k);
+        interp_stages_interval<P, ORDER>(yi, yi1, h, ti, p, Kl, KIl);
+    }
+    // boundary evaluation points: U[k] = sol(times[k]) with the end-point short cut; nodes[k] as k_bc
+    __device__ __noinline__ int bc_gather(double* U, int* nodes) const {
+        double tm[P::max_bc_pts];
+        int m;
+        const double t0 = MESH(0), t1 = MESH(N - 1);
+        if (P::problem_type == 1) { m = 2; tm[0] = t0; tm[1] = t1; }
+        else m = P::bc_times(tm, p, t0, t1);
+        for (int k = 0; k < m; k++) {
+            const double t = tm[k];
+            if (t == t0) {
+                nodes[k] = 0;
+                for (int c = 0; c < n; c++) U[k * n + c] = Y(0, c);
+            } else if (t == t1) {
+                nodes[k] = N - 1;
+                for (int c = 0; c < n; c++) U[k * n + c] = Y(N - 1, c);
+            } else {
+                const int i = interval_strided(t);
+                nodes[k] = i;
+                double Kl[s * n], KIl[si * n], yi[n], yi1[n], ti, h;
+                interp_stages_at(i, Kl, KIl, yi, yi1, ti, h);
+                const double tau = (t - ti) / h;
+                double w[TB::s_star], wp[TB::s_star];
+                TB::weights(tau, w, wp);
+                for (int c = 0; c < n; c++) {
+                    double z = 0.0;
+#pragma unroll
+                    for (int r = 0; r < s; r++) z += Kl[r * n + c] * w[r];
+#pragma unroll
+                    for (int r = 0; r < si; r++) z += KIl[r * n + c] * w[s + r];
+                    U[k * n + c] = z * h + yi[c];
+                }
+            }
+        }
+        return m;
+    }
+    // F(y): Phi and stages for every interval, boundary rows; returns |F|_inf, bc rows in rbc
+    __device__ __noinline__ double residual_sweep(double* rbc) {
+        double nrm = 0.0;
+        double yi[n], yi1[n];
+#pragma unroll
+        for (int k = 0; k < n; k++) yi1[k] = Y(0, k);
+        double tn = MESH(0);
+        for (int i = 0; i < N - 1; i++) {
+            const double ti = tn;
+            tn = MESH(i + 1);
+#pragma unroll
+            for (int k = 0; k < n; k++) { yi[k] = yi1[k]; yi1[k] = Y(i + 1, k); }
+            double K[s][n], phi[n];
+            phi_interval<P, ORDER, double>(yi, yi1, tn - ti, ti, p, K, phi);
+#pragma unroll
+            for (int r = 0; r < s; r++)
+#pragma unroll
+                for (int k = 0; k < n; k++) KD(i, r, k) = K[r][k];
+#pragma unroll
+            for (int k = 0; k < n; k++) { PHI(i, k) = phi[k]; nrm = nmax(nrm, phi[k]); }
+        }
+        double U[P::max_bc_pts * n];
+        int nodes[P::max_bc_pts];
+        bc_gather(U, nodes);
+        P::template bc<double>(rbc, U, p);
+        for (int q = 0; q < L; q++) nrm = nmax(nrm, rbc[q]);
+        return nrm;
+    }
+
+    // J(y) delta = F(y), y -= delta.  Returns false on a singular block.
+    __device__ __noinline__ bool newton_update(const double* rbc) {
+        double U[P::max_bc_pts * n];
+        int bcn[P::max_bc_pts], kept[QMAX];
+        const int m = bc_gather(U, bcn);
+        int Q = 0;
+        kept[Q++] = 0;
+        // sorted unique union of {0, N-1} and the boundary nodes (tiny insertion sort)
+        for (int k = 0; k < m; k++) {
+            const int v = bcn[k];
+            bool found = false;
+            for (int e = 0; e < Q; e++) found = found || kept[e] == v;
+            if (!found && v != N - 1) kept[Q++] = v;
+        }
+        kept[Q++] = N - 1;
+        for (int e = 1; e < Q - 1; e++)
+            for (int f = e + 1; f < Q - 1; f++)
+                if (kept[f] < kept[e]) { const int t_ = kept[e]; kept[e] = kept[f]; kept[f] = t_; }
+        // closing matrix, boundary rows first
+        double M[DMAX][DMAX + 1];
+        const int D = Q * n;
+        for (int r = 0; r < D; r++)
+            for (int c = 0; c <= D; c++) M[r][c] = 0.0;
+        for (int d = 0; d < m * n; d++) {
+            Dual Ud[P::max_bc_pts * n], rd[L];
+            for (int e = 0; e < m * n; e++) Ud[e] = Dual(U[e], e == d ? 1.0 : 0.0);
+            P::template bc<Dual>(rd, Ud, p);
+            const int k = d / n, c = d % n;
+            int slot = 0;
+            for (int e = 0; e < Q; e++) if (kept[e] == bcn[k]) slot = e;
+            for (int q = 0; q < L; q++) M[q][slot * n + c] += rd[q].d;
+        }
+        for (int q = 0; q < L; q++) M[q][D] = rbc[q];
+
+        // Jacobian sweep fused with the elimination
+        double W[rows][cols];
+        int seg = 0;
+        double yv[n], yv1[n];
+#pragma unroll (UF)
+        for (int k = 0; k < n; k++) yv1[k] = Y(0, k);
+        double tn = MESH(0);
+        for (int i = 0; i < N - 1; i++) {
+            const double ti = tn;
+            tn = MESH(i + 1);
+            const double h = tn - ti;
+#pragma unroll (UF)
+            for (int k = 0; k < n; k++) { yv[k] = yv1[k]; yv1[k] = Y(i + 1, k); }
+            double Lm[n][n], Rm[n][n];
+#pragma unroll (UF)
+            for (int d = 0; d < 2 * n; d++) {
+                Dual yi[n], yi1[n], K[s][n], phi[n];
+#pragma unroll (UF)
+                for (int k = 0; k < n; k++) {
+                    yi[k] = Dual(yv[k], k == d ? 1.0 : 0.0);
+                    yi1[k] = Dual(yv1[k], (n + k) == d ? 1.0 : 0.0);
+                }
+                phi_interval<P, ORDER, Dual>(yi, yi1, h, ti, p, K, phi);
+#pragma unroll (UF)
+                for (int k = 0; k < n; k++) {
+                    if (d < n) Lm[k][d < n ? d : 0] = phi[k].d;
+                    else Rm[k][d >= n ? d - n : 0] = phi[k].d;
+                }
+            }
+            const bool start = (i == kept[seg]);
+            if (start) {
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+#pragma unroll (UF)
+                    for (int k = 0; k < n; k++) { W[q][k] = Rm[q][k]; W[q][n + k] = Lm[q][k]; W[q][2 * n + k] = 0.0; }
+                    W[q][3 * n] = PHI(i, q);
+                }
+            } else {
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+#pragma unroll (UF)
+                    for (int k = 0; k < n; k++) { W[n + q][k] = Lm[q][k]; W[n + q][n + k] = 0.0; W[n + q][2 * n + k] = Rm[q][k]; }
+                    W[n + q][3 * n] = PHI(i, q);
+                }
+                // row-pivoted Gauss-Jordan on the n E-columns, pivot row swapped into place
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+                    int pr = q;
+                    double best = fabs(W[q][q]);
+#pragma unroll (UF)
+                    for (int r = q + 1; r < rows; r++) {
+                        const double av = fabs(W[r][q]);
+                        if (av > best || !(av == av)) { best = av; pr = r; }
+                    }
+                    if (!(best > 0.0) || !(best < INFINITY)) return false;
+#pragma unroll (UF)
+                    for (int r = q + 1; r < rows; r++) {
+                        if (pr == r) {
+#pragma unroll (UF)
+                            for (int c = q; c < cols; c++) { const double t_ = W[q][c]; W[q][c] = W[r][c]; W[r][c] = t_; }
+                        }
+                    }
+                    const double inv = 1.0 / W[q][q];
+#pragma unroll (UF)
+                    for (int c = q + 1; c < cols; c++) W[q][c] *= inv;
+#pragma unroll (UF)
+                    for (int r = 0; r < rows; r++) {
+                        if (r != q) {
+                            const double mlt = W[r][q];
+#pragma unroll (UF)
+                            for (int c = q + 1; c < cols; c++) W[r][c] = fma(-mlt, W[q][c], W[r][c]);
+                        }
+                    }
+                }
+                // factors of node i: d_i = rt - TL d_a - TR d_{i+1}
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+#pragma unroll (UF)
+                    for (int k = 0; k < n; k++) { TLF(i, q, k) = W[q][n + k]; TRF(i, q, k) = W[q][2 * n + k]; }
+                    RTF(i, q) = W[q][3 * n];
+                }
+                // survivors become the carried rows: E <- B, B <- 0
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+#pragma unroll (UF)
+                    for (int k = 0; k < n; k++) { W[q][k] = W[n + q][2 * n + k]; W[q][n + k] = W[n + q][n + k]; W[q][2 * n + k] = 0.0; }
+                    W[q][3 * n] = W[n + q][3 * n];
+                }
+            }
+            if (i + 1 == kept[seg + 1]) {  // segment closed: relation (kept[seg], kept[seg+1])
+                for (int q = 0; q < n; q++) {
+                    const int r = L + seg * n + q;
+                    for (int k = 0; k < n; k++) { M[r][seg * n + k] = W[q][n + k]; M[r][(seg + 1) * n + k] = W[q][k]; }
+                    M[r][D] = W[q][3 * n];
+                }
+                seg++;
+            }
+        }
+        // closing solve: dense Gauss-Jordan with row pivoting on D unknowns
+        for (int q = 0; q < D; q++) {
+            int pr = q;
+            double best = fabs(M[q][q]);
+            for (int r = q + 1; r < D; r++) {
+                const double av = fabs(M[r][q]);
+                if (av > best || !(av == av)) { best = av; pr = r; }
+            }
+            if (!(best > 0.0) || !(best < INFINITY)) return false;
+            if (pr != q)
+                for (int c = q; c <= D; c++) { const double t_ = M[q][c]; M[q][c] = M[pr][c]; M[pr][c] = t_; }
+            const double inv = 1.0 / M[q][q];
+            for (int c = q + 1; c <= D; c++) M[q][c] *= inv;
+            for (int r = 0; r < D; r++) {
+                if (r != q) {
+                    const double mlt = M[r][q];
+                    for (int c = q + 1; c <= D; c++) M[r][c] = fma(-mlt, M[q][c], M[r][c]);
+                }
+            }
+        }
+        // back substitution segment by segment, fused with y -= delta
+        for (int sg = Q - 2; sg >= 0; sg--) {
+            double da[n], dr[n];
+#pragma unroll (UF)
+            for (int k = 0; k < n; k++) { da[k] = M[sg * n + k][D]; dr[k] = M[(sg + 1) * n + k][D]; }
+            for (int c = kept[sg + 1] - 1; c > kept[sg]; c--) {
+                double dc[n];
+#pragma unroll (UF)
+                for (int q = 0; q < n; q++) {
+                    double acc = RTF(c, q);
+#pragma unroll (UF)
+                    for (int k = 0; k < n; k++) acc -= TLF(c, q, k) * da[k] + TRF(c, q, k) * dr[k];
+                    dc[q] = acc;
+                }
+#pragma unroll (UF)
+                for (int k = 0; k < n; k++) { Y(c, k) -= dc[k]; dr[k] = dc[k]; }
+            }
+        }
+        for (int e = 0; e < Q; e++)
+#pragma unroll (UF)
+            for (int k = 0; k < n; k++) Y(kept[e], k) -= M[e * n + k][D];
+        return true;
+    }
+
+    // ---- adaptive outer loop (same control flow as mirk_solve in mirk_b200.cu) -----------------
+    __device__ void run(const EnsArgs& a, long long tid) {
+    const double abstol = a.abstol;
+    int info = MIRK_RET_SUCCESS_, newton_total = 0, outer = 0;
+    double error_norm = 2.0 * abstol, resid_norm = 0.0;
+    do {
+        // -- Newton solve with best-iterate bookkeeping
+        int ret = MIRK_RET_MAXITERS_, it = 0;
+        double best = INFINITY;
+        bool have_best = false;
+        double rbc[L];
+        double nrm = residual_sweep(rbc);
+        while (it < a.maxiters) {
+            if (!newton_update(rbc)) { ret = MIRK_RET_FAILURE_; break; }
+            it++;
+            nrm = residual_sweep(rbc);
+            if (!(fabs(nrm) < INFINITY)) { ret = MIRK_RET_UNSTABLE_; break; }
+            if (nrm < best) {
+                best = nrm;
+                have_best = true;
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int k = 0; k < n; k++) YB(i, k) = Y(i, k);
+            }
+            if (nrm <= abstol) { ret = MIRK_RET_SUCCESS_; break; }
+        }
+        if (ret != MIRK_RET_SUCCESS_ && it > 0 && have_best && ret != MIRK_RET_FAILURE_) {
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int k = 0; k < n; k++) Y(i, k) = YB(i, k);
+            nrm = residual_sweep(rbc);
+        }
+        resid_norm = nrm;
+        newton_total += it;
+        error_norm = 2.0 * abstol;
+        info = ret;
+        outer++;
+        if (!a.adaptive) break;
+        if (info == MIRK_RET_SUCCESS_) {
+            // -- defect estimate (Appendix A.5), keeps the interpolation stages for the re-interpolation
+            double defect = 0.0;
+            for (int i = 0; i < N - 1; i++) {
+                double Kl[s * n], KIl[si * n], yi[n], yi1[n], ti, h;
+                interp_stages_at(i, Kl, KIl, yi, yi1, ti, h);
+#pragma unroll
+                for (int r = 0; r < si; r++)
+#pragma unroll
+                    for (int k = 0; k < n; k++) KI(i, r, k) = KIl[r * n + k];
+                double e12[2];
+#pragma unroll
+                for (int smp = 0; smp < 2; smp++) {
+                    const double tau = smp ? (1.0 - TB::tau_star()) : TB::tau_star();
+                    double w[TB::s_star], wp[TB::s_star], z[n], zp[n], g[n];
+                    TB::weights(tau, w, wp);
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+                        double za = 0.0, zb = 0.0;
+#pragma unroll
+                        for (int r = 0; r < s; r++) { za += Kl[r * n + k] * w[r]; zb += Kl[r * n + k] * wp[r]; }
+#pragma unroll
+                        for (int r = 0; r < si; r++) { za += KIl[r * n + k] * w[s + r]; zb += KIl[r * n + k] * wp[s + r]; }
+                        z[k] = za * h + yi[k];
+                        zp[k] = zb;
+                    }
+                    P::template f<double>(g, z, p, ti + tau * h);
+                    double e = 0.0;
+                    bool isnan_ = false;
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+                        const double dd = (zp[k] - g[k]) / (fabs(g[k]) + 1.0);
+                        if (fabs(dd) > e) e = fabs(dd);
+                        isnan_ = isnan_ || !(dd == dd);
+                    }
+                    e12[smp] = isnan_ ? NAN : e;
+                }
+                // the kept sample is the larger one; its norm is all the mesh selector needs
+                const double em = (e12[0] > e12[1]) ? e12[0] : e12[1];
+                EST(i) = em;
+                defect = !(em <= defect) ? em : defect;
+            }
+            error_norm = defect;
+            if (!(error_norm <= a.defect_threshold)) info = MIRK_RET_FAILURE_;
+            if (info == MIRK_RET_SUCCESS_ && error_norm > abstol) {
+                // -- mesh selection (Appendix A.6), sequential like the reference
+                const int ni = N - 1;
+                const double ex = 1.0 / (double)(ORDER + 1);
+                double r1 = 0.0, r2 = 0.0;
+                for (int i = 0; i < ni; i++) {
+                    const double sh = pow(EST(i) / abstol, ex);
+                    EST(i) = sh;
+                    if (sh > r1) r1 = sh;
+                    r2 += sh;
+                }
+                const double r3 = r2 / ni;
+                long long n_predict = (long long)nearbyint(1.3 * r2 + 1.0);
+                const double n_ = 0.1 * ni;
+                if (fabs((double)(n_predict - ni)) < n_) n_predict = (long long)nearbyint(ni + n_);
+                int ns;
+                bool halve = false;
+                if (r1 <= 1.0 * r3) { ns = 2 * ni; halve = true; }
+                else {
+                    const long long lb = N / 2, ub = 4LL * ni;
+                    ns = (int)(n_predict < lb ? lb : (n_predict > ub ? ub : n_predict));
+                }
+                if (ns > a.max_sub || ns + 1 > NC) {
+                    info = MIRK_RET_FAILURE_;
+                } else {
+                    if (halve) {
+                        for (int i = 0; i < ni; i++) {
+                            const double m0 = MESH(i), m1 = MESH(i + 1);
+                            MESH2(2 * i) = m0;
+                            MESH2(2 * i + 1) = (m1 + m0) / 2.0;
+                        }
+                        MESH2(2 * ni) = MESH(ni);
+                    } else {
+                        const double tend = MESH(ni);
+                        for (int i = 0; i <= ns; i++) MESH2(i) = (i < N) ? MESH(i) : tend;
+                        double tot = 0.0;
+                        for (int i = 0; i < ni; i++) {
+                            const double hh = MESH(i + 1) - MESH(i);
+                            const double sh = EST(i) / hh;
+                            EST(i) = sh;
+                            tot += sh * hh;
+                        }
+                        const double zeta = tot / (double)ns;
+                        int k = 0;
+                        long long i = 0;
+                        double t = MESH(0), integral = 0.0;
+                        MESH2(0) = t;
+                        double shk = EST(0), mk1 = MESH(1);
+                        while (k < ni) {
+                            const double next_piece = shk * (mk1 - t);
+                            const double int_next = integral + next_piece;
+                            if (int_next > zeta) {
+                                const double tn2 = (zeta - integral) / shk + t;
+                                if (i + 1 <= ns) MESH2(i + 1) = tn2;
+                                t = tn2;
+                                i++;
+                                integral = 0.0;
+                            } else {
+                                integral = int_next;
+                                t = mk1;
+                                k++;
+                                if (k < ni) { shk = EST(k); mk1 = MESH(k + 1); }
+                            }
+                        }
+                        MESH2(ns) = tend;
+                    }
+                    // -- new guess: old interpolant at the new nodes (Appendix A.7)
+                    const int Nn = ns + 1;
+                    for (int j = 0; j < Nn; j++) {
+                        const double t = MESH2(j);
+                        const int i = interval_strided(t);
+                        const double ti = MESH(i), h = MESH(i + 1) - ti, tau = (t - ti) / h;
+                        double w[TB::s_star], wp[TB::s_star];
+                        TB::weights(tau, w, wp);
+#pragma unroll
+                        for (int k = 0; k < n; k++) {
+                            double z = 0.0;
+#pragma unroll
+                            for (int r = 0; r < s; r++) z += KD(i, r, k) * w[r];
+#pragma unroll
+                            for (int r = 0; r < si; r++) z += KI(i, r, k) * w[s + r];
+                            // quirk Q3: the reference adds the base from the array it is rewriting
+                            const double base = (a.reinterp_inplace && i < j) ? Y2(i, k) : Y(i, k);
+                            Y2(j, k) = z * h + base;
+                        }
+                    }
+                    for (int j = 0; j < Nn; j++) {
+                        MESH(j) = MESH2(j);
+#pragma unroll
+                        for (int k = 0; k < n; k++) Y(j, k) = Y2(j, k);
+                    }
+                    N = Nn;
+                }
+                continue;
+            }
+        }
+        if (info != MIRK_RET_SUCCESS_) {
+            // mirk.jl:374-385: halve the mesh, zero the guess, restart (quirk Q4)
+            if (2 * (N - 1) > a.max_sub || 2 * (N - 1) + 1 > NC) {
+                info = MIRK_RET_FAILURE_;
+            } else {
+                const int ni = N - 1;
+                for (int i = 0; i < ni; i++) {
+                    const double m0 = MESH(i), m1 = MESH(i + 1);
+                    MESH2(2 * i) = m0;
+                    MESH2(2 * i + 1) = (m1 + m0) / 2.0;
+                }
+                MESH2(2 * ni) = MESH(ni);
+                N = 2 * ni + 1;
+                for (int j = 0; j < N; j++) {
+                    MESH(j) = MESH2(j);
+#pragma unroll
+                    for (int k = 0; k < n; k++) Y(j, k) = 0.0;
+                }
+                info = MIRK_RET_SUCCESS_;
+            }
+        }
+    } while (info == MIRK_RET_SUCCESS_ && error_norm > abstol && outer < a.max_outer);
+    if (info == MIRK_RET_SUCCESS_ && a.adaptive && error_norm > abstol) info = MIRK_RET_MAXITERS_;
+    a.retcode[tid] = info;
+    a.n_mesh[tid] = N;
+    a.newton_iters[tid] = newton_total;
+    a.outer_iters[tid] = outer;
+    a.resid_norm[tid] = resid_norm;
+    a.defect_norm[tid] = error_norm;
+    }
+};
+
+template <class P, int ORDER>
+__global__ void __launch_bounds__(64)
+k_ensemble_solve(EnsArgs a) {
+    using ES = EnsSolver<P, ORDER>;
+    using LY = EnsLayout<P, ORDER>;
+    constexpr int n = P::n;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.ntraj) return;
+    ES S;
+    S.B = a.work + tid;
+    S.st = (size_t)a.stride;
+    S.NC = a.NC;
+    S.N = a.N0;
+#pragma unroll
+    for (int k = 0; k < P::np; k++) S.p[k] = a.params[tid * P::np + k];
+    {
+        double* const B = S.B;
+        const size_t st = S.st;
+        const int NC = S.NC;
+        for (int i = 0; i < S.N; i++) {
+            MESH(i) = a.mesh0[i];
+            for (int k = 0; k < n; k++) Y(i, k) = a.u0[(a.u0_per_traj ? tid * n : 0) + k];
+        }
+    }
+    S.run(a, tid);
+}
+#undef SLOT
+#undef MESH
+#undef MESH2
+#undef Y
+#undef Y2
+#undef YB
+#undef KD
+#undef KI
+#undef EST
+#undef PHI
+#undef TLF
+#undef TRF
+#undef RTF
+
+// gather one trajectory's mesh and node values out of the strided slab: out_mesh[NC], out_y[NC][n]
+static __global__ void k_ensemble_extract(long long stride, int NC, int n, int oMESH, int oY, const double* __restrict__ work,
+                                   long long traj, int N, double* __restrict__ out_mesh, double* __restrict__ out_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double* B = work + traj;
+    out_mesh[i] = B[((size_t)oMESH * NC + i) * (size_t)stride];
+    for (int k = 0; k < n; k++) out_y[(size_t)i * n + k] = B[((size_t)(oY + k) * NC + i) * (size_t)stride];
+}
+
+// y at node 0 of every trajectory (what SciML ensemble reductions typically read): out[ntraj][n]
+static __global__ void k_ensemble_first(long long ntraj, long long stride, int NC, int n, int oY, const double* __restrict__ work,
+                                 double* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntraj) return;
+    for (int k = 0; k < n; k++) out[t * n + k] = work[((size_t)(oY + k) * NC) * (size_t)stride + t];
+}
+
+}  // namespace mirk

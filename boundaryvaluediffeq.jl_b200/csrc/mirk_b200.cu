@@ -19,6 +19,7 @@
 
 #include "abd.cuh"
 #include "abd_warp.cuh"
+#include "ensemble.cuh"
 #include "generic_kernels.cuh"
 #include "mirk_b200.h"
 #include "ops.cuh"
@@ -991,6 +992,193 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
     if (launches) *launches = S->launches - l0;
     CKS(read_words(S));
     return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
+}
+
+}  // extern "C"
+
+// ---- ensembles: SciMLBase EnsembleProblem over MIRK (usage MIRK/test/Core/ensemble_tests.jl:20-38) --
+struct mirk_ensemble_s {
+    mirk_ensemble_desc desc;
+    const EnsembleOps* ops = nullptr;
+    int64_t ntraj = 0, stride = 0;
+    int NC = 0, N0 = 0;
+    cudaStream_t st = nullptr;
+    double *work = nullptr, *params = nullptr, *u0 = nullptr, *mesh0 = nullptr, *resid_norm = nullptr,
+           *defect_norm = nullptr, *y_first = nullptr, *tmesh = nullptr, *ty = nullptr;
+    int *retcode = nullptr, *n_mesh = nullptr, *newton_iters = nullptr, *outer_iters = nullptr;
+    int u0_per_traj = 0;
+    bool have_inputs = false, ran = false;
+};
+
+static const EnsembleOps* find_ensemble_ops(int id, int order) {
+    if (id >= 0 && id <= problems::kLayer) return ensemble_ops_small(id, order);
+    return nullptr;
+}
+
+extern "C" {
+
+int mirk_ensemble_destroy(mirk_ensemble_handle E) {
+    if (!E) return MIRK_OK;
+    cudaSetDevice(E->desc.device);
+    if (E->st) cudaStreamSynchronize(E->st);
+    dfree(E->work); dfree(E->params); dfree(E->u0); dfree(E->mesh0); dfree(E->resid_norm); dfree(E->defect_norm);
+    dfree(E->y_first); dfree(E->tmesh); dfree(E->ty); dfree(E->retcode); dfree(E->n_mesh); dfree(E->newton_iters);
+    dfree(E->outer_iters);
+    if (E->st) cudaStreamDestroy(E->st);
+    delete E;
+    return MIRK_OK;
+}
+
+int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ensemble_handle* out) {
+    if (!desc || !out) return fail(MIRK_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (ntraj < 1) return fail(MIRK_ERR_ARG, "trajectories must be >= 1");
+    if (desc->order != 4 && desc->order != 6) return fail(MIRK_ERR_UNSUPPORTED, "order must be 4 (MIRK4) or 6 (MIRK6)");
+    if (!(desc->dt > 0)) return fail(MIRK_ERR_ARG, "dt must be positive");
+    if (!(desc->t1 > desc->t0)) return fail(MIRK_ERR_ARG, "tspan must be increasing");
+    if (!(desc->abstol > 0)) return fail(MIRK_ERR_ARG, "abstol must be positive");
+    const EnsembleOps* ops = find_ensemble_ops(desc->problem_id, desc->order);
+    if (!ops) return fail(MIRK_ERR_UNSUPPORTED, "no batched ensemble kernel for this problem (needs n <= 6)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MIRK_ERR_NO_DEVICE, "no CUDA device: libmirkb200 has no CPU fallback");
+    }
+    if (desc->device < 0 || desc->device >= count) return fail(MIRK_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(desc->device));
+    const int nint = (int)ceil((desc->t1 - desc->t0) / desc->dt);  // cld(t1 - t0, dt), CORE/utils.jl:362
+    const int N0 = nint + 1;
+    int NC = desc->node_cap > 0 ? desc->node_cap : 128;
+    if (NC < N0) NC = N0;
+    mirk_ensemble_s* E = new mirk_ensemble_s();
+    E->desc = *desc;
+    E->ops = ops;
+    E->ntraj = ntraj;
+    E->stride = (ntraj + 31) / 32 * 32;
+    E->NC = NC;
+    E->N0 = N0;
+#define CKE(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e2 = (call);                                                        \
+        if (e2 != cudaSuccess) {                                                        \
+            mirk_ensemble_destroy(E);                                                   \
+            return fail(MIRK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2)); \
+        }                                                                               \
+    } while (0)
+    CKE(cudaStreamCreateWithFlags(&E->st, cudaStreamNonBlocking));
+    CKE(dalloc(&E->work, (size_t)ops->slots_per_node * NC * (size_t)E->stride));
+    CKE(dalloc(&E->params, (size_t)ntraj * std::max(ops->np, 1)));
+    CKE(dalloc(&E->u0, (size_t)ntraj * ops->n));
+    CKE(dalloc(&E->mesh0, (size_t)N0));
+    CKE(dalloc(&E->resid_norm, (size_t)ntraj));
+    CKE(dalloc(&E->defect_norm, (size_t)ntraj));
+    CKE(dalloc(&E->y_first, (size_t)ntraj * ops->n));
+    CKE(dalloc(&E->tmesh, (size_t)NC));
+    CKE(dalloc(&E->ty, (size_t)NC * ops->n));
+    CKE(dalloc(&E->retcode, (size_t)ntraj));
+    CKE(dalloc(&E->n_mesh, (size_t)ntraj));
+    CKE(dalloc(&E->newton_iters, (size_t)ntraj));
+    CKE(dalloc(&E->outer_iters, (size_t)ntraj));
+    std::vector<double> mesh(N0);
+    mirk_mesh_uniform_fill(desc->t0, desc->t1, nint, mesh.data());
+    CKE(cudaMemcpy(E->mesh0, mesh.data(), sizeof(double) * N0, cudaMemcpyHostToDevice));
+#undef CKE
+    *out = E;
+    return MIRK_OK;
+}
+
+int mirk_ensemble_set_inputs(mirk_ensemble_handle E, const double* params, const double* u0, int32_t u0_per_traj) {
+    if (!E || !u0 || (E->ops->np > 0 && !params)) return fail(MIRK_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(E->desc.device));
+    if (E->ops->np > 0)
+        CK(cudaMemcpyAsync(E->params, params, sizeof(double) * (size_t)E->ntraj * E->ops->np, cudaMemcpyHostToDevice, E->st));
+    CK(cudaMemcpyAsync(E->u0, u0, sizeof(double) * (size_t)(u0_per_traj ? E->ntraj : 1) * E->ops->n,
+                       cudaMemcpyHostToDevice, E->st));
+    CK(cudaStreamSynchronize(E->st));
+    E->u0_per_traj = u0_per_traj ? 1 : 0;
+    E->have_inputs = true;
+    return MIRK_OK;
+}
+
+int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
+    if (!E) return fail(MIRK_ERR_ARG, "NULL handle");
+    if (!E->have_inputs) return fail(MIRK_ERR_STATE, "no inputs set");
+    CK(cudaSetDevice(E->desc.device));
+    EnsArgs a;
+    a.ntraj = E->ntraj; a.stride = E->stride; a.NC = E->NC; a.N0 = E->N0;
+    a.mesh0 = E->mesh0; a.params = E->params; a.u0 = E->u0; a.u0_per_traj = E->u0_per_traj;
+    a.abstol = E->desc.abstol; a.defect_threshold = E->desc.defect_threshold;
+    a.adaptive = E->desc.adaptive; a.max_sub = E->desc.max_num_subintervals;
+    a.maxiters = E->desc.maxiters < 0 ? 0 : E->desc.maxiters; a.reinterp_inplace = E->desc.reinterp_inplace;
+    a.max_outer = 100;
+    a.work = E->work;
+    a.retcode = E->retcode; a.n_mesh = E->n_mesh; a.newton_iters = E->newton_iters; a.outer_iters = E->outer_iters;
+    a.resid_norm = E->resid_norm; a.defect_norm = E->defect_norm;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, E->st));
+    E->ops->run(E->st, a);
+    k_ensemble_first<<<(unsigned)((E->ntraj + 255) / 256), 256, 0, E->st>>>(E->ntraj, E->stride, E->NC, E->ops->n,
+                                                                          E->ops->oY, E->work, E->y_first);
+    CK(cudaEventRecord(e1, E->st));
+    CKS(launch_check("ensemble"));
+    CK(cudaStreamSynchronize(E->st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    E->ran = true;
+    return MIRK_OK;
+}
+
+int mirk_ensemble_get_results(mirk_ensemble_handle E, int32_t* retcodes, int32_t* n_mesh, int32_t* newton_iters,
+                              int32_t* outer_iters, double* resid_norm, double* defect_norm, double* y_first) {
+    if (!E) return fail(MIRK_ERR_ARG, "NULL handle");
+    if (!E->ran) return fail(MIRK_ERR_STATE, "ensemble has not been run");
+    CK(cudaSetDevice(E->desc.device));
+    const size_t nt = (size_t)E->ntraj;
+    if (retcodes) CK(cudaMemcpyAsync(retcodes, E->retcode, sizeof(int) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (n_mesh) CK(cudaMemcpyAsync(n_mesh, E->n_mesh, sizeof(int) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (newton_iters) CK(cudaMemcpyAsync(newton_iters, E->newton_iters, sizeof(int) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (outer_iters) CK(cudaMemcpyAsync(outer_iters, E->outer_iters, sizeof(int) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (resid_norm) CK(cudaMemcpyAsync(resid_norm, E->resid_norm, sizeof(double) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (defect_norm) CK(cudaMemcpyAsync(defect_norm, E->defect_norm, sizeof(double) * nt, cudaMemcpyDeviceToHost, E->st));
+    if (y_first) CK(cudaMemcpyAsync(y_first, E->y_first, sizeof(double) * nt * E->ops->n, cudaMemcpyDeviceToHost, E->st));
+    CK(cudaStreamSynchronize(E->st));
+    return MIRK_OK;
+}
+
+int mirk_ensemble_get_trajectory(mirk_ensemble_handle E, int64_t traj, int32_t* n_mesh, double* mesh, double* y) {
+    if (!E || !n_mesh) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (!E->ran) return fail(MIRK_ERR_STATE, "ensemble has not been run");
+    if (traj < 0 || traj >= E->ntraj) return fail(MIRK_ERR_ARG, "trajectory index out of range");
+    CK(cudaSetDevice(E->desc.device));
+    int N = 0;
+    CK(cudaMemcpyAsync(&N, E->n_mesh + traj, sizeof(int), cudaMemcpyDeviceToHost, E->st));
+    CK(cudaStreamSynchronize(E->st));
+    *n_mesh = N;
+    if (mesh || y) {
+        k_ensemble_extract<<<(N + 127) / 128, 128, 0, E->st>>>(E->stride, E->NC, E->ops->n, E->ops->oMESH, E->ops->oY,
+                                                               E->work, traj, N, E->tmesh, E->ty);
+        CKS(launch_check("ensemble_extract"));
+        if (mesh) CK(cudaMemcpyAsync(mesh, E->tmesh, sizeof(double) * N, cudaMemcpyDeviceToHost, E->st));
+        if (y) CK(cudaMemcpyAsync(y, E->ty, sizeof(double) * (size_t)N * E->ops->n, cudaMemcpyDeviceToHost, E->st));
+        CK(cudaStreamSynchronize(E->st));
+    }
+    return MIRK_OK;
+}
+
+int mirk_ensemble_solve(const mirk_ensemble_desc* desc, int64_t ntraj, const double* params, const double* u0,
+                        int32_t u0_per_traj, int32_t* retcodes, int32_t* n_mesh, int32_t* newton_iters, double* y_first) {
+    mirk_ensemble_handle E = nullptr;
+    CKS(mirk_ensemble_create(desc, ntraj, &E));
+    int st = mirk_ensemble_set_inputs(E, params, u0, u0_per_traj);
+    if (st == MIRK_OK) st = mirk_ensemble_run(E, nullptr);
+    if (st == MIRK_OK) st = mirk_ensemble_get_results(E, retcodes, n_mesh, newton_iters, nullptr, nullptr, nullptr, y_first);
+    mirk_ensemble_destroy(E);
+    return st;
 }
 
 }  // extern "C"

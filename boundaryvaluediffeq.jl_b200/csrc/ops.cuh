@@ -75,4 +75,12 @@ const ProblemOps* ops_chain8(int order);
 const ProblemOps* ops_chain16(int order);
 const ProblemOps* ops_bratu64(int order);
 
+// K6 (ensemble.cuh): whole adaptive solves, one thread per trajectory, for the small built-ins
+struct EnsArgs;
+struct EnsembleOps {
+    int n, np, slots_per_node, oMESH, oY;
+    void (*run)(cudaStream_t, const EnsArgs& a);
+};
+const EnsembleOps* ensemble_ops_small(int id, int order);
+
 }  // namespace mirk

@@ -1,0 +1,32 @@
+// ensemble (one thread per trajectory) instantiations for the built-in problems with n <= 6
+#include "ensemble.cuh"
+#include "ops.cuh"
+namespace mirk {
+using namespace problems;
+template <class P, int ORDER> struct EnsImpl {
+    static void run(cudaStream_t st, const EnsArgs& a) {
+        const long long blocks = (a.ntraj + 63) / 64;
+        k_ensemble_solve<P, ORDER><<<(unsigned)blocks, 64, 0, st>>>(a);
+    }
+    static EnsembleOps make() {
+        using LY = EnsLayout<P, ORDER>;
+        return EnsembleOps{P::n, P::np, LY::slots_per_node, LY::oMESH, LY::oY, &run};
+    }
+};
+#define ENS2(P)                                                  \
+    { static const EnsembleOps o4 = EnsImpl<P, 4>::make();       \
+      static const EnsembleOps o6 = EnsImpl<P, 6>::make();       \
+      return order == 4 ? &o4 : order == 6 ? &o6 : nullptr; }
+const EnsembleOps* ensemble_ops_small(int id, int order) {
+    switch (id) {
+    case kPendulum: ENS2(Pendulum)
+    case kLinear2: ENS2(Linear2)
+    case kLinear2TP: ENS2(Linear2TP)
+    case kSwirling: ENS2(Swirling)
+    case kLotka: ENS2(Lotka)
+    case kTorus: ENS2(Torus)
+    case kLayer: ENS2(Layer)
+    default: return nullptr;
+    }
+}
+}  // namespace mirk

@@ -141,6 +141,36 @@ int mirk_bench_newton_steps(mirk_handle h, int32_t steps, float* total_ms, float
 /* roofline denominators measured on the device: FP64 FMA TFLOP/s and HBM copy GB/s */
 int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
 
+/* -- ensembles: solve(EnsembleProblem(prob; prob_func), alg; trajectories, dt)
+ *    (SciMLBase driver; usage lib/BoundaryValueDiffEqMIRK/test/Core/ensemble_tests.jl:20-38).
+ *    The host harvests prob_func's parameters (and optionally per-trajectory u0) into packed arrays;
+ *    every trajectory then runs the complete adaptive solve! loop on the device, one thread each. ---- */
+typedef struct mirk_ensemble_s* mirk_ensemble_handle;
+typedef struct {
+    int32_t problem_id, order;
+    double abstol;
+    int32_t adaptive;
+    double defect_threshold;
+    int32_t max_num_subintervals, maxiters, reinterp_inplace, device;
+    int32_t node_cap;       /* per-trajectory mesh capacity in nodes (0: 128); a mesh that would outgrow it
+                               ends that trajectory with MIRK_RET_FAILURE, like max_num_subintervals does */
+    double t0, t1, dt;      /* tspan and dt: uniform initial mesh of cld(t1 - t0, dt) intervals */
+} mirk_ensemble_desc;
+int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ensemble_handle* out);
+int mirk_ensemble_destroy(mirk_ensemble_handle h);
+/* params[ntraj][n_params]; u0[n] shared by all trajectories or u0[ntraj][n] when u0_per_traj != 0 */
+int mirk_ensemble_set_inputs(mirk_ensemble_handle h, const double* params, const double* u0, int32_t u0_per_traj);
+int mirk_ensemble_run(mirk_ensemble_handle h, float* device_ms);
+/* per-trajectory outcomes (any pointer may be NULL): sol.retcode, length(sol.t), Newton steps, outer
+ * iterations, |sol.resid|_inf, last defect, sol.u[1] */
+int mirk_ensemble_get_results(mirk_ensemble_handle h, int32_t* retcodes, int32_t* n_mesh, int32_t* newton_iters,
+                              int32_t* outer_iters, double* resid_norm, double* defect_norm, double* y_first);
+/* sol.t / sol.u of one trajectory; mesh[node_cap], y[node_cap][n] */
+int mirk_ensemble_get_trajectory(mirk_ensemble_handle h, int64_t traj, int32_t* n_mesh, double* mesh, double* y);
+/* one-shot convenience: create + set_inputs + run + get_results + destroy */
+int mirk_ensemble_solve(const mirk_ensemble_desc* desc, int64_t ntraj, const double* params, const double* u0,
+                        int32_t u0_per_traj, int32_t* retcodes, int32_t* n_mesh, int32_t* newton_iters, double* y_first);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,121 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, argument
+errors surface without a GPU, the ensemble sharding logic, and the world_size-2 gloo gather."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_the_header():
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import _lib as B
+    header = open(os.path.join(ROOT, "include", "mirk_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(mirk_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    lib = M.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mirk_b200.h but not exported"
+    assert declared == set(B.SYMBOLS), (declared ^ set(B.SYMBOLS))
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import ctypes as C
+
+    import mirk_b200 as M
+    cnt = C.c_int32(0)
+    if M.lib().mirk_device_count(C.byref(cnt)) == 0 and cnt.value > 0:
+        pytest.skip("a CUDA device is present")
+    prob = M.BVProblem("pendulum", [1.5, 1.5], (0.0, 1.5), p=[9.81])
+    with pytest.raises(M.MirkError) as ei:
+        M.solve(prob, M.MIRK4(), dt=0.05)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_registry_and_host_helpers():
+    import mirk_b200 as M
+    from oracle import oracle as O
+    for name, pid in O.PROBLEM_IDS.items():
+        f = M.BVPDeviceFunction(name)
+        assert f.problem_id == pid
+        P = O.builtin(name)
+        assert (f.info.n, f.info.n_params, f.info.problem_type, f.info.n_bc, f.info.n_bca) == \
+               (P.n, P.n_p, P.problem_type, P.n_bc, P.n_bca)
+    with pytest.raises(M.MirkError):
+        M.BVPDeviceFunction("nope").problem_id
+    for t0, t1, nint in [(0.0, np.pi / 2, 32), (0.0, 0.5, 19999), (-1.0, 1.0, 7)]:
+        assert np.array_equal(M.mesh_uniform(t0, t1, nint), O.mesh_uniform(t0, t1, nint))
+    with pytest.raises(NotImplementedError):
+        M.MIRK4(nlsolve="NewtonRaphson")
+
+
+def test_partition_covers_every_trajectory_once():
+    from boundaryvaluediffeq_jl_b200.ensemble import partition
+    import mirk_b200  # noqa: F401
+    for nt in (1, 7, 10, 262144, 262145):
+        for world in (1, 2, 3, 8):
+            parts = partition(nt, world)
+            assert len(parts) == world and parts[0][0] == 0
+            assert sum(c for _, c in parts) == nt
+            for (f0, c0), (f1, _) in zip(parts, parts[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_harvest_calls_prob_func_one_based():
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200.ensemble import harvest
+    base = M.BVProblem("linear2", [0.0, 1.0], (0.0, 1.0), p=[1.0, 0.0, 1.0, 1.0, 0.0, 0, 0])
+    seen = []
+
+    def prob_func(prob, i):
+        seen.append(i)
+        p = prob.p.copy()
+        p[0] = float(i)
+        return prob.remake(p=p)
+
+    params, u0, per = harvest(M.EnsembleProblem(base, prob_func=prob_func), 4)
+    assert seen == [1, 2, 3, 4] and list(params[:, 0]) == [1.0, 2.0, 3.0, 4.0] and not per
+    assert np.array_equal(base.p, [1.0, 0.0, 1.0, 1.0, 0.0, 0, 0])  # prob_func must not mutate the base problem
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+import mirk_b200  # noqa
+from boundaryvaluediffeq_jl_b200.ensemble import partition, gather_outcomes
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+nt = 11
+parts = partition(nt, 2)
+first, count = parts[dist.get_rank()]
+local = (np.arange(first, first + count, dtype=np.int32) * 3)          # stands for per-trajectory outcomes
+local2 = np.stack([np.arange(first, first + count, dtype=np.float64)] * 2, axis=1)
+g = gather_outcomes(local, [c for _, c in parts])
+g2 = gather_outcomes(local2, [c for _, c in parts])
+assert np.array_equal(g, np.arange(nt, dtype=np.int32) * 3), g
+assert g2.shape == (nt, 2) and np.array_equal(g2[:, 0], np.arange(nt))
+dist.barrier()
+dist.destroy_process_group()
+print("ok", dist_rank := int(sys.argv[1]))
+"""
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0, err[-2000:]
+        assert "ok" in out
