@@ -225,20 +225,20 @@ def main():
 
     if rank == 0:
         # ---- roofline of the dominant kernel -------------------------------------------------------
-        names = ["residual", "jacobian_blocks", "abd_reduce_level0", "abd_reduce_upper", "abd_closing_solve",
+        names = ["(unused)", "residual+jacobian_blocks", "abd_reduce_level0", "abd_reduce_upper", "abd_tail+closing_solve",
                  "abd_backsub", "update"]
         per_step_ms = [p / args.steps for p in phases[:7]]
         k = int(np.argmax(per_step_ms))
         nn, ni = n * n, N - 1
         s = 5 if cfg.order == 6 else 3
         alg_bytes = {
-            "residual": 8 * (n * N + N + (s + 1) * n * ni),
-            "jacobian_blocks": 8 * (n * N + N + 2 * nn * ni),
+            "(unused)": 0,
+            "residual+jacobian_blocks": 8 * (n * N + N + (s + 1) * n * ni + 2 * nn * ni),
             # reads L_i, R_i, Phi_i; writes the elimination factors of every eliminated node and the
             # collapsed relations: together again (2 n^2 + n) doubles per interval
             "abd_reduce_level0": 8 * 2 * (2 * nn + n) * ni,
             "abd_reduce_upper": 8 * 2 * (2 * nn + n) * ni // 7,
-            "abd_closing_solve": 8 * (2 * nn + n) * 2,
+            "abd_tail+closing_solve": 8 * 2 * (2 * nn + n) * 64,
             "abd_backsub": 8 * ((2 * nn + n) * ni + n * N),
             "update": 8 * 3 * n * N,
         }

@@ -196,13 +196,10 @@ k_backsub_generic(int n, const int* __restrict__ nodes, const int* __restrict__ 
 
 // Closing solve on the surviving nodes kept[0..Q): Q-1 relations + L boundary rows, dense
 // Gauss-Jordan with row pivoting in a global scratch matrix M (D x (D+1), D = Q n).  One block.
-__global__ void __launch_bounds__(1024)
-k_final_solve(int n, int Q, const int* __restrict__ kept, const double* __restrict__ relL,
-              const double* __restrict__ relR, const double* __restrict__ relr, int L, int La,
-              const int* __restrict__ m_ptr, const int* __restrict__ bc_nodes,
-              const double* __restrict__ Bc, const double* __restrict__ resid, size_t tail_off,
-              double* M, double* __restrict__ delta, int* __restrict__ status) {
-    extern __shared__ double smem[];
+__device__ void final_solve_body(int n, int Q, const int* kept, const double* relL, const double* relR,
+                                 const double* relr, int L, int La, const int* m_ptr, const int* bc_nodes,
+                                 const double* Bc, const double* resid, size_t tail_off, double* M, double* delta,
+                                 int* status, double* smem) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int D = Q * n, cols = D + 1, ld = cols;
     const size_t nn = (size_t)n * n;
@@ -243,6 +240,17 @@ k_final_solve(int n, int Q, const int* __restrict__ kept, const double* __restri
         const int s = e / n, c = e % n;
         delta[(size_t)kept[s] * n + c] = M[(size_t)pivrow[e] * ld + D];
     }
+}
+
+
+__global__ void __launch_bounds__(1024)
+k_final_solve(int n, int Q, const int* __restrict__ kept, const double* __restrict__ relL,
+              const double* __restrict__ relR, const double* __restrict__ relr, int L, int La,
+              const int* __restrict__ m_ptr, const int* __restrict__ bc_nodes,
+              const double* __restrict__ Bc, const double* __restrict__ resid, size_t tail_off,
+              double* M, double* __restrict__ delta, int* __restrict__ status) {
+    extern __shared__ double smem[];
+    final_solve_body(n, Q, kept, relL, relR, relr, L, La, m_ptr, bc_nodes, Bc, resid, tail_off, M, delta, status, smem);
 }
 
 }  // namespace mirk

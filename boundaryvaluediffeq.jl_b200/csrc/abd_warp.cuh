@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "abd.cuh"
+
 namespace mirk {
 
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -148,18 +150,14 @@ template <int n> struct WarpABD {
     }
 };
 
-// One level of the reduction, one warp per group (see k_reduce_generic for the argument meaning).
+// One group of one reduction level, done by one warp (see k_reduce_generic for the argument meaning).
+// Returns false (warp-uniform) on a singular block.
 template <int n>
-__global__ void __launch_bounds__(128, 3)
-k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ inR, const double* __restrict__ inr,
-              double* __restrict__ outL, double* __restrict__ outR, double* __restrict__ outr,
-              const int* __restrict__ nodes, const int* __restrict__ gs, double* __restrict__ TL,
-              double* __restrict__ TR, double* __restrict__ rt, int* __restrict__ status) {
+__device__ __forceinline__ bool warp_reduce_group(int g, const double* inL, const double* inR, const double* inr,
+                                                  double* outL, double* outR, double* outr, const int* nodes,
+                                                  const int* gs, double* TL, double* TR, double* rt, double* pbuf,
+                                                  int lane) {
     using WA = WarpABD<n>;
-    __shared__ __align__(16) double pbuf[4][WA::smem_doubles_per_warp];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
-    if (g >= G) return;
     constexpr size_t nn = (size_t)n * n;
     const int k0 = gs[g], k1 = gs[g + 1];
     double w[WA::cols];
@@ -176,35 +174,28 @@ k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ 
         }
         int myq;
         double myinv;
-        if (!WA::eliminate(w, lane, pbuf[wib], myq, myinv)) {
-            if (lane == 0) atomicExch(status, 1);
-            return;
-        }
+        if (!WA::eliminate(w, lane, pbuf, myq, myinv)) return false;
         const int c = nodes[j];
         WA::store_factors_and_shift(w, lane, myq, myinv, TL + c * nn, TR + c * nn, rt + (size_t)c * n);
         carried = rowmask & ~__ballot_sync(kFullMask, myq >= 0);
         __syncwarp();
     }
     WA::store_relation(w, lane, carried, outL + g * nn, outR + g * nn, outr + (size_t)g * n);
+    return true;
 }
 
-// Back substitution of one level, one warp per group: d_c = rt_c - TL_c d_a - TR_c d_right, right to
-// left.  Lanes [0,n) own the rows of the TL product, lanes [16,16+n) those of the TR product.
+// Back substitution of one group: d_c = rt_c - TL_c d_a - TR_c d_right, right to left.  Lanes [0,n) own
+// the rows of the TL product, lanes [16,16+n) those of the TR product; da/dr are 16-double shared lines.
 template <int n>
-__global__ void __launch_bounds__(128)
-k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs, const double* __restrict__ TL,
-               const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta) {
-    __shared__ __align__(16) double dbuf[4][2][16];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
-    if (g >= G) return;
+__device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, const int* gs, const double* TL,
+                                                   const double* TR, const double* rt, double* delta, double* da,
+                                                   double* dr, int lane) {
     const int k0 = gs[g], k1 = gs[g + 1];
     if (k1 - k0 == 1) return;
     constexpr size_t nn = (size_t)n * n;
     const int half = lane >> 4, q = lane & 15;
     const bool act = q < n;
-    double* da = dbuf[wib][0];
-    double* dr = dbuf[wib][1];
+    __syncwarp();
     if (lane < n) {
         da[lane] = delta[(size_t)nodes[k0] * n + lane];
         dr[lane] = delta[(size_t)nodes[k1] * n + lane];
@@ -243,6 +234,84 @@ k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs,
     }
 }
 
+template <int n>
+__global__ void __launch_bounds__(128, 3)
+k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ inR, const double* __restrict__ inr,
+              double* __restrict__ outL, double* __restrict__ outR, double* __restrict__ outr,
+              const int* __restrict__ nodes, const int* __restrict__ gs, double* __restrict__ TL,
+              double* __restrict__ TR, double* __restrict__ rt, int* __restrict__ status) {
+    __shared__ __align__(16) double pbuf[4][WarpABD<n>::smem_doubles_per_warp];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= G) return;
+    if (!warp_reduce_group<n>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf[wib], lane))
+        if (lane == 0) atomicExch(status, 1);
+}
+
+template <int n>
+__global__ void __launch_bounds__(128)
+k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs, const double* __restrict__ TL,
+               const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta) {
+    __shared__ __align__(16) double dbuf[4][2][16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 4 + wib;
+    if (g >= G) return;
+    warp_backsub_group<n>(g, nodes, gs, TL, TR, rt, delta, dbuf[wib][0], dbuf[wib][1], lane);
+}
+
+// ---- the tail: every remaining level, the closing solve and the matching back substitutions in ONE
+// block, so the log-depth end of the reduction costs one launch instead of 2 x levels + 1.
+constexpr int kMaxTail = 20;
+struct TailArgs {
+    int nlev;
+    int G[kMaxTail];
+    const int* nodes[kMaxTail];
+    const int* gs[kMaxTail];
+    const double *inL[kMaxTail], *inR[kMaxTail], *inr[kMaxTail];
+    double *outL[kMaxTail], *outR[kMaxTail], *outr[kMaxTail];
+    double *TL, *TR, *rt;
+    int* status;
+    // closing system (see k_final_solve)
+    int Q;
+    const int* kept;
+    const double *relL, *relR, *relr;
+    int L, La;
+    const int* m_ptr;
+    const int* bc_nodes;
+    const double* Bc;
+    const double* resid;
+    size_t tail_off;
+    double* M;  // global scratch or nullptr when the closing matrix fits in shared memory
+    double* delta;
+};
+
+constexpr int kTailWarps = 8;
+
+template <int n>
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
+k_tail_warp(const TailArgs a) {
+    extern __shared__ double tail_smem[];
+    __shared__ __align__(16) double pbuf[kTailWarps][WarpABD<n>::smem_doubles_per_warp];
+    __shared__ __align__(16) double dbuf[kTailWarps][2][16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int l = 0; l < a.nlev; l++) {
+        for (int g = wib; g < a.G[l]; g += kTailWarps) {
+            if (!warp_reduce_group<n>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
+                                      a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
+                if (lane == 0) atomicExch(a.status, 1);
+        }
+        __syncthreads();
+    }
+    final_solve_body(n, a.Q, a.kept, a.relL, a.relR, a.relr, a.L, a.La, a.m_ptr, a.bc_nodes, a.Bc, a.resid, a.tail_off,
+                     a.M, a.delta, a.status, tail_smem);
+    __syncthreads();
+    for (int l = a.nlev - 1; l >= 0; l--) {
+        for (int g = wib; g < a.G[l]; g += kTailWarps)
+            warp_backsub_group<n>(g, a.nodes[l], a.gs[l], a.TL, a.TR, a.rt, a.delta, dbuf[wib][0], dbuf[wib][1], lane);
+        __syncthreads();
+    }
+}
+
 inline bool warp_reduce_supported(int n) { return n == 2 || n == 4 || n == 6 || n == 8 || n == 16; }
 
 #define MIRK_WARP_DISPATCH(n, CALL) \
@@ -261,6 +330,12 @@ inline void launch_warp_reduce(cudaStream_t st, int n, int G, const double* inL,
     const int blocks = (G + 3) / 4;
     MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN><<<blocks, 128, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs, TL,
                                                                     TR, rt, status)));
+}
+inline void launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, int smem_bytes) {
+    MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<1, kTailWarps * 32, smem_bytes, st>>>(a)));
+}
+inline void set_warp_tail_smem(int n, int bytes) {
+    MIRK_WARP_DISPATCH(n, (cudaFuncSetAttribute(k_tail_warp<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
 }
 inline void launch_warp_backsub(cudaStream_t st, int n, int G, const int* nodes, const int* gs, const double* TL,
                                 const double* TR, const double* rt, double* delta) {

@@ -263,6 +263,50 @@ k_jac_blocks(int N, const double* __restrict__ mesh, const double* __restrict__ 
     for (int k = 0; k < n; k++) out[k * n] = phi[k].d;
 }
 
+// ---- K1+K2 fused: the dual sweep of column 0 carries the residual for free ------------------------
+// Same thread mapping as k_jac_blocks; the thread of column d = 0 also writes the discrete stages,
+// Phi_i and |Phi|_inf, so a Newton iteration needs no separate residual pass over the mesh.
+template <class P, int ORDER>
+__global__ void __launch_bounds__(128)
+k_resjac(int N, const double* __restrict__ mesh, const double* __restrict__ y, const double* __restrict__ p,
+         double* __restrict__ Kd, double* __restrict__ phi_out, unsigned long long* __restrict__ norm_bits,
+         double* __restrict__ Lb, double* __restrict__ Rb) {
+    using TB = Tableau<ORDER>;
+    constexpr int n = P::n;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(gid / (2 * n)), d = (int)(gid % (2 * n));
+    unsigned long long m = 0ull;
+    if (i < N - 1) {
+        Dual yi[n], yi1[n], K[TB::s][n], phi[n];
+        const double* yp = y + (size_t)i * n;
+#pragma unroll (unroll_for(n))
+        for (int k = 0; k < n; k++) {
+            yi[k] = Dual(yp[k], k == d ? 1.0 : 0.0);
+            yi1[k] = Dual(yp[n + k], (n + k) == d ? 1.0 : 0.0);
+        }
+        const double ti = mesh[i], h = mesh[i + 1] - ti;
+        phi_interval<P, ORDER, Dual>(yi, yi1, h, ti, p, K, phi);
+        double* out = (d < n ? Lb : Rb) + (size_t)i * n * n + (d < n ? d : d - n);
+#pragma unroll (unroll_for(n))
+        for (int k = 0; k < n; k++) out[k * n] = phi[k].d;
+        if (d == 0) {
+            double* Ko = Kd + (size_t)i * TB::s * n;
+#pragma unroll (unroll_for(n))
+            for (int r = 0; r < TB::s; r++)
+#pragma unroll (unroll_for(n))
+                for (int k = 0; k < n; k++) Ko[r * n + k] = K[r][k].v;
+            double* po = phi_out + (size_t)i * n;
+#pragma unroll (unroll_for(n))
+            for (int k = 0; k < n; k++) {
+                po[k] = phi[k].v;
+                const unsigned long long b = abs_bits(phi[k].v);
+                m = b > m ? b : m;
+            }
+        }
+    }
+    block_max_to_global(m, norm_bits);
+}
+
 // ---- K4: defect estimate (Appendix A.5) ---------------------------------------------------------
 // one thread per interval: interpolation stages, two samples, errors[i][:], est[i] = |errors_i|_inf
 template <class P, int ORDER>

@@ -94,6 +94,7 @@ struct Plan {
     int* d_gs[kMaxLev];
     double *relL[kMaxLev + 1], *relR[kMaxLev + 1], *relr[kMaxLev + 1];
     std::vector<int> pinned;  // the pinned nodes the plan was built for
+    int tail_begin = 0;       // levels [tail_begin, nlev) + the closing solve run in the one-block tail kernel
     int N = 0, chunk = 0;
     bool valid = false;
 };
@@ -173,7 +174,14 @@ static int build_plan(mirk_solver_s* S) {
     std::vector<int> pinned(bcn, bcn + m);
     std::sort(pinned.begin(), pinned.end());
     pinned.erase(std::unique(pinned.begin(), pinned.end()), pinned.end());
-    const int chunk = S->desc.chunk >= 2 ? S->desc.chunk : 8;
+    // desc.chunk packs the reduction shape: bits 0-7 relations per group at level 0 (default 8),
+    // bits 8-15 at the upper levels (default: same), bits 16-31 the relation count from which the
+    // remaining levels run radix-2 inside the single-block tail kernel (default 64; 1 disables it)
+    const int chunk = S->desc.chunk;
+    const int c0 = (chunk & 0xff) >= 2 ? (chunk & 0xff) : 8;
+    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : c0;
+    const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 64;
+    const bool warp_path = warp_reduce_supported(n);
     if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
 
     std::vector<char> is_pinned(N, 0);
@@ -181,8 +189,15 @@ static int build_plan(mirk_solver_s* S) {
     std::vector<std::vector<int>> nodes_l, gs_l;
     std::vector<int> nodes(N);
     for (int i = 0; i < N; i++) nodes[i] = i;
+    int tail_begin = -1;
     while ((int)nodes_l.size() < kMaxLev) {
         const int R = (int)nodes.size() - 1;
+        const int lvl = (int)nodes_l.size();
+        int chunk = lvl == 0 ? c0 : c1;
+        if (warp_path && (tail_begin >= 0 || R <= tail_thr)) {
+            if (tail_begin < 0) tail_begin = lvl;
+            chunk = 2;
+        }
         std::vector<int> gs;
         gs.push_back(0);
         int k = 0;
@@ -202,6 +217,8 @@ static int build_plan(mirk_solver_s* S) {
         nodes.swap(next);
     }
     P.nlev = (int)nodes_l.size();
+    P.tail_begin = (tail_begin < 0 || !warp_path) ? P.nlev : tail_begin;
+    if (P.nlev - P.tail_begin > kMaxTail) return fail(MIRK_ERR_STATE, "reduction tail deeper than kMaxTail");
     P.Q = (int)nodes.size();
     size_t ints = 0, rels = 0;
     for (int l = 0; l < P.nlev; l++) {
@@ -297,11 +314,22 @@ static int eval_jacobian(mirk_solver_s* S) {
     return launch_check("jacobian");
 }
 
+// F(y) and J(y) in one pass over the mesh: the Newton loop's per-iteration evaluation
+static int eval_resjac(mirk_solver_s* S) {
+    CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
+    S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb);
+    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
+               S->words, 1);
+    S->launches += 2;
+    S->resid_valid = S->jac_valid = true;
+    return launch_check("resjac");
+}
+
 static int abd_reduce(mirk_solver_s* S, int l_begin = 0, int l_end = kMaxLev) {
     Plan& P = S->plan;
     const int n = S->n;
     const bool smem_ok = reduce_smem_bytes(n) <= kSmemLimit;
-    for (int l = l_begin; l < P.nlev && l < l_end; l++) {
+    for (int l = l_begin; l < P.tail_begin && l < l_end; l++) {
         if (warp_reduce_supported(n)) {
             launch_warp_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
                                P.relr[l + 1], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt,
@@ -329,6 +357,24 @@ static int abd_final(mirk_solver_s* S) {
     const int n = S->n, D = P.Q * n;
     const bool m_in_smem = final_smem_bytes(D, true) <= kSmemLimit;
     const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n;
+    if (warp_reduce_supported(n)) {
+        TailArgs a;
+        a.nlev = P.nlev - P.tail_begin;
+        for (int t = 0; t < a.nlev; t++) {
+            const int l = P.tail_begin + t;
+            a.G[t] = P.G[l]; a.nodes[t] = P.d_nodes[l]; a.gs[t] = P.d_gs[l];
+            a.inL[t] = P.relL[l]; a.inR[t] = P.relR[l]; a.inr[t] = P.relr[l];
+            a.outL[t] = P.relL[l + 1]; a.outR[t] = P.relR[l + 1]; a.outr[t] = P.relr[l + 1];
+        }
+        a.TL = S->TL; a.TR = S->TR; a.rt = S->rt; a.status = (int*)(S->words + 2);
+        a.Q = P.Q; a.kept = P.d_nodes[P.nlev];
+        a.relL = P.relL[P.nlev]; a.relR = P.relR[P.nlev]; a.relr = P.relr[P.nlev];
+        a.L = S->L; a.La = S->La; a.m_ptr = S->m_dev; a.bc_nodes = S->bc_nodes; a.Bc = S->Bc; a.resid = S->resid;
+        a.tail_off = tail_off; a.M = m_in_smem ? nullptr : S->Mfinal; a.delta = S->delta;
+        launch_warp_tail(S->st, n, a, final_smem_bytes(D, m_in_smem));
+        S->launches++;
+        return launch_check("abd_tail");
+    }
     const int threads = D * (D + 1) >= 4096 ? 1024 : 256;
     k_final_solve<<<1, threads, final_smem_bytes(D, m_in_smem), S->st>>>(
         n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, S->m_dev,
@@ -341,7 +387,7 @@ static int abd_final(mirk_solver_s* S) {
 static int abd_backsub(mirk_solver_s* S) {
     Plan& P = S->plan;
     const int n = S->n;
-    for (int l = P.nlev - 1; l >= 0; l--) {
+    for (int l = P.tail_begin - 1; l >= 0; l--) {
         if (warp_reduce_supported(n))
             launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt, S->delta);
         else
@@ -384,15 +430,14 @@ static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* 
     int ret = MIRK_RET_MAXITERS, it = 0;
     double best = INFINITY;
     bool have_best = false;
-    CKS(eval_residual(S));
+    if (maxiters > 0) CKS(eval_resjac(S)); else CKS(eval_residual(S));
     CKS(read_words(S));
     double nrm = bits_to_double(S->h_words[0]);
     while (it < maxiters) {
-        CKS(eval_jacobian(S));
         CKS(linear_solve(S));
         CKS(apply_update(S));
         it++;
-        CKS(eval_residual(S));
+        CKS(eval_resjac(S));  // F and J at the new iterate; J is unused only on the converged last pass
         CKS(read_words(S));
         if (S->h_words[2] != 0ull) {  // singular block met by the elimination
             ret = MIRK_RET_FAILURE;
@@ -629,6 +674,7 @@ int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     cudaFuncSetAttribute(k_reduce_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(k_final_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(k_mesh_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (warp_reduce_supported(ops->n)) set_warp_tail_smem(ops->n, kSmemLimit);
     *out = S;
     return MIRK_OK;
 }
@@ -731,11 +777,10 @@ int mirk_linear_solve(mirk_handle S, double* delta) {
 
 int mirk_newton_step(mirk_handle S, double* resid_norm) {
     NEED_GUESS(S);
-    if (!S->resid_valid) CKS(eval_residual(S));
-    CKS(eval_jacobian(S));
+    if (!S->resid_valid || !S->jac_valid) CKS(eval_resjac(S));
     CKS(linear_solve(S));
     CKS(apply_update(S));
-    CKS(eval_residual(S));
+    CKS(eval_resjac(S));
     CKS(read_words(S));
     if (resid_norm) *resid_norm = bits_to_double(S->h_words[0]);
     return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
@@ -957,9 +1002,8 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
         cudaEvent_t* e = &ev[(size_t)it * NE];
         CK(cudaMemcpyAsync(S->y, S->y_guess, yb, cudaMemcpyDeviceToDevice, S->st));
         CK(cudaEventRecord(e[0], S->st));
-        CKS(eval_residual(S));
         CK(cudaEventRecord(e[1], S->st));
-        CKS(eval_jacobian(S));
+        CKS(eval_resjac(S));
         CK(cudaEventRecord(e[2], S->st));
         CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
         CKS(abd_reduce(S, 0, 1));

@@ -19,6 +19,8 @@ struct ProblemOps {
                unsigned long long* norm_bits, int want_jac);
     void (*jac_blocks)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
                        double* Lb, double* Rb);
+    void (*resjac)(cudaStream_t, int N, const double* mesh, const double* y, const double* p, double* Kd,
+                   double* phi_out, unsigned long long* norm_bits, double* Lb, double* Rb);
     void (*defect)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
                    const double* Kd, double* Ki, double* errors, double* est,
                    unsigned long long* defect_bits);
@@ -44,6 +46,11 @@ template <class P, int ORDER> struct OpsImpl {
         const long long tot = (long long)(N - 1) * 2 * P::n;
         k_jac_blocks<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Lb, Rb);
     }
+    static void resjac(cudaStream_t st, int N, const double* mesh, const double* y, const double* p, double* Kd,
+                       double* phi_out, unsigned long long* nb, double* Lb, double* Rb) {
+        const long long tot = (long long)(N - 1) * 2 * P::n;
+        k_resjac<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Kd, phi_out, nb, Lb, Rb);
+    }
     static void defect(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
                        const double* Kd, double* Ki, double* errors, double* est,
                        unsigned long long* db) {
@@ -64,7 +71,7 @@ template <class P, int ORDER> struct OpsImpl {
     static ProblemOps make(const char* name) {
         using TB = Tableau<ORDER>;
         return ProblemOps{name, ORDER, P::n, P::np, P::n_bc, P::n_bca, P::problem_type, P::max_bc_pts,
-                          TB::s, TB::s_star, &residual, &bc, &jac_blocks, &defect, &interp_setup,
+                          TB::s, TB::s_star, &residual, &bc, &jac_blocks, &resjac, &defect, &interp_setup,
                           &bc_nodes_host};
     }
 };

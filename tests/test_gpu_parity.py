@@ -101,7 +101,7 @@ def test_residual_jacobian_and_update_match_oracle(M, oracle, name, order, p, ts
     cache.close()
 
 
-@pytest.mark.parametrize("chunk", [2, 3, 8, 64])
+@pytest.mark.parametrize("chunk", [2, 3, 8, 64, 8 | (4 << 8) | (1 << 16), 5 | (3 << 8) | (200 << 16)])
 def test_update_is_independent_of_reduction_chunking(M, oracle, chunk):
     O = oracle
     p = _params("chain8", None)
