@@ -188,7 +188,8 @@ def main():
     barrier()
     assert st == 0
     if args.profile:
-        print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps}))
+        print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps,
+                          "phases_us": [round(1e3 * p / args.steps, 1) for p in phases[:7]]}))
         cache.close()
         return
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")

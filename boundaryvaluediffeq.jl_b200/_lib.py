@@ -84,6 +84,8 @@ SYMBOLS = {
     "mirk_interp": (C.c_int, [Handle, dp, C.c_int32, C.c_int32, dp]),
     "mirk_bench_newton_steps": (C.c_int, [Handle, C.c_int32, fp, fp, C.POINTER(C.c_int64)]),
     "mirk_measure_peaks": (C.c_int, [C.c_int32, dp, dp]),
+    "mirk_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mirk_partition_attach": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p, C.c_char_p]),
     "mirk_ensemble_create": (C.c_int, [C.POINTER(EnsembleDesc), C.c_int64, C.POINTER(Handle)]),
     "mirk_ensemble_destroy": (C.c_int, [Handle]),
     "mirk_ensemble_set_inputs": (C.c_int, [Handle, dp, dp, C.c_int32]),

@@ -13,6 +13,7 @@
 // kernels_fused.cuh shares it.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "abd.cuh"
 
@@ -56,29 +57,33 @@ template <int n> struct WarpABD {
         bool elig = lane < rows;
 #pragma unroll
         for (int q = 0; q < n; q++) {
-            const unsigned key = elig ? (unsigned)__double2hiint(fabs(w[q])) : 0u;
+            const double own = w[q];
+            // speculative reciprocal of every lane's candidate: overlaps with the pivot search, so the
+            // reciprocal is off the critical path of the pivot lane
+            const double own_inv = fast_rcp(own);
+            // one REDUX gives the pivot and its lane: high word of |w| (low 5 bits dropped) | (31 - lane)
+            const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
             const unsigned mx = __reduce_max_sync(kFullMask, key);
-            if (mx == 0u || mx >= 0x7ff00000u) return false;
-            const unsigned bal = __ballot_sync(kFullMask, elig && key == mx);
-            const int pr = __ffs(bal) - 1;
+            if ((mx >> 5) == 0u || mx >= 0x7ff00000u) return false;
+            const int pr = 31 - (int)(mx & 31u);
             double* line = pb + (q & 1) * pb_stride;
             if (lane == pr) {
 #pragma unroll
                 for (int c = (q & ~1); c < cols; c += 2) {
-                    const double hi = (c + 1 < cols) ? w[(c + 1 < cols) ? c + 1 : c] : 0.0;
-                    *reinterpret_cast<double2*>(line + c) = make_double2(w[c], hi);
+                    const double lo = (c == q) ? own_inv : w[c];
+                    const double hi = (c + 1 == q) ? own_inv : ((c + 1 < cols) ? w[(c + 1 < cols) ? c + 1 : c] : 0.0);
+                    *reinterpret_cast<double2*>(line + c) = make_double2(lo, hi);
                 }
                 elig = false;
                 myq = q;
+                myinv = own_inv;
             }
             __syncwarp();
             // volatile shared loads: nvcc otherwise forwards the pivot lane's own stores across the
             // __syncwarp and keeps a second copy of the row in registers (spills at n = 16)
             const unsigned la = (unsigned)__cvta_generic_to_shared(line);
-            const double pvq = lds_f64(la + 8u * q);
-            const double inv = fast_rcp(pvq);
-            if (lane == pr) myinv = inv;
-            const double m = (lane == pr) ? 0.0 : -(w[q] * inv);
+            const double inv = lds_f64(la + 8u * q);
+            const double m = (lane == pr) ? 0.0 : -(own * inv);
 #pragma unroll
             for (int c = ((q + 1) & ~1); c < cols; c += 2) {
                 const double2 v = lds_v2f64(la + 8u * c);
@@ -234,15 +239,15 @@ __device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, cons
     }
 }
 
-template <int n>
-__global__ void __launch_bounds__(128, 3)
+template <int n, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ inR, const double* __restrict__ inr,
               double* __restrict__ outL, double* __restrict__ outR, double* __restrict__ outr,
               const int* __restrict__ nodes, const int* __restrict__ gs, double* __restrict__ TL,
               double* __restrict__ TR, double* __restrict__ rt, int* __restrict__ status) {
     __shared__ __align__(16) double pbuf[4][WarpABD<n>::smem_doubles_per_warp];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
+    const int g = blockIdx.x * (blockDim.x >> 5) + wib;
     if (g >= G) return;
     if (!warp_reduce_group<n>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf[wib], lane))
         if (lane == 0) atomicExch(status, 1);
@@ -254,7 +259,7 @@ k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs,
                const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta) {
     __shared__ __align__(16) double dbuf[4][2][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 4 + wib;
+    const int g = blockIdx.x * (blockDim.x >> 5) + wib;
     if (g >= G) return;
     warp_backsub_group<n>(g, nodes, gs, TL, TR, rt, delta, dbuf[wib][0], dbuf[wib][1], lane);
 }
@@ -263,6 +268,7 @@ k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs,
 // block, so the log-depth end of the reduction costs one launch instead of 2 x levels + 1.
 constexpr int kMaxTail = 20;
 struct TailArgs {
+    int mode;  // bit 0: reduce the tail levels, bit 1: closing solve, bit 2: back-substitute the tail levels
     int nlev;
     int G[kMaxTail];
     const int* nodes[kMaxTail];
@@ -287,6 +293,8 @@ struct TailArgs {
 
 constexpr int kTailWarps = 8;
 
+// (A cooperative multi-CTA variant with one warp per SM and grid barriers between levels was measured
+// slower: ~20 grid syncs cost more than the shared-memory contention they avoid — profiles/r01_notes.md.)
 template <int n>
 __global__ void __launch_bounds__(kTailWarps * 32, 1)
 k_tail_warp(const TailArgs a) {
@@ -294,7 +302,7 @@ k_tail_warp(const TailArgs a) {
     __shared__ __align__(16) double pbuf[kTailWarps][WarpABD<n>::smem_doubles_per_warp];
     __shared__ __align__(16) double dbuf[kTailWarps][2][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (int l = 0; l < a.nlev; l++) {
+    for (int l = 0; l < a.nlev && (a.mode & 1); l++) {
         for (int g = wib; g < a.G[l]; g += kTailWarps) {
             if (!warp_reduce_group<n>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
                                       a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
@@ -302,10 +310,11 @@ k_tail_warp(const TailArgs a) {
         }
         __syncthreads();
     }
-    final_solve_body(n, a.Q, a.kept, a.relL, a.relR, a.relr, a.L, a.La, a.m_ptr, a.bc_nodes, a.Bc, a.resid, a.tail_off,
-                     a.M, a.delta, a.status, tail_smem);
+    if (a.mode & 2)
+        final_solve_body(n, a.Q, a.kept, a.relL, a.relR, a.relr, a.L, a.La, a.m_ptr, a.bc_nodes, a.Bc, a.resid,
+                         a.tail_off, a.M, a.delta, a.status, tail_smem);
     __syncthreads();
-    for (int l = a.nlev - 1; l >= 0; l--) {
+    for (int l = a.nlev - 1; l >= 0 && (a.mode & 4); l--) {
         for (int g = wib; g < a.G[l]; g += kTailWarps)
             warp_backsub_group<n>(g, a.nodes[l], a.gs[l], a.TL, a.TR, a.rt, a.delta, dbuf[wib][0], dbuf[wib][1], lane);
         __syncthreads();
@@ -327,20 +336,32 @@ inline bool warp_reduce_supported(int n) { return n == 2 || n == 4 || n == 6 || 
 inline void launch_warp_reduce(cudaStream_t st, int n, int G, const double* inL, const double* inR, const double* inr,
                                double* outL, double* outR, double* outr, const int* nodes, const int* gs, double* TL,
                                double* TR, double* rt, int* status) {
-    const int blocks = (G + 3) / 4;
-    MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN><<<blocks, 128, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs, TL,
-                                                                    TR, rt, status)));
+    // few groups: one warp per CTA so the merges spread over the SMs (each merge is bound by its SM's
+    // shared-memory broadcast pipe); many groups: four warps per CTA
+    const int wpb = G < 1024 ? 1 : 4;
+    const int blocks = (G + wpb - 1) / wpb;
+    static const int occ = getenv("MIRK_REDUCE_OCC") ? atoi(getenv("MIRK_REDUCE_OCC")) : 3;  // tuning knob
+    if (occ >= 4) {
+        MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN, 4><<<blocks, 32 * wpb, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs,
+                                                                           TL, TR, rt, status)));
+    } else {
+        MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN, 3><<<blocks, 32 * wpb, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs,
+                                                                           TL, TR, rt, status)));
+    }
 }
-inline void launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, int smem_bytes) {
+inline cudaError_t launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, int ctas, int smem_bytes) {
+    (void)ctas;
     MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<1, kTailWarps * 32, smem_bytes, st>>>(a)));
+    return cudaGetLastError();
 }
 inline void set_warp_tail_smem(int n, int bytes) {
     MIRK_WARP_DISPATCH(n, (cudaFuncSetAttribute(k_tail_warp<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
 }
 inline void launch_warp_backsub(cudaStream_t st, int n, int G, const int* nodes, const int* gs, const double* TL,
                                 const double* TR, const double* rt, double* delta) {
-    const int blocks = (G + 3) / 4;
-    MIRK_WARP_DISPATCH(n, (k_backsub_warp<NN><<<blocks, 128, 0, st>>>(G, nodes, gs, TL, TR, rt, delta)));
+    const int wpb = G < 1024 ? 1 : 4;
+    const int blocks = (G + wpb - 1) / wpb;
+    MIRK_WARP_DISPATCH(n, (k_backsub_warp<NN><<<blocks, 32 * wpb, 0, st>>>(G, nodes, gs, TL, TR, rt, delta)));
 }
 
 }  // namespace mirk

@@ -8,6 +8,7 @@
 // back 8-byte norms / status words, and decides sizes.  There is no CPU fallback.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nccl.h>  // types only: the functions are resolved with dlopen, the library has no link-time NCCL dependency
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -69,6 +70,48 @@ static const ProblemOps* find_ops(int id, int order) {
     return nullptr;
 }
 
+// ---- NCCL (mesh-partitioned mode only), loaded on demand ------------------------------------------
+struct NcclApi {
+    void* dl = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static int load_nccl(const char* path) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.dl) return MIRK_OK;
+    const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+    void* dl = nullptr;
+    for (const char* c : cands) {
+        if (c && *c) dl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (dl) break;
+    }
+    if (!dl) return fail(MIRK_ERR_UNSUPPORTED, std::string("cannot load NCCL: ") + dlerror());
+    NcclApi a;
+    a.dl = dl;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(dl, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(dl, "ncclCommInitRank");
+    a.AllGather = (decltype(a.AllGather))dlsym(dl, "ncclAllGather");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(dl, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(dl, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(dl, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+        return fail(MIRK_ERR_UNSUPPORTED, "NCCL library lacks a required symbol");
+    g_nccl = a;
+    return MIRK_OK;
+}
+#define CKN(call)                                                                                     \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail(MIRK_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_));        \
+    } while (0)
+
 // ---- device arena helpers -----------------------------------------------------------------------
 template <class T> static cudaError_t dalloc(T** p, size_t count) {
     *p = nullptr;
@@ -120,6 +163,12 @@ struct mirk_solver_s {
     unsigned long long* h_words = nullptr;  // pinned host
     Plan plan;
     int64_t launches = 0;
+    int sm_count = 1;
+    // mesh-partitioned mode: this handle holds one contiguous mesh segment of a two-point problem
+    bool part = false;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr, *Mpart = nullptr;
     bool jac_valid = false, resid_valid = false;
     double last_resid_norm = NAN;
 };
@@ -293,13 +342,28 @@ static int launch_check(const char* what) {
     return MIRK_OK;
 }
 
+// boundary rows (+ blocks); in partitioned mode only the rows this rank owns count towards |F|_inf, and
+// the norm is then max-reduced over the ranks so every rank takes the same Newton decisions
+static int eval_bc(mirk_solver_s* S, int want_jac, bool into_norm) {
+    unsigned long long* nb = (into_norm && !S->part) ? S->words : S->words + 3;
+    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev, nb, want_jac);
+    S->launches++;
+    if (S->part && into_norm) {
+        const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * S->n;
+        k_bc_norm_masked<<<1, 128, 0, S->st>>>(S->L, S->La, S->resid, tail_off, S->rank == 0, S->rank == S->nranks - 1,
+                                               S->words);
+        S->launches++;
+        CKN(g_nccl.AllReduce(S->words, S->words, 1, ncclUint64, ncclMax, S->comm, S->st));
+    }
+    return MIRK_OK;
+}
+
 // F(y): Phi rows, boundary rows, |F|_inf bits into words[0]
 static int eval_residual(mirk_solver_s* S) {
     CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
     S->ops->residual(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words);
-    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
-               S->words, 0);
-    S->launches += 2;
+    S->launches++;
+    CKS(eval_bc(S, 0, true));
     S->resid_valid = true;
     return launch_check("residual");
 }
@@ -307,9 +371,8 @@ static int eval_residual(mirk_solver_s* S) {
 static int eval_jacobian(mirk_solver_s* S) {
     S->ops->jac_blocks(S->st, S->N, S->mesh, S->y, S->p, S->Lb, S->Rb);
     // boundary blocks (reference pattern); rewrites the same boundary residual values
-    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
-               S->words + 3, 1);
-    S->launches += 2;
+    S->launches++;
+    CKS(eval_bc(S, 1, false));
     S->jac_valid = true;
     return launch_check("jacobian");
 }
@@ -318,9 +381,8 @@ static int eval_jacobian(mirk_solver_s* S) {
 static int eval_resjac(mirk_solver_s* S) {
     CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
     S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb);
-    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev,
-               S->words, 1);
-    S->launches += 2;
+    S->launches++;
+    CKS(eval_bc(S, 1, true));
     S->resid_valid = S->jac_valid = true;
     return launch_check("resjac");
 }
@@ -352,13 +414,32 @@ static int final_smem_bytes(int D, bool m_in_smem) {
     return (int)b;
 }
 
+// mesh-partitioned closing: pack this segment's collapsed relation (+ the boundary blocks it owns), one
+// NCCL all-gather of (2n^2 + n + 2Ln + L) doubles per rank on the solver's stream, then the interface
+// system on the G+1 segment end nodes is solved redundantly by every rank
+static int part_exchange_and_close(mirk_solver_s* S) {
+    Plan& P = S->plan;
+    const int n = S->n, G = S->nranks, D = (G + 1) * n;
+    const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n, pay = part_payload_doubles(n, S->L);
+    k_part_pack<<<8, 256, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
+                                      tail_off, S->sendbuf);
+    CKN(g_nccl.AllGather(S->sendbuf, S->recvbuf, pay, ncclDouble, S->comm, S->st));
+    const int smem = (int)(sizeof(double) * (2 * (size_t)D + 1) + sizeof(int) * (2 * (size_t)D + 4));
+    k_part_closing<<<1, 1024, smem, S->st>>>(n, G, S->L, S->La, S->rank, S->recvbuf, S->Mpart, S->delta,
+                                             S->delta + (size_t)(S->N - 1) * n, (int*)(S->words + 2));
+    S->launches += 2;
+    return launch_check("part_closing");
+}
+
 static int abd_final(mirk_solver_s* S) {
     Plan& P = S->plan;
     const int n = S->n, D = P.Q * n;
     const bool m_in_smem = final_smem_bytes(D, true) <= kSmemLimit;
     const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n;
+    if (S->part && P.Q != 2) return fail(MIRK_ERR_STATE, "a mesh segment must reduce to one relation");
     if (warp_reduce_supported(n)) {
         TailArgs a;
+        a.mode = 7;
         a.nlev = P.nlev - P.tail_begin;
         for (int t = 0; t < a.nlev; t++) {
             const int l = P.tail_begin + t;
@@ -371,10 +452,19 @@ static int abd_final(mirk_solver_s* S) {
         a.relL = P.relL[P.nlev]; a.relR = P.relR[P.nlev]; a.relr = P.relr[P.nlev];
         a.L = S->L; a.La = S->La; a.m_ptr = S->m_dev; a.bc_nodes = S->bc_nodes; a.Bc = S->Bc; a.resid = S->resid;
         a.tail_off = tail_off; a.M = m_in_smem ? nullptr : S->Mfinal; a.delta = S->delta;
-        launch_warp_tail(S->st, n, a, final_smem_bytes(D, m_in_smem));
-        S->launches++;
-        return launch_check("abd_tail");
+        if (!S->part) {
+            CK(launch_warp_tail(S->st, n, a, 1, final_smem_bytes(D, m_in_smem)));
+            S->launches++;
+            return launch_check("abd_tail");
+        }
+        a.mode = 1;  // reduce the tail levels, exchange, close, then back-substitute them
+        if (a.nlev > 0) { CK(launch_warp_tail(S->st, n, a, 1, 0)); S->launches++; }
+        CKS(part_exchange_and_close(S));
+        a.mode = 4;
+        if (a.nlev > 0) { CK(launch_warp_tail(S->st, n, a, 1, 0)); S->launches++; }
+        return launch_check("abd_tail_partitioned");
     }
+    if (S->part) return part_exchange_and_close(S);
     const int threads = D * (D + 1) >= 4096 ? 1024 : 256;
     k_final_solve<<<1, threads, final_smem_bytes(D, m_in_smem), S->st>>>(
         n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, S->m_dev,
@@ -604,6 +694,38 @@ int mirk_problem_register_plugin(const char* name, const char* so_path, int32_t*
     return MIRK_OK;
 }
 
+int mirk_nccl_unique_id(void* id128, const char* libnccl_path) {
+    if (!id128) return fail(MIRK_ERR_ARG, "id buffer is NULL");
+    CKS(load_nccl(libnccl_path));
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return MIRK_OK;
+}
+
+int mirk_partition_attach(mirk_handle S, int32_t rank, int32_t nranks, const void* id128, const char* libnccl_path) {
+    if (!S || !id128) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MIRK_ERR_ARG, "bad rank / nranks");
+    if (S->ops->problem_type != 1) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning needs a TwoPointBVProblem");
+    if (S->desc.adaptive) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning runs on a fixed mesh (adaptive = false)");
+    if (S->part) return fail(MIRK_ERR_STATE, "already attached");
+    CKS(load_nccl(libnccl_path));
+    CK(cudaSetDevice(S->desc.device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    CKN(g_nccl.CommInitRank(&S->comm, nranks, id, rank));
+    const size_t pay = part_payload_doubles(S->n, S->L), D = (size_t)(nranks + 1) * S->n;
+    CK(dalloc(&S->sendbuf, pay));
+    CK(dalloc(&S->recvbuf, pay * nranks));
+    CK(dalloc(&S->Mpart, D * (D + 1)));
+    cudaFuncSetAttribute(k_part_closing, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    S->rank = rank;
+    S->nranks = nranks;
+    S->part = true;
+    S->jac_valid = S->resid_valid = false;
+    return MIRK_OK;
+}
+
 int mirk_mesh_uniform(double t0, double t1, int32_t nint, double* mesh) {
     if (!mesh || nint < 1) return fail(MIRK_ERR_ARG, "bad mesh request");
     mirk_mesh_uniform_fill(t0, t1, nint, mesh);  // binary128, host_util.cpp
@@ -618,6 +740,8 @@ int mirk_destroy(mirk_handle S) {
     dfree(S->p); dfree(S->Bc); dfree(S->scratch); dfree(S->Mfinal); dfree(S->tbuf); dfree(S->obuf);
     dfree(S->bc_nodes); dfree(S->m_dev); dfree(S->sel_out); dfree(S->words);
     dfree(S->plan.d_int); dfree(S->plan.d_rel);
+    dfree(S->sendbuf); dfree(S->recvbuf); dfree(S->Mpart);
+    if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
     if (S->h_words) cudaFreeHost(S->h_words);
     if (S->st) cudaStreamDestroy(S->st);
     delete S;
@@ -659,6 +783,7 @@ int mirk_create(const mirk_desc* desc, mirk_handle* out) {
             return fail(MIRK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2)); \
         }                                                                               \
     } while (0)
+    CKD(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, desc->device));
     CKD(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     CKD(dalloc(&S->p, S->h_p.size()));
     CKD(cudaMemcpy(S->p, S->h_p.data(), S->h_p.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -141,6 +141,16 @@ int mirk_bench_newton_steps(mirk_handle h, int32_t steps, float* total_ms, float
 /* roofline denominators measured on the device: FP64 FMA TFLOP/s and HBM copy GB/s */
 int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
 
+/* -- mesh-partitioned single problem (no reference counterpart: the reference is single-threaded).
+ *    Every rank creates a handle on its GPU holding one contiguous mesh segment (neighbours share their
+ *    boundary node) of a TwoPointBVProblem on a fixed mesh, then attaches it to a communicator.  From then
+ *    on mirk_residual / mirk_newton_step / mirk_newton_solve / mirk_solve / mirk_bench_newton_steps are
+ *    COLLECTIVE calls: per Newton step one 8-byte all-reduce(max) of |F|_inf and one all-gather of the
+ *    (2n^2 + n + 2Ln + L)-double reduced interface relation per rank, over NCCL on the solver's stream.
+ *    NCCL is dlopen'ed on first use (libnccl_path or the default soname), never at link time. */
+int mirk_nccl_unique_id(void* id128 /* 128 bytes */, const char* libnccl_path);
+int mirk_partition_attach(mirk_handle h, int32_t rank, int32_t nranks, const void* id128, const char* libnccl_path);
+
 /* -- ensembles: solve(EnsembleProblem(prob; prob_func), alg; trajectories, dt)
  *    (SciMLBase driver; usage lib/BoundaryValueDiffEqMIRK/test/Core/ensemble_tests.jl:20-38).
  *    The host harvests prob_func's parameters (and optionally per-trajectory u0) into packed arrays;

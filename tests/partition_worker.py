@@ -1,0 +1,54 @@
+"""torchrun worker of tests/test_gpu_partition.py: a mesh-partitioned Newton solve over WORLD_SIZE GPUs
+against the same solve on one GPU (rank 0), for the problems of BASELINE configs C2 (n = 16) and C5 (n = 32)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mirk_b200 as M  # noqa: E402
+from boundaryvaluediffeq_jl_b200 import configs, partition  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for maker, nint in (("c2_chain8", 4001), ("c5_chain16", 1203), ("c2_chain8", 20 * world + 3)):
+        c = getattr(configs, maker)(nint)
+        alg = M.MIRK6() if c.order == 6 else M.MIRK4()
+        prob = M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh)
+        cache, (lo, hi) = partition.init_partitioned(prob, alg, device=local)
+        r_loc, nrm0 = cache.residual()
+        ret, it, nrm = cache.newton_solve()
+        full = partition.gather_solution(cache, c.N)
+        if rank == 0:
+            ref = M.init(prob, alg, adaptive=False, device=local)
+            _, ref_nrm0 = ref.residual()
+            rret, rit, rnrm = ref.newton_solve()
+            _, u = ref.solution()
+            err = np.max(np.abs(full - u)) / np.max(np.abs(u))
+            print(f"{maker} N={c.N} world={world}: iters {it} vs {rit}, |F| {nrm:.3e} vs {rnrm:.3e}, rel err {err:.2e}", flush=True)
+            assert (ret, it) == (rret, rit) and ret == 0
+            assert abs(nrm0 - ref_nrm0) <= 1e-12 * max(1.0, ref_nrm0)
+            assert err < 1e-10
+            ref.close()
+        # timing of the collective Newton step (device events, max over ranks)
+        st, ms, ph, launches = cache.bench_newton_steps(5)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"  partitioned Newton step: {t.item() / 5:.3f} ms (phases us: {[round(1e3 * p / 5, 1) for p in ph[:7]]})", flush=True)
+        cache.close()
+    dist.barrier()
+    if rank == 0:
+        print("PARTITION_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

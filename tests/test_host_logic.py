@@ -67,6 +67,21 @@ def test_partition_covers_every_trajectory_once():
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
 
 
+def test_mesh_partition_segments_share_exactly_their_boundary_nodes():
+    import mirk_b200  # noqa: F401
+    from boundaryvaluediffeq_jl_b200.partition import partition_mesh
+    for N in (9, 20000, 2000001):
+        for world in (1, 2, 4, 8):
+            parts = partition_mesh(N, world)
+            assert parts[0][0] == 0 and parts[-1][1] == N - 1
+            for (lo0, hi0), (lo1, hi1) in zip(parts, parts[1:]):
+                assert hi0 == lo1
+            sizes = [hi - lo for lo, hi in parts]
+            assert sum(sizes) == N - 1 and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        partition_mesh(3, 4)
+
+
 def test_harvest_calls_prob_func_one_based():
     import mirk_b200 as M
     from boundaryvaluediffeq_jl_b200.ensemble import harvest
