@@ -129,6 +129,137 @@ def _config(cfg, n_gpus):
             "l2_policy": "per-step working set (Jacobian blocks + elimination factors, ~4 x 82 MB) exceeds the 126 MB L2"}
 
 
+def run_ensemble(args):
+    """BASELINE config C3: EnsembleProblem pendulum sweep, 262 144 BVPs, MIRK4, dt = 0.05, adaptive.
+    A step = one complete batched solve of this rank's shard.  strong scaling: the 262 144 trajectories are
+    block-partitioned over the ranks (no data-path collective); weak: 262 144 per rank."""
+    import math
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import configs, ensemble as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total = args.trajectories * (world if args.ensemble_scaling == "weak" else 1)
+    params_all = configs.c3_ensemble_params(total)
+    first, count = E.partition(total, world)[rank]
+    prob = M.BVProblem("pendulum", [math.pi / 2, math.pi / 2], (0.0, math.pi / 2), p=[9.81])
+    h = E.EnsembleHandle(prob, M.MIRK4(), count, 0.05, device=local)
+    pin = torch.empty(count, 1, dtype=torch.float64).pin_memory()
+    pin.numpy()[:] = params_all[first:first + count]
+    h.set_inputs(pin.numpy(), prob.u0)
+    for _ in range(args.warmup):
+        h.run()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ms = sum(h.run() for _ in range(args.steps))
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value = total * args.steps / (float(t.item()) * 1e-3)
+    res = h.results()
+    conv = torch.tensor([int(np.sum(res["retcodes"] == 0))], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(conv)
+    # end to end: parameters from pinned host memory, batched solve, outcomes back to the host, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.set_inputs(pin.numpy(), prob.u0)
+        h.run()
+        res = h.results()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            from oracle import oracle as O
+            nthreads = os.cpu_count() or 1
+            sample = 8192
+            t1 = time.perf_counter()
+            O.ensemble_solve(O.builtin("pendulum"), 4, params_all[:sample], prob.u0, prob.tspan, 32, nthreads=nthreads)
+            dt = time.perf_counter() - t1
+            cpu = {"value": sample / dt, "unit": "bvp_solves/s", "cores": nthreads, "kind": "port",
+                   "sample": f"first {sample} trajectories of the sweep, OpenMP over {nthreads} host threads (mirrors EnsembleThreads)"}
+        its = float(np.mean(res["newton_iters"]))
+        nm = float(np.mean(res["n_mesh"]))
+        print(json.dumps({
+            "metric": "ensemble_bvp_solves_per_sec", "value": value, "unit": "bvp_solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t.item()) / args.steps,
+            "higher_is_better": True, "scaling": args.ensemble_scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C3: EnsembleProblem pendulum parameter sweep, g/L ~ U(8,12), MIRK4, dt=0.05, adaptive, abstol=1e-6",
+                       "trajectories_total": total, "trajectories_per_gpu": count, "parallelism": f"trajectory shards x{world}",
+                       "l2_policy": "per-trajectory state slab (8.3 GB per 262144 trajectories) exceeds L2"},
+            "converged_fraction": float(conv.item()) / total, "mean_newton_iters": its, "mean_final_nodes": nm,
+            "e2e": {"value": total * args.steps / float(te.item()), "unit": "bvp_solves/s",
+                    "h2d_bytes_per_step": 8 * count + 16, "d2h_bytes_per_step": count * (4 * 4 + 8 * 2 + 16)},
+            "gpu_launches": 2 * args.steps, "cpu_baseline": cpu, "clocks": clocks}), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_partitioned(args):
+    """Mesh-partitioned single problem: C2's chain (n = 16, MIRK6), `--nint` intervals PER RANK (weak scaling),
+    one NCCL all-gather of the reduced interface relation + one 8-byte all-reduce per Newton step."""
+    import torch
+    import torch.distributed as dist
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import configs, partition
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    maker = configs.c5_chain16 if args.workload == "c5part" else configs.c2_chain8
+    c = maker(args.nint * world + (world - 1))
+    prob = M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh)
+    cache, (lo, hi) = partition.init_partitioned(prob, M.MIRK6(), device=local, chunk=args.chunk)
+    cache.bench_newton_steps(max(args.warmup, 5))
+    dist.barrier()
+    torch.cuda.synchronize()
+    st, ms, ph, launches = cache.bench_newton_steps(args.steps)
+    dist.barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        per_step = float(t.item()) / args.steps
+        print(json.dumps({
+            "metric": "mirk_newton_steps_per_sec_mesh_partitioned", "value": 1e3 / per_step, "unit": "newton_steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
+            "scaling": "weak", "dtype": "f64", "data": "synthetic",
+            "mesh_interval_updates_per_sec": (c.N - 1) * 1e3 / per_step,
+            "config": {"workload": f"{c.desc}; mesh partitioned into {world} segments", "mesh_nodes_total": c.N,
+                       "mesh_nodes_per_gpu": hi - lo + 1, "n_states": c.n,
+                       "collectives_per_step": "1 all-reduce(max) of 8 B + 1 all-gather of (2n^2+n+2Ln+L) doubles per rank"},
+            "phases_us_rank0": [round(1e3 * p / args.steps, 1) for p in ph[:7]], "gpu_launches": int(launches)}), flush=True)
+    cache.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,9 +268,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nint", type=int, default=19999, help="mesh intervals (default: C2's 19 999)")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2part", "c5part"],
+                    help="c2: the headline Newton-step metric (default); c3: ensemble sweep; c2part/c5part: mesh-partitioned")
+    ap.add_argument("--trajectories", type=int, default=262144)
+    ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200" and args.workload == "c3":
+        return run_ensemble(args)
+    if args.impl == "b200" and args.workload in ("c2part", "c5part"):
+        return run_partitioned(args)
 
     import numpy as np
 
