@@ -260,54 +260,27 @@ __global__ void k_part_pack(int n, int L, int La, const double* __restrict__ rel
     for (int e = tid; e < 2 * L * n; e += T) ob[e] = Bc[e];
     for (int q = tid; q < L; q += T) ob[2 * L * n + q] = q < La ? resid[q] : resid[tail_off + (q - La)];
 }
-// Interface system on the G+1 segment end nodes: rows [bc_a (rank 0) ; relation 0 ; ... ; relation G-1 ; bc_b
-// (rank G-1)], dense row-pivoted Gauss-Jordan in a global scratch matrix.  Writes this rank's two end updates.
-__global__ void __launch_bounds__(1024)
-k_part_closing(int n, int G, int L, int La, int rank, const double* __restrict__ recv, double* M,
-               double* __restrict__ delta_first, double* __restrict__ delta_last, int* __restrict__ status) {
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int D = (G + 1) * n, cols = D + 1, ld = cols, nn = n * n;
+// gathered payloads -> contiguous relation arrays of the interface system + its boundary blocks:
+// block 0 (node 0) = rank 0's bc_a rows, block 1 (node G) = rank G-1's bc_b rows; if_resid = [bc_a ; bc_b]
+__global__ void k_part_unpack(int n, int G, int L, int La, const double* __restrict__ recv, double* __restrict__ oL,
+                              double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
+                              double* __restrict__ oresid) {
+    const int nn = n * n, tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
     const size_t P = part_payload_doubles(n, L);
-    double* mult = smem;
-    double* prow = mult + D;
-    int* elig = (int*)(prow + cols);
-    int* pivrow = elig + D;
-    int* s_p = pivrow + D;
-    for (int e = tid; e < D * cols; e += T) M[e] = 0.0;
-    __syncthreads();
-    const double* b0 = recv + 2 * nn + n;                          // rank 0: bc_a rows act on node 0 (block 0)
-    const double* bG = recv + (size_t)(G - 1) * P + 2 * nn + n;    // rank G-1: bc_b rows act on node G (block 1)
-    for (int e = tid; e < L * n; e += T) {
-        const int q = e / n, c = e % n;
-        if (q < La) M[(size_t)q * ld + c] = b0[(size_t)q * n + c];
-        else M[(size_t)(D - L + q) * ld + G * n + c] = bG[((size_t)L + q) * n + c];
-    }
-    for (int q = tid; q < L; q += T) {
-        if (q < La) M[(size_t)q * ld + D] = b0[2 * L * n + q];
-        else M[(size_t)(D - L + q) * ld + D] = bG[2 * L * n + q];
-    }
     for (int e = tid; e < G * nn; e += T) {
-        const int g = e / nn, q = (e % nn) / n, c = e % n;
-        const double* pl = recv + (size_t)g * P;
-        double* row = M + (size_t)(La + g * n + q) * ld;
-        row[g * n + c] = pl[(size_t)q * n + c];
-        row[(g + 1) * n + c] = pl[nn + (size_t)q * n + c];
+        const int g = e / nn, k = e % nn;
+        oL[e] = recv[(size_t)g * P + k];
+        oR[e] = recv[(size_t)g * P + nn + k];
     }
-    for (int e = tid; e < G * n; e += T) {
-        const int g = e / n, q = e % n;
-        M[(size_t)(La + g * n + q) * ld + D] = recv[(size_t)g * P + 2 * nn + q];
+    for (int e = tid; e < G * n; e += T) orr[e] = recv[(size_t)(e / n) * P + 2 * nn + e % n];
+    const double* b0 = recv + 2 * nn + n;
+    const double* bG = recv + (size_t)(G - 1) * P + 2 * nn + n;
+    for (int e = tid; e < L * n; e += T) {
+        const int q = e / n;
+        oBc[e] = q < La ? b0[e] : 0.0;                        // block 0: Bc[0][q][c]
+        oBc[L * n + e] = q < La ? 0.0 : bG[L * n + e];        // block 1: Bc[1][q][c]
     }
-    for (int r = tid; r < D; r += T) elig[r] = 1;
-    __syncthreads();
-    if (!block_gauss_jordan(M, D, cols, ld, D, elig, pivrow, mult, prow, s_p)) {
-        if (tid == 0) atomicExch(status, 1);
-        return;
-    }
-    for (int c = tid; c < n; c += T) {
-        delta_first[c] = M[(size_t)pivrow[rank * n + c] * ld + D];
-        delta_last[c] = M[(size_t)pivrow[(rank + 1) * n + c] * ld + D];
-    }
+    for (int q = tid; q < L; q += T) oresid[q] = q < La ? b0[2 * L * n + q] : bG[2 * L * n + q];
 }
 // |bc rows|_inf of the rows this rank owns (a-rows on rank 0, b-rows on the last rank) into norm_bits
 __global__ void k_bc_norm_masked(int L, int La, const double* __restrict__ resid, size_t tail_off, int own_a, int own_b,

@@ -168,7 +168,12 @@ struct mirk_solver_s {
     bool part = false;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
-    double *sendbuf = nullptr, *recvbuf = nullptr, *Mpart = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    // interface system on the nranks+1 segment end nodes
+    Plan iplan;
+    double *if_L = nullptr, *if_R = nullptr, *if_r = nullptr, *if_TL = nullptr, *if_TR = nullptr, *if_rt = nullptr,
+           *if_delta = nullptr, *if_Bc = nullptr, *if_resid = nullptr;
+    int *if_bc_nodes = nullptr, *if_m = nullptr;
     bool jac_valid = false, resid_valid = false;
     double last_resid_norm = NAN;
 };
@@ -215,12 +220,20 @@ static int reduce_small_smem_bytes(int n) {  // only mult/prow/ints when W lives
 }
 static const int kSmemLimit = 200 * 1024;
 
+static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pinned, double* rel0L, double* rel0R,
+                          double* rel0r);
+
 static int build_plan(mirk_solver_s* S) {
-    Plan& P = S->plan;
-    const int N = S->N, n = S->n;
     int bcn[16];
-    const int m = S->ops->bc_nodes_host(N, S->h_mesh.data(), S->h_p.data(), bcn);
-    std::vector<int> pinned(bcn, bcn + m);
+    const int m = S->ops->bc_nodes_host(S->N, S->h_mesh.data(), S->h_p.data(), bcn);
+    // level-0 relations are the Jacobian blocks; Phi rows start after the leading boundary rows
+    return build_plan_for(S, S->plan, S->N, std::vector<int>(bcn, bcn + m), S->Lb, S->Rb, S->resid + S->La);
+}
+
+// Levels of the block cyclic reduction over N nodes whose `pinned` nodes are never eliminated.
+static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pinned, double* rel0L, double* rel0R,
+                          double* rel0r) {
+    const int n = S->n;
     std::sort(pinned.begin(), pinned.end());
     pinned.erase(std::unique(pinned.begin(), pinned.end()), pinned.end());
     // desc.chunk packs the reduction shape: bits 0-7 relations per group at level 0 (default 8),
@@ -291,9 +304,9 @@ static int build_plan(mirk_solver_s* S) {
     }
     std::vector<int> hint(ints);
     size_t io = 0, ro = 0;
-    P.relL[0] = S->Lb;
-    P.relR[0] = S->Rb;
-    P.relr[0] = S->resid + S->La;  // Phi rows start after the leading boundary rows
+    P.relL[0] = rel0L;
+    P.relR[0] = rel0R;
+    P.relr[0] = rel0r;
     for (int l = 0; l < P.nlev; l++) {
         P.d_nodes[l] = P.d_int + io;
         std::copy(nodes_l[l].begin(), nodes_l[l].end(), hint.begin() + io);
@@ -387,20 +400,37 @@ static int eval_resjac(mirk_solver_s* S) {
     return launch_check("resjac");
 }
 
-static int abd_reduce(mirk_solver_s* S, int l_begin = 0, int l_end = kMaxLev) {
-    Plan& P = S->plan;
+// what one almost-block-diagonal solve works on: the mesh system of this handle, or (mesh-partitioned
+// mode) the small interface system on the segment end nodes
+struct SolveCtx {
+    Plan* P;
+    double *TL, *TR, *rt, *delta;
+    const double* Bc;
+    const int* bc_nodes;
+    const int* m_dev;
+    const double* resid;
+    size_t tail_off;
+    bool exchange;  // run the partition exchange in place of the closing solve
+};
+static SolveCtx main_ctx(mirk_solver_s* S) {
+    return SolveCtx{&S->plan, S->TL, S->TR, S->rt, S->delta, S->Bc, S->bc_nodes, S->m_dev, S->resid,
+                    (size_t)S->La + (size_t)(S->N - 1) * S->n, S->part};
+}
+
+static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int l_end = kMaxLev) {
+    Plan& P = *C.P;
     const int n = S->n;
     const bool smem_ok = reduce_smem_bytes(n) <= kSmemLimit;
     for (int l = l_begin; l < P.tail_begin && l < l_end; l++) {
         if (warp_reduce_supported(n)) {
             launch_warp_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
-                               P.relr[l + 1], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt,
+                               P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt,
                                (int*)(S->words + 2));
         } else {
             const int smem = smem_ok ? reduce_smem_bytes(n) : reduce_small_smem_bytes(n);
             k_reduce_generic<<<P.G[l], 256, smem, S->st>>>(n, P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1],
                                                             P.relR[l + 1], P.relr[l + 1], P.d_nodes[l],
-                                                            P.d_gs[l], S->TL, S->TR, S->rt, S->scratch,
+                                                            P.d_gs[l], C.TL, C.TR, C.rt, S->scratch,
                                                             smem_ok ? 1 : 0, (int*)(S->words + 2));
         }
         S->launches++;
@@ -414,29 +444,39 @@ static int final_smem_bytes(int D, bool m_in_smem) {
     return (int)b;
 }
 
+static int abd_final(mirk_solver_s* S, const SolveCtx& C);
+static int abd_backsub(mirk_solver_s* S, const SolveCtx& C);
+
 // mesh-partitioned closing: pack this segment's collapsed relation (+ the boundary blocks it owns), one
-// NCCL all-gather of (2n^2 + n + 2Ln + L) doubles per rank on the solver's stream, then the interface
-// system on the G+1 segment end nodes is solved redundantly by every rank
+// NCCL all-gather of (2n^2 + n + 2Ln + L) doubles per rank on the solver's stream, then every rank solves
+// the interface system on the G+1 segment end nodes redundantly — it is itself almost block diagonal, so
+// it goes through the same reduction (radix-2 levels + closing solve + back substitution).
 static int part_exchange_and_close(mirk_solver_s* S) {
     Plan& P = S->plan;
-    const int n = S->n, G = S->nranks, D = (G + 1) * n;
+    const int n = S->n, G = S->nranks;
     const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n, pay = part_payload_doubles(n, S->L);
     k_part_pack<<<8, 256, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
                                       tail_off, S->sendbuf);
     CKN(g_nccl.AllGather(S->sendbuf, S->recvbuf, pay, ncclDouble, S->comm, S->st));
-    const int smem = (int)(sizeof(double) * (2 * (size_t)D + 1) + sizeof(int) * (2 * (size_t)D + 4));
-    k_part_closing<<<1, 1024, smem, S->st>>>(n, G, S->L, S->La, S->rank, S->recvbuf, S->Mpart, S->delta,
-                                             S->delta + (size_t)(S->N - 1) * n, (int*)(S->words + 2));
+    k_part_unpack<<<8, 256, 0, S->st>>>(n, G, S->L, S->La, S->recvbuf, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid);
     S->launches += 2;
+    SolveCtx I{&S->iplan, S->if_TL, S->if_TR, S->if_rt, S->if_delta, S->if_Bc, S->if_bc_nodes, S->if_m, S->if_resid,
+               (size_t)S->La, false};
+    CKS(abd_reduce(S, I));
+    CKS(abd_final(S, I));
+    CKS(abd_backsub(S, I));
+    // this rank's two end nodes
+    CK(cudaMemcpyAsync(S->delta, S->if_delta + (size_t)S->rank * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaMemcpyAsync(S->delta + (size_t)(S->N - 1) * n, S->if_delta + (size_t)(S->rank + 1) * n, sizeof(double) * n,
+                       cudaMemcpyDeviceToDevice, S->st));
     return launch_check("part_closing");
 }
 
-static int abd_final(mirk_solver_s* S) {
-    Plan& P = S->plan;
+static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
+    Plan& P = *C.P;
     const int n = S->n, D = P.Q * n;
     const bool m_in_smem = final_smem_bytes(D, true) <= kSmemLimit;
-    const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n;
-    if (S->part && P.Q != 2) return fail(MIRK_ERR_STATE, "a mesh segment must reduce to one relation");
+    if (C.exchange && P.Q != 2) return fail(MIRK_ERR_STATE, "a mesh segment must reduce to one relation");
     if (warp_reduce_supported(n)) {
         TailArgs a;
         a.mode = 7;
@@ -447,41 +487,40 @@ static int abd_final(mirk_solver_s* S) {
             a.inL[t] = P.relL[l]; a.inR[t] = P.relR[l]; a.inr[t] = P.relr[l];
             a.outL[t] = P.relL[l + 1]; a.outR[t] = P.relR[l + 1]; a.outr[t] = P.relr[l + 1];
         }
-        a.TL = S->TL; a.TR = S->TR; a.rt = S->rt; a.status = (int*)(S->words + 2);
+        a.TL = C.TL; a.TR = C.TR; a.rt = C.rt; a.status = (int*)(S->words + 2);
         a.Q = P.Q; a.kept = P.d_nodes[P.nlev];
         a.relL = P.relL[P.nlev]; a.relR = P.relR[P.nlev]; a.relr = P.relr[P.nlev];
-        a.L = S->L; a.La = S->La; a.m_ptr = S->m_dev; a.bc_nodes = S->bc_nodes; a.Bc = S->Bc; a.resid = S->resid;
-        a.tail_off = tail_off; a.M = m_in_smem ? nullptr : S->Mfinal; a.delta = S->delta;
-        if (!S->part) {
+        a.L = S->L; a.La = S->La; a.m_ptr = C.m_dev; a.bc_nodes = C.bc_nodes; a.Bc = C.Bc; a.resid = C.resid;
+        a.tail_off = C.tail_off; a.M = m_in_smem ? nullptr : S->Mfinal; a.delta = C.delta;
+        if (!C.exchange) {
             CK(launch_warp_tail(S->st, n, a, 1, final_smem_bytes(D, m_in_smem)));
             S->launches++;
             return launch_check("abd_tail");
         }
-        a.mode = 1;  // reduce the tail levels, exchange, close, then back-substitute them
+        a.mode = 1;  // reduce the tail levels, exchange + close the interface system, back-substitute them
         if (a.nlev > 0) { CK(launch_warp_tail(S->st, n, a, 1, 0)); S->launches++; }
         CKS(part_exchange_and_close(S));
         a.mode = 4;
         if (a.nlev > 0) { CK(launch_warp_tail(S->st, n, a, 1, 0)); S->launches++; }
         return launch_check("abd_tail_partitioned");
     }
-    if (S->part) return part_exchange_and_close(S);
+    if (C.exchange) return part_exchange_and_close(S);
     const int threads = D * (D + 1) >= 4096 ? 1024 : 256;
     k_final_solve<<<1, threads, final_smem_bytes(D, m_in_smem), S->st>>>(
-        n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, S->m_dev,
-        S->bc_nodes, S->Bc, S->resid, tail_off, m_in_smem ? nullptr : S->Mfinal, S->delta,
-        (int*)(S->words + 2));
+        n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, C.m_dev,
+        C.bc_nodes, C.Bc, C.resid, C.tail_off, m_in_smem ? nullptr : S->Mfinal, C.delta, (int*)(S->words + 2));
     S->launches++;
     return launch_check("abd_final");
 }
 
-static int abd_backsub(mirk_solver_s* S) {
-    Plan& P = S->plan;
+static int abd_backsub(mirk_solver_s* S, const SolveCtx& C) {
+    Plan& P = *C.P;
     const int n = S->n;
     for (int l = P.tail_begin - 1; l >= 0; l--) {
         if (warp_reduce_supported(n))
-            launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt, S->delta);
+            launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
         else
-            k_backsub_generic<<<P.G[l], 256, 0, S->st>>>(n, P.d_nodes[l], P.d_gs[l], S->TL, S->TR, S->rt, S->delta);
+            k_backsub_generic<<<P.G[l], 256, 0, S->st>>>(n, P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
         S->launches++;
     }
     return launch_check("abd_backsub");
@@ -490,9 +529,10 @@ static int abd_backsub(mirk_solver_s* S) {
 static int linear_solve(mirk_solver_s* S) {
     CKS(build_plan(S));
     CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
-    CKS(abd_reduce(S));
-    CKS(abd_final(S));
-    CKS(abd_backsub(S));
+    const SolveCtx C = main_ctx(S);
+    CKS(abd_reduce(S, C));
+    CKS(abd_final(S, C));
+    CKS(abd_backsub(S, C));
     return MIRK_OK;
 }
 
@@ -714,13 +754,21 @@ int mirk_partition_attach(mirk_handle S, int32_t rank, int32_t nranks, const voi
     ncclUniqueId id;
     memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
     CKN(g_nccl.CommInitRank(&S->comm, nranks, id, rank));
-    const size_t pay = part_payload_doubles(S->n, S->L), D = (size_t)(nranks + 1) * S->n;
+    const size_t pay = part_payload_doubles(S->n, S->L), nn = (size_t)S->n * S->n, Q = (size_t)nranks + 1;
     CK(dalloc(&S->sendbuf, pay));
     CK(dalloc(&S->recvbuf, pay * nranks));
-    CK(dalloc(&S->Mpart, D * (D + 1)));
-    cudaFuncSetAttribute(k_part_closing, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    CK(dalloc(&S->if_L, nn * nranks)); CK(dalloc(&S->if_R, nn * nranks)); CK(dalloc(&S->if_r, (size_t)S->n * nranks));
+    CK(dalloc(&S->if_TL, nn * Q)); CK(dalloc(&S->if_TR, nn * Q)); CK(dalloc(&S->if_rt, (size_t)S->n * Q));
+    CK(dalloc(&S->if_delta, (size_t)S->n * Q));
+    CK(dalloc(&S->if_Bc, (size_t)2 * S->L * S->n)); CK(dalloc(&S->if_resid, (size_t)S->L));
+    CK(dalloc(&S->if_bc_nodes, 2)); CK(dalloc(&S->if_m, 1));
+    const int hb[2] = {0, nranks}, hm = 2;
+    CK(cudaMemcpy(S->if_bc_nodes, hb, sizeof(hb), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->if_m, &hm, sizeof(int), cudaMemcpyHostToDevice));
     S->rank = rank;
     S->nranks = nranks;
+    // interface plan: nranks relations on nranks+1 nodes, the two outer ends carry the boundary rows
+    CKS(build_plan_for(S, S->iplan, nranks + 1, std::vector<int>{0, nranks}, S->if_L, S->if_R, S->if_r));
     S->part = true;
     S->jac_valid = S->resid_valid = false;
     return MIRK_OK;
@@ -740,7 +788,10 @@ int mirk_destroy(mirk_handle S) {
     dfree(S->p); dfree(S->Bc); dfree(S->scratch); dfree(S->Mfinal); dfree(S->tbuf); dfree(S->obuf);
     dfree(S->bc_nodes); dfree(S->m_dev); dfree(S->sel_out); dfree(S->words);
     dfree(S->plan.d_int); dfree(S->plan.d_rel);
-    dfree(S->sendbuf); dfree(S->recvbuf); dfree(S->Mpart);
+    dfree(S->sendbuf); dfree(S->recvbuf);
+    dfree(S->if_L); dfree(S->if_R); dfree(S->if_r); dfree(S->if_TL); dfree(S->if_TR); dfree(S->if_rt);
+    dfree(S->if_delta); dfree(S->if_Bc); dfree(S->if_resid); dfree(S->if_bc_nodes); dfree(S->if_m);
+    dfree(S->iplan.d_int); dfree(S->iplan.d_rel);
     if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
     if (S->h_words) cudaFreeHost(S->h_words);
     if (S->st) cudaStreamDestroy(S->st);
@@ -1131,13 +1182,14 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
         CKS(eval_resjac(S));
         CK(cudaEventRecord(e[2], S->st));
         CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
-        CKS(abd_reduce(S, 0, 1));
+        const SolveCtx C = main_ctx(S);
+        CKS(abd_reduce(S, C, 0, 1));
         CK(cudaEventRecord(e[3], S->st));
-        CKS(abd_reduce(S, 1, kMaxLev));
+        CKS(abd_reduce(S, C, 1, kMaxLev));
         CK(cudaEventRecord(e[4], S->st));
-        CKS(abd_final(S));
+        CKS(abd_final(S, C));
         CK(cudaEventRecord(e[5], S->st));
-        CKS(abd_backsub(S));
+        CKS(abd_backsub(S, C));
         CK(cudaEventRecord(e[6], S->st));
         CKS(apply_update(S));
         CK(cudaEventRecord(e[7], S->st));
