@@ -150,15 +150,22 @@ template <class P, int ORDER> struct EnsSolver {
     // F(y): Phi and stages for every interval, boundary rows; returns |F|_inf, bc rows in rbc
     __device__ __noinline__ double residual_sweep(double* rbc) {
         double nrm = 0.0;
-        double yi[n], yi1[n];
+        double yi[n], yi1[n], ynx[n];
 #pragma unroll
-        for (int k = 0; k < n; k++) yi1[k] = Y(0, k);
-        double tn = MESH(0);
+        for (int k = 0; k < n; k++) { yi1[k] = Y(0, k); ynx[k] = Y(1, k); }
+        double tn = MESH(0), tnx = MESH(1);
         for (int i = 0; i < N - 1; i++) {
             const double ti = tn;
-            tn = MESH(i + 1);
+            tn = tnx;
 #pragma unroll
-            for (int k = 0; k < n; k++) { yi[k] = yi1[k]; yi1[k] = Y(i + 1, k); }
+            for (int k = 0; k < n; k++) { yi[k] = yi1[k]; yi1[k] = ynx[k]; }
+            // software prefetch of node i+2: the stores below go through the same base pointer, so the
+            // compiler cannot hoist the next iteration's loads above them by itself
+            if (i + 2 < N) {
+                tnx = MESH(i + 2);
+#pragma unroll
+                for (int k = 0; k < n; k++) ynx[k] = Y(i + 2, k);
+            }
             double K[s][n], phi[n];
             phi_interval<P, ORDER, double>(yi, yi1, tn - ti, ti, p, K, phi);
 #pragma unroll
@@ -213,16 +220,21 @@ template <class P, int ORDER> struct EnsSolver {
         // Jacobian sweep fused with the elimination
         double W[rows][cols];
         int seg = 0;
-        double yv[n], yv1[n];
+        double yv[n], yv1[n], ynx[n], phc[n], phn[n];
 #pragma unroll (UF)
-        for (int k = 0; k < n; k++) yv1[k] = Y(0, k);
-        double tn = MESH(0);
+        for (int k = 0; k < n; k++) { yv1[k] = Y(0, k); ynx[k] = Y(1, k); phn[k] = PHI(0, k); }
+        double tn = MESH(0), tnx = MESH(1);
         for (int i = 0; i < N - 1; i++) {
             const double ti = tn;
-            tn = MESH(i + 1);
+            tn = tnx;
             const double h = tn - ti;
 #pragma unroll (UF)
-            for (int k = 0; k < n; k++) { yv[k] = yv1[k]; yv1[k] = Y(i + 1, k); }
+            for (int k = 0; k < n; k++) { yv[k] = yv1[k]; yv1[k] = ynx[k]; phc[k] = phn[k]; }
+            if (i + 2 < N) {  // software prefetch of the next interval's inputs (see residual_sweep)
+                tnx = MESH(i + 2);
+#pragma unroll (UF)
+                for (int k = 0; k < n; k++) { ynx[k] = Y(i + 2, k); phn[k] = PHI(i + 1, k); }
+            }
             double Lm[n][n], Rm[n][n];
 #pragma unroll (UF)
             for (int d = 0; d < 2 * n; d++) {
@@ -245,14 +257,14 @@ template <class P, int ORDER> struct EnsSolver {
                 for (int q = 0; q < n; q++) {
 #pragma unroll (UF)
                     for (int k = 0; k < n; k++) { W[q][k] = Rm[q][k]; W[q][n + k] = Lm[q][k]; W[q][2 * n + k] = 0.0; }
-                    W[q][3 * n] = PHI(i, q);
+                    W[q][3 * n] = phc[q];
                 }
             } else {
 #pragma unroll (UF)
                 for (int q = 0; q < n; q++) {
 #pragma unroll (UF)
                     for (int k = 0; k < n; k++) { W[n + q][k] = Lm[q][k]; W[n + q][n + k] = 0.0; W[n + q][2 * n + k] = Rm[q][k]; }
-                    W[n + q][3 * n] = PHI(i, q);
+                    W[n + q][3 * n] = phc[q];
                 }
                 // row-pivoted Gauss-Jordan on the n E-columns, pivot row swapped into place
 #pragma unroll (UF)
@@ -333,6 +345,50 @@ template <class P, int ORDER> struct EnsSolver {
             double da[n], dr[n];
 #pragma unroll (UF)
             for (int k = 0; k < n; k++) { da[k] = M[sg * n + k][D]; dr[k] = M[(sg + 1) * n + k][D]; }
+            if constexpr (n <= 2) {
+                // factors of the next node are fetched before the current node's read-modify-write of y
+                double crt[n], ctl[n][n], ctr[n][n], nrt[n], ntl[n][n], ntr[n][n];
+                int c = kept[sg + 1] - 1;
+                if (c > kept[sg]) {
+#pragma unroll
+                    for (int q = 0; q < n; q++) {
+                        nrt[q] = RTF(c, q);
+#pragma unroll
+                        for (int k = 0; k < n; k++) { ntl[q][k] = TLF(c, q, k); ntr[q][k] = TRF(c, q, k); }
+                    }
+                }
+                double yc[n], ycn[n];
+#pragma unroll
+                for (int k = 0; k < n; k++) ycn[k] = (c > kept[sg]) ? Y(c, k) : 0.0;
+                for (; c > kept[sg]; c--) {
+#pragma unroll
+                    for (int q = 0; q < n; q++) {
+                        crt[q] = nrt[q];
+                        yc[q] = ycn[q];
+#pragma unroll
+                        for (int k = 0; k < n; k++) { ctl[q][k] = ntl[q][k]; ctr[q][k] = ntr[q][k]; }
+                    }
+                    if (c - 1 > kept[sg]) {
+#pragma unroll
+                        for (int q = 0; q < n; q++) {
+                            nrt[q] = RTF(c - 1, q);
+                            ycn[q] = Y(c - 1, q);
+#pragma unroll
+                            for (int k = 0; k < n; k++) { ntl[q][k] = TLF(c - 1, q, k); ntr[q][k] = TRF(c - 1, q, k); }
+                        }
+                    }
+                    double dc[n];
+#pragma unroll
+                    for (int q = 0; q < n; q++) {
+                        double acc = crt[q];
+#pragma unroll
+                        for (int k = 0; k < n; k++) acc -= ctl[q][k] * da[k] + ctr[q][k] * dr[k];
+                        dc[q] = acc;
+                    }
+#pragma unroll
+                    for (int k = 0; k < n; k++) { Y(c, k) = yc[k] - dc[k]; dr[k] = dc[k]; }
+                }
+            } else {
             for (int c = kept[sg + 1] - 1; c > kept[sg]; c--) {
                 double dc[n];
 #pragma unroll (UF)
@@ -344,6 +400,7 @@ template <class P, int ORDER> struct EnsSolver {
                 }
 #pragma unroll (UF)
                 for (int k = 0; k < n; k++) { Y(c, k) -= dc[k]; dr[k] = dc[k]; }
+            }
             }
         }
         for (int e = 0; e < Q; e++)

@@ -295,3 +295,46 @@ def test_large_block_problems_match_golden(M, key, maker, nint):
     assert abs(u.sum() - gold["sum"]) < 1e-9 * gold["sum_abs"]
     assert np.max(np.abs(u[c.N // 2] - np.array(gold["y_mid"]))) < 1e-9
     cache.close()
+
+
+USER_FUNCTOR = r"""
+// u'' + lam * exp(u) = 0, u(0) = u(1) = 0 (1-D Bratu) as a user-supplied device functor
+struct UserBratu {
+    static constexpr int n = 2, np = 1, n_bc = 2, n_bca = 1, problem_type = 1, max_bc_pts = 2;
+    MIRK_PF f(T* du, const T* u, const double* p, double) {
+        using namespace fn;
+        du[0] = u[1];
+        du[1] = -p[0] * exp(u[0]);
+    }
+    MIRK_PT bc_times(double* tm, const double*, double t0, double t1) { return ends_times(tm, t0, t1); }
+    MIRK_PF bc(T* r, const T* U, const double*) {
+        r[0] = U[0];
+        r[1] = U[2];
+    }
+};
+"""
+
+
+def test_user_supplied_device_functor_plugin(M, oracle, tmp_path):
+    """The CUDA-side twin of passing Julia closures f!/bc! to BVProblem: a user functor compiled with nvcc
+    into a plugin and registered at run time, checked against the oracle driven by python callbacks."""
+    O = oracle
+    f = M.compile_device_function("user_bratu", "UserBratu", USER_FUNCTOR, workdir=str(tmp_path))
+    assert f.info.n == 2 and f.info.problem_type == 1
+    lam = 1.0
+    P = O.custom_problem(
+        2, 1,
+        f=lambda u, p, t: np.array([u[1], -p[0] * np.exp(u[0])]),
+        dfdu=lambda u, p, t: np.array([[0.0, 1.0], [-p[0] * np.exp(u[0]), 0.0]]),
+        bc_times=lambda p, t0, t1: [t0, t1],
+        bc=lambda U, p: np.array([U[0, 0], U[1, 0]]),
+        dbc=lambda U, p: np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]]),
+        problem_type=1, n_bc=2, n_bca=1)
+    for alg, order in ((M.MIRK4(), 4), (M.MIRK6(), 6)):
+        ref = O.solve_dt(P, order, [lam], [0.0, 0.0], (0.0, 1.0), 0.1)
+        sol = M.solve(M.BVProblem(f, [0.0, 0.0], (0.0, 1.0), p=[lam]), alg, dt=0.1)
+        assert sol.retcode == ref.retcode == 0
+        assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+        assert _rel(sol.u, ref.u) < 1e-10
+    # known answer: u(1/2) = 2 ln(cosh(theta/4)... for lam = 1: max u = 0.14050 (Bratu lower branch)
+    assert abs(sol(0.5)[0] - 0.1405392) < 1e-5
