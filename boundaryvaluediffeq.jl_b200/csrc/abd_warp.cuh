@@ -66,6 +66,15 @@ template <int n> struct WarpABD {
             const unsigned mx = __reduce_max_sync(kFullMask, key);
             if ((mx >> 5) == 0u || mx >= 0x7ff00000u) return false;
             const int pr = 31 - (int)(mx & 31u);
+#if defined(MIRK_BCAST_SHFL)
+            // measured alternative: broadcast the pivot row by warp shuffles instead of shared memory
+            if (lane == pr) { elig = false; myq = q; myinv = own_inv; }
+            const double inv = __shfl_sync(kFullMask, own_inv, pr);
+            const double m = (lane == pr) ? 0.0 : -(own * inv);
+#pragma unroll
+            for (int c = q + 1; c < cols; c++) w[c] = fma(m, __shfl_sync(kFullMask, w[c], pr), w[c]);
+            (void)pb;
+#else
             double* line = pb + (q & 1) * pb_stride;
             if (lane == pr) {
 #pragma unroll
@@ -90,6 +99,7 @@ template <int n> struct WarpABD {
                 if (c > q) w[c] = fma(m, v.x, w[c]);
                 if (c + 1 < cols) w[(c + 1 < cols) ? c + 1 : c] = fma(m, v.y, w[(c + 1 < cols) ? c + 1 : c]);
             }
+#endif
         }
         return true;
     }

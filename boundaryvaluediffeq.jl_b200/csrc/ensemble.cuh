@@ -619,8 +619,8 @@ template <class P, int ORDER> struct EnsSolver {
     }
 };
 
-template <class P, int ORDER>
-__global__ void __launch_bounds__(64)
+template <class P, int ORDER, int MINB = 1>
+__global__ void __launch_bounds__(64, MINB)
 k_ensemble_solve(EnsArgs a) {
     using ES = EnsSolver<P, ORDER>;
     using LY = EnsLayout<P, ORDER>;

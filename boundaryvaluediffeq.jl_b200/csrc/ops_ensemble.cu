@@ -6,7 +6,10 @@ using namespace problems;
 template <class P, int ORDER> struct EnsImpl {
     static void run(cudaStream_t st, const EnsArgs& a) {
         const long long blocks = (a.ntraj + 63) / 64;
-        k_ensemble_solve<P, ORDER><<<(unsigned)blocks, 64, 0, st>>>(a);
+        // n <= 2: cap registers at 96 (10 CTAs of 64 threads per SM): the kernel is memory-latency bound and
+        // the extra resident warps buy 17 % (experiments/exp_ens.cu); larger n needs the registers
+        constexpr int MINB = P::n <= 2 ? 10 : 1;
+        k_ensemble_solve<P, ORDER, MINB><<<(unsigned)blocks, 64, 0, st>>>(a);
     }
     static EnsembleOps make() {
         using LY = EnsLayout<P, ORDER>;
