@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "abd.cuh"
+#include "abd_pair.cuh"
 #include "abd_warp.cuh"
 #include "ensemble.cuh"
 #include "generic_kernels.cuh"
@@ -426,6 +427,9 @@ static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int 
             launch_warp_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
                                P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt,
                                (int*)(S->words + 2));
+        } else if (pair_reduce_supported(n)) {
+            launch_pair_reduce(S->st, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
+                               P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, (int*)(S->words + 2));
         } else {
             const int smem = smem_ok ? reduce_smem_bytes(n) : reduce_small_smem_bytes(n);
             k_reduce_generic<<<P.G[l], 256, smem, S->st>>>(n, P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1],
@@ -519,6 +523,8 @@ static int abd_backsub(mirk_solver_s* S, const SolveCtx& C) {
     for (int l = P.tail_begin - 1; l >= 0; l--) {
         if (warp_reduce_supported(n))
             launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
+        else if (pair_reduce_supported(n))
+            launch_pair_backsub(S->st, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
         else
             k_backsub_generic<<<P.G[l], 256, 0, S->st>>>(n, P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
         S->launches++;
