@@ -383,6 +383,11 @@ def main():
             "update": 8 * 3 * n * N,
         }
         hbm_peak, peak_src = _peaks()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and cfg.N == 20000:   # ncu-measured DRAM bytes per launch of that kernel (static capture)
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(names[k])
         achieved = alg_bytes[names[k]] / (per_step_ms[k] * 1e-3) * 1e-9
         step_bytes = 8 * (2 * n * N + N + 2 * 2 * nn * ni)  # B = 32 n^2 N + 16 n N
         # ---- CPU baseline (bounded sample: a few full-size steps, ~1 s each) ---------------------------
@@ -403,7 +408,7 @@ def main():
                     "d2h_bytes_per_step": 8 * (N + N * n) + 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": names[k], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes[names[k]], "kernel_ms": per_step_ms[k],
                          "whole_step": {"algorithmic_bytes": step_bytes,
                                         "achieved_gbs": step_bytes / (total_ms_max / args.steps * 1e-3) * 1e-9},

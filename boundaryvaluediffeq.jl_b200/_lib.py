@@ -100,7 +100,7 @@ _lib = None
 
 def build(verbose: bool = False) -> str:
     """Compile libmirkb200.so in-tree with csrc/Makefile (nvcc, sm_100a only)."""
-    r = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:])
         print(r.stderr[-4000:])
