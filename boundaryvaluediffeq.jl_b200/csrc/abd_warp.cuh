@@ -45,7 +45,46 @@ __device__ __forceinline__ double fast_rcp(double x) {
 template <int n> struct WarpABD {
     static constexpr int rows = 2 * n, cols = 3 * n + 1;
     static constexpr int pb_stride = (cols + 2) & ~1;  // doubles per broadcast line, even
-    static constexpr int smem_doubles_per_warp = 2 * pb_stride;
+    // per-warp shared memory: the double-buffered pivot line + a staging buffer the NEXT relation of the
+    // group is prefetched into with cp.async while the current merge runs (which lanes will be free to
+    // receive it is only known after the merge, so it cannot be prefetched into registers)
+    static constexpr int stage_stride = 2 * n + 2;  // doubles per staged row [L row | R row | r | pad], 16-byte multiple
+    static constexpr int stage_doubles = n * stage_stride;
+    static constexpr int smem_doubles_per_warp = 2 * pb_stride + stage_doubles;
+
+    __device__ __forceinline__ static void stage_issue(double* st, const double* Lk, const double* Rk, const double* rk,
+                                                       int lane) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(st);
+        constexpr int chunks_per_row = n / 2;  // 16-byte chunks in one n-double row
+        for (int e = lane; e < 2 * n * chunks_per_row; e += 32) {
+            const int which = e / (n * chunks_per_row), rem = e % (n * chunks_per_row);
+            const int q = rem / chunks_per_row, ch = rem % chunks_per_row;
+            const double* src = (which ? Rk : Lk) + q * n + 2 * ch;
+            const unsigned dst = sa + 8u * (q * stage_stride + which * n + 2 * ch);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        }
+        if (lane < n) {
+            const unsigned dst = sa + 8u * (lane * stage_stride + 2 * n);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(rk + lane));
+        }
+        asm volatile("cp.async.commit_group;");
+    }
+    __device__ __forceinline__ static void stage_wait() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    // staged relation row q into an incoming row  [E | A | B | rhs] = [L | 0 | R | r]
+    __device__ __forceinline__ static void load_incoming_staged(double (&w)[cols], const double* st, int q) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(st) + 8u * (q * stage_stride);
+#pragma unroll
+        for (int k = 0; k < n; k += 2) {
+            const double2 a = lds_v2f64(sa + 8u * k), b = lds_v2f64(sa + 8u * (n + k));
+            w[k] = a.x; w[k + 1] = a.y;
+            w[n + k] = 0.0; w[n + k + 1] = 0.0;
+            w[2 * n + k] = b.x; w[2 * n + k + 1] = b.y;
+        }
+        w[3 * n] = lds_f64(sa + 8u * (2 * n));
+    }
 
     // Gauss-Jordan on the n E-columns over all `rows` lanes.  On return lanes with myq >= 0 own unit
     // column myq up to the scale myinv (= 1 / pivot); lanes with myq < 0 are the survivors.
@@ -180,13 +219,15 @@ __device__ __forceinline__ bool warp_reduce_group(int g, const double* inL, cons
     for (int c = 0; c < WA::cols; c++) w[c] = 0.0;
     unsigned carried = (1u << n) - 1u;
     const unsigned rowmask = (WA::rows == 32) ? kFullMask : ((1u << WA::rows) - 1u);
+    double* stage = pbuf + 2 * WA::pb_stride;
+    if (k0 + 1 < k1) WA::stage_issue(stage, inL + (k0 + 1) * nn, inR + (k0 + 1) * nn, inr + (size_t)(k0 + 1) * n, lane);
     if (lane < n) WA::load_carried(w, inL + k0 * nn + (size_t)lane * n, inR + k0 * nn + (size_t)lane * n, inr[(size_t)k0 * n + lane]);
     for (int j = k0 + 1; j < k1; j++) {
         const unsigned freem = rowmask & ~carried;
-        if ((freem >> lane) & 1u) {
-            const int q = __popc(freem & ((1u << lane) - 1u));
-            WA::load_incoming(w, inL + j * nn + (size_t)q * n, inR + j * nn + (size_t)q * n, inr[(size_t)j * n + q]);
-        }
+        WA::stage_wait();
+        if ((freem >> lane) & 1u) WA::load_incoming_staged(w, stage, __popc(freem & ((1u << lane) - 1u)));
+        __syncwarp();  // every lane has its row before the buffer is refilled
+        if (j + 1 < k1) WA::stage_issue(stage, inL + (j + 1) * nn, inR + (j + 1) * nn, inr + (size_t)(j + 1) * n, lane);
         int myq;
         double myinv;
         if (!WA::eliminate(w, lane, pbuf, myq, myinv)) return false;
@@ -364,8 +405,16 @@ inline cudaError_t launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, i
     MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<1, kTailWarps * 32, smem_bytes, st>>>(a)));
     return cudaGetLastError();
 }
+// opt in to as much dynamic shared memory as fits beside the kernel's static allocation
 inline void set_warp_tail_smem(int n, int bytes) {
-    MIRK_WARP_DISPATCH(n, (cudaFuncSetAttribute(k_tail_warp<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)));
+    MIRK_WARP_DISPATCH(n, {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_tail_warp<NN>) == cudaSuccess) {
+            const int room = 227 * 1024 - (int)fa.sharedSizeBytes - 1024;
+            cudaFuncSetAttribute(k_tail_warp<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes < room ? bytes : room);
+        }
+        cudaGetLastError();
+    });
 }
 inline void launch_warp_backsub(cudaStream_t st, int n, int G, const int* nodes, const int* gs, const double* TL,
                                 const double* TR, const double* rt, double* delta) {

@@ -237,13 +237,20 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     const int n = S->n;
     std::sort(pinned.begin(), pinned.end());
     pinned.erase(std::unique(pinned.begin(), pinned.end()), pinned.end());
-    // desc.chunk packs the reduction shape: bits 0-7 relations per group at level 0 (default 8),
-    // bits 8-15 at the upper levels (default: same), bits 16-31 the relation count from which the
-    // remaining levels run radix-2 inside the single-block tail kernel (default 64; 1 disables it)
+    // desc.chunk packs the reduction shape: bits 0-7 relations per group at level 0, bits 8-15 at the upper
+    // levels, bits 16-31 the relation count from which the remaining levels run radix-2 inside the single-
+    // block tail kernel (1 disables it).  Zero fields take the measured defaults (profiles/r01_notes.md): on
+    // the warp path level 0 is sized to ONE wave of resident warps (12 per SM at 168 registers), clamped to
+    // [8, 16]; upper levels collapse 4 relations per warp (short dependent chains); the tail takes over at 16.
     const int chunk = S->desc.chunk;
-    const int c0 = (chunk & 0xff) >= 2 ? (chunk & 0xff) : 8;
-    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : c0;
-    const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 64;
+    const bool warp_path0 = warp_reduce_supported(n);
+    int c0 = chunk & 0xff;
+    if (c0 < 2) {
+        c0 = 8;
+        if (warp_path0) c0 = std::min(16, std::max(8, (N - 1 + S->sm_count * 12 - 1) / (S->sm_count * 12)));
+    }
+    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : (warp_path0 ? 4 : c0);
+    const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 16;
     const bool warp_path = warp_reduce_supported(n);
     if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
 
@@ -442,6 +449,7 @@ static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int 
     return launch_check("abd_reduce");
 }
 
+static const int kTailDynLimit = 160 * 1024;  // dynamic shared memory the tail kernel may use beside its static buffers
 static int final_smem_bytes(int D, bool m_in_smem) {
     size_t b = sizeof(double) * ((size_t)D + D + 1) + sizeof(int) * (2 * (size_t)D + 4);
     if (m_in_smem) b += sizeof(double) * (size_t)D * (D + 1);
@@ -479,7 +487,7 @@ static int part_exchange_and_close(mirk_solver_s* S) {
 static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
     Plan& P = *C.P;
     const int n = S->n, D = P.Q * n;
-    const bool m_in_smem = final_smem_bytes(D, true) <= kSmemLimit;
+    const bool m_in_smem = final_smem_bytes(D, true) <= (warp_reduce_supported(n) ? kTailDynLimit : kSmemLimit);
     if (C.exchange && P.Q != 2) return fail(MIRK_ERR_STATE, "a mesh segment must reduce to one relation");
     if (warp_reduce_supported(n)) {
         TailArgs a;
@@ -856,7 +864,7 @@ int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     cudaFuncSetAttribute(k_reduce_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(k_final_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(k_mesh_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (warp_reduce_supported(ops->n)) set_warp_tail_smem(ops->n, kSmemLimit);
+    if (warp_reduce_supported(ops->n)) set_warp_tail_smem(ops->n, kTailDynLimit);
     *out = S;
     return MIRK_OK;
 }
