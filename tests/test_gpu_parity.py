@@ -338,3 +338,52 @@ def test_user_supplied_device_functor_plugin(M, oracle, tmp_path):
         assert _rel(sol.u, ref.u) < 1e-10
     # known answer: u(1/2) = 2 ln(cosh(theta/4)... for lam = 1: max u = 0.14050 (Bratu lower branch)
     assert abs(sol(0.5)[0] - 0.1405392) < 1e-5
+
+
+@pytest.mark.parametrize("kw", [{"max_num_subintervals": 40}, {"max_num_subintervals": 60},
+                                {"nlsolve_kwargs": {"maxiters": 1}}, {"nlsolve_kwargs": {"maxiters": 3}}])
+def test_failure_paths_match_oracle(M, oracle, kw):
+    """Edge cases of the outer loop (mirk.jl:374-385, adaptivity.jl:55-75): the mesh cap stops refinement
+    (Failure with the last mesh), and a Newton solve cut short by maxiters triggers the halve-and-zero
+    cascade until 2 Nig exceeds max_num_subintervals — same history, same return code, same best iterate."""
+    okw = {}
+    alg_kw = {}
+    if "max_num_subintervals" in kw:
+        okw["max_num_subintervals"] = kw["max_num_subintervals"]
+        alg_kw["max_num_subintervals"] = kw["max_num_subintervals"]
+    skw = {}
+    if "nlsolve_kwargs" in kw:
+        okw["maxiters"] = kw["nlsolve_kwargs"]["maxiters"]
+        skw["nlsolve_kwargs"] = kw["nlsolve_kwargs"]
+    ref = oracle.solve_dt(oracle.builtin("pendulum"), 4, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, **okw)
+    sol = M.solve(M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[9.81]), M.MIRK4(**alg_kw), dt=0.05, **skw)
+    assert sol.retcode == ref.retcode
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+    assert len(sol.t) == ref.N and _rel(sol.u, ref.u) < 1e-9
+    assert sol.original["resid_norm"] == pytest.approx(ref.resid_norm, rel=1e-6, abs=1e-15)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_two_node_mesh(M, oracle, adaptive):
+    """Smallest possible mesh (one interval): the reduction has nothing to eliminate, the closing solve does
+    everything; adaptive refinement then grows the mesh 2 -> 3 -> 9 -> 31 exactly like the oracle."""
+    p, mesh, y = [1.0, 5.0, 0.0], np.array([0.0, 5.0]), np.zeros((2, 2))
+    ref = oracle.solve(oracle.builtin("linear2_tp"), 4, p, mesh, y, adaptive=int(adaptive))
+    sol = M.solve(M.BVProblem("linear2_tp", y, (0.0, 5.0), p=p, mesh=mesh), M.MIRK4(), adaptive=adaptive)
+    assert sol.retcode == ref.retcode == 0
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+    assert _rel(sol.u, ref.u) < 1e-10
+
+
+def test_argument_errors_are_status_codes_not_crashes(M):
+    prob = M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[9.81])
+    with pytest.raises(M.MirkError):  # non-increasing mesh
+        M.solve(M.BVProblem("pendulum", np.zeros((3, 2)), PENDULUM_T, p=[9.81], mesh=[0.0, 1.0, 0.5]), M.MIRK4())
+    with pytest.raises(M.MirkError):  # too few parameters
+        M.solve(M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[]), M.MIRK4(), dt=0.05)
+    with pytest.raises(ValueError):   # wrong state dimension
+        M.solve(M.BVProblem("pendulum", [1.0, 2.0, 3.0], PENDULUM_T, p=[9.81]), M.MIRK4(), dt=0.05)
+    cache = M.init(prob, M.MIRK4(), dt=0.05)
+    out = cache.solution()
+    assert out[1].shape == (33, 2) and np.allclose(out[1], np.pi / 2)   # the guess, untouched by init
+    cache.close()
