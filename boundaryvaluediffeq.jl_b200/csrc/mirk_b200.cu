@@ -970,7 +970,7 @@ int mirk_newton_step(mirk_handle S, double* resid_norm) {
     if (!S->resid_valid || !S->jac_valid) CKS(eval_resjac(S));
     CKS(linear_solve(S));
     CKS(apply_update(S));
-    CKS(eval_resjac(S));
+    CKS(eval_residual(S));  // |F| at the new iterate; its Jacobian is built only if another step follows
     CKS(read_words(S));
     if (resid_norm) *resid_norm = bits_to_double(S->h_words[0]);
     return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;

@@ -118,3 +118,26 @@ def test_full_size_sweep_properties(M):
     assert np.array_equal(r2["n_mesh"], r["n_mesh"][perm]) and np.array_equal(r2["y_first"], r["y_first"][perm])
     h.close()
     print(f"262144 pendulum BVPs in {ms:.1f} ms")
+
+
+def test_one_shot_c_abi_entry_point(M, oracle):
+    """mirk_ensemble_solve (create + set_inputs + run + get_results + destroy in one call), bound directly."""
+    import ctypes as C
+    from boundaryvaluediffeq_jl_b200 import _lib as B, configs
+    nt = 64
+    params = np.ascontiguousarray(configs.c3_ensemble_params(nt))
+    u0 = np.array([math.pi / 2, math.pi / 2])
+    desc = B.EnsembleDesc(M.BVPDeviceFunction("pendulum").problem_id, 4, 1e-6, 1, 0.1, 3000, 1000, 0, 0, 0,
+                          0.0, math.pi / 2, 0.05)
+    ret, nm, its = (np.zeros(nt, dtype=np.int32) for _ in range(3))
+    yf = np.zeros((nt, 2))
+    d = lambda a: a.ctypes.data_as(B.dp)   # noqa: E731
+    i = lambda a: a.ctypes.data_as(B.ip)   # noqa: E731
+    B.check(B.lib().mirk_ensemble_solve(C.byref(desc), nt, d(params), d(u0), 0, i(ret), i(nm), i(its), d(yf)))
+    r_ret, r_nm, r_y0, r_its = oracle.ensemble_solve(oracle.builtin("pendulum"), 4, params, u0, (0.0, math.pi / 2), 32, nthreads=4)
+    assert np.array_equal(ret, r_ret) and np.array_equal(nm, r_nm) and np.array_equal(its, r_its)
+    assert np.max(np.abs(yf - r_y0)) < 1e-10 * np.max(np.abs(r_y0))
+    # argument errors come back as status codes
+    bad = B.EnsembleDesc(desc.problem_id, 4, 1e-6, 1, 0.1, 3000, 1000, 0, 0, 0, 0.0, 1.0, 0.0)
+    with pytest.raises(ValueError, match="dt must be positive"):
+        B.check(B.lib().mirk_ensemble_solve(C.byref(bad), nt, d(params), d(u0), 0, i(ret), i(nm), i(its), d(yf)))

@@ -387,3 +387,31 @@ def test_argument_errors_are_status_codes_not_crashes(M):
     out = cache.solution()
     assert out[1].shape == (33, 2) and np.allclose(out[1], np.pi / 2)   # the guess, untouched by init
     cache.close()
+
+
+def test_handles_are_reentrant_across_host_threads(M, oracle):
+    """The reference allows independent solves on concurrent Julia threads
+    (lib/BoundaryValueDiffEqMIRK/src/BoundaryValueDiffEqMIRK.jl:106-109); every C-ABI handle owns its stream and
+    buffers, so solves from several host threads must not disturb each other."""
+    import threading
+    cases = [("pendulum", 4, [9.81], PENDULUM_U0, PENDULUM_T, 0.05), ("pendulum", 6, [9.0], PENDULUM_U0, PENDULUM_T, 0.05),
+             ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05),
+             ("swirling", 4, [0.01], [0.0] * 6, (0.0, 1.0), 0.01)]
+    out = [None] * (4 * len(cases))
+
+    def work(slot, name, order, p, u0, tspan, dt):
+        kw = {"abstol": 1e-4} if name == "swirling" else {}
+        out[slot] = M.solve(M.BVProblem(name, u0, tspan, p=p), M.MIRK4() if order == 4 else M.MIRK6(), dt=dt, **kw)
+
+    threads = [threading.Thread(target=work, args=(k, *cases[k % len(cases)])) for k in range(len(out))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k, sol in enumerate(out):
+        name, order, p, u0, tspan, dt = cases[k % len(cases)]
+        kw = {"abstol": 1e-4} if name == "swirling" else {}
+        ref = oracle.solve_dt(oracle.builtin(name), order, p, u0, tspan, dt, **kw)
+        assert sol is not None and sol.retcode == ref.retcode == 0
+        assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+        assert _rel(sol.u, ref.u) < 1e-10
