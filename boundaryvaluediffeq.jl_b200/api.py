@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib as B
 
-__all__ = ["BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK4", "MIRK6", "DefectControl",
+__all__ = ["BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "DefectControl",
            "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b",
            "EnsembleProblem", "EnsembleSolution", "EnsembleB200", "compile_device_function",
            "successful_retcode"]
@@ -176,8 +176,23 @@ class _AbstractMIRK:
 
 
 @dataclass(frozen=True)
+class MIRK2(_AbstractMIRK):
+    order = 2
+
+
+@dataclass(frozen=True)
+class MIRK3(_AbstractMIRK):
+    order = 3
+
+
+@dataclass(frozen=True)
 class MIRK4(_AbstractMIRK):
     order = 4
+
+
+@dataclass(frozen=True)
+class MIRK5(_AbstractMIRK):
+    order = 5
 
 
 @dataclass(frozen=True)
@@ -244,7 +259,7 @@ class MIRKCache:
         self.info = prob.f.info
         self.n = self.info.n
         self.order = alg.order
-        self.s, self.s_star = (3, 4) if alg.order == 4 else (5, 9)
+        self.s, self.s_star = {2: (1, 3), 3: (2, 3), 4: (3, 4), 5: (4, 6), 6: (5, 9)}[alg.order]
         p = prob.p
         self._p = p
         desc = B.Desc(prob.f.problem_id, alg.order, float(self.nlsolve_kwargs["abstol"]), int(bool(adaptive)),

@@ -62,7 +62,7 @@ static const int kPluginBase = 1000;
 
 static const ProblemOps* find_ops(int id, int order) {
     using namespace problems;
-    if (id >= 0 && id <= kLayer) return ops_small(id, order);
+    if (id >= 0 && id <= kLayer) return (order == 4 || order == 6) ? ops_small(id, order) : ops_small_235(id, order);
     if (id == kChain8) return ops_chain8(order);
     if (id == kChain16) return ops_chain16(order);
     if (id == kBratu64) return ops_bratu64(order);
@@ -629,8 +629,13 @@ static void launch_interp(mirk_solver_s* S, int N, const double* mesh, const dou
 }
 static int do_interp(mirk_solver_s* S, int N, const double* mesh, const double* y, int nt, const double* ts, int deriv,
                      int add_base, double* out, int* iold) {
-    if (S->desc.order == 4) launch_interp<4>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold);
-    else launch_interp<6>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold);
+    switch (S->desc.order) {
+    case 2: launch_interp<2>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    case 3: launch_interp<3>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    case 4: launch_interp<4>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    case 5: launch_interp<5>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    default: launch_interp<6>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    }
     S->launches++;
     return launch_check("interp");
 }
@@ -816,9 +821,9 @@ int mirk_destroy(mirk_handle S) {
 int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     if (!desc || !out) return fail(MIRK_ERR_ARG, "NULL argument");
     *out = nullptr;
-    if (desc->order != 4 && desc->order != 6) return fail(MIRK_ERR_UNSUPPORTED, "order must be 4 (MIRK4) or 6 (MIRK6)");
+    if (desc->order < 2 || desc->order > 6) return fail(MIRK_ERR_UNSUPPORTED, "order must be 2..6 (MIRK2 .. MIRK6)");
     const ProblemOps* ops = find_ops(desc->problem_id, desc->order);
-    if (!ops) return fail(MIRK_ERR_UNSUPPORTED, "unknown problem id");
+    if (!ops) return fail(MIRK_ERR_UNSUPPORTED, "unknown problem id, or this order is not instantiated for it");
     if (desc->n_params < ops->np) return fail(MIRK_ERR_ARG, "too few parameters for this problem");
     if (ops->np > 0 && !desc->params) return fail(MIRK_ERR_ARG, "params is NULL");
     if (!(desc->abstol > 0)) return fail(MIRK_ERR_ARG, "abstol must be positive");

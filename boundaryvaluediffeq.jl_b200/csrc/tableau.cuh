@@ -1,10 +1,13 @@
-// tableau.cuh — MIRK4 / MIRK6 coefficient tables and continuous-extension weights as
+// tableau.cuh — MIRK2 / MIRK3 / MIRK4 / MIRK5 / MIRK6 coefficient tables and continuous-extension weights as
 // compile-time constants, so every stage loop in the kernels unrolls to straight-line FP64.
 //
 // Restates (not copied; the reference stores them as runtime Julia arrays built from rationals):
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:13-34   (MIRK2: s=1, s*=3, tau*=0.25)
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:36-60   (MIRK3: s=2, s*=3, tau*=0.25)
 //   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:62-87   (MIRK4: s=3, s*=4, tau*=0.226)
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:89-118  (MIRK5: s=4, s*=6, tau*=0.3)
 //   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:120-152 (MIRK6: s=5, s*=9, tau*=0.7156)
-//   lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:481-499, 528-575 (weights w, w')
+//   lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:463-575 (weights w, w' per order)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -13,6 +16,83 @@ namespace mirk {
 #define MIRK_HD __host__ __device__ __forceinline__
 
 template <int ORDER> struct Tableau;
+
+// MIRK2: the implicit midpoint rule; the interpolant is built on f(y_i), f(y_{i+1})
+template <> struct Tableau<2> {
+    static constexpr int order = 2, s = 1, s_star = 3, si = 2;
+    MIRK_HD static constexpr double c(int) { return 0.5; }
+    MIRK_HD static constexpr double v(int) { return 0.5; }
+    MIRK_HD static constexpr double b(int) { return 1.0; }
+    MIRK_HD static constexpr double x(int, int) { return 0.0; }
+    MIRK_HD static constexpr double c_star(int r) { return r == 0 ? 0.0 : 1.0; }
+    MIRK_HD static constexpr double v_star(int r) { return r == 0 ? 0.0 : 1.0; }
+    MIRK_HD static constexpr double x_star(int, int) { return 0.0; }
+    MIRK_HD static constexpr double tau_star() { return 0.25; }
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        w[0] = 0.0; w[1] = t * (1.0 - t / 2.0); w[2] = t * t / 2.0;
+        wp[0] = 0.0; wp[1] = 1.0 - t; wp[2] = t;
+    }
+};
+
+template <> struct Tableau<3> {
+    static constexpr int order = 3, s = 2, s_star = 3, si = 1;
+    MIRK_HD static constexpr double c(int r) { return r == 0 ? 0.0 : 2.0 / 3.0; }
+    MIRK_HD static constexpr double v(int r) { return r == 0 ? 0.0 : 4.0 / 9.0; }
+    MIRK_HD static constexpr double b(int r) { return r == 0 ? 1.0 / 4.0 : 3.0 / 4.0; }
+    MIRK_HD static constexpr double x(int r, int j) { return (r == 1 && j == 0) ? 2.0 / 9.0 : 0.0; }
+    MIRK_HD static constexpr double c_star(int) { return 1.0; }
+    MIRK_HD static constexpr double v_star(int) { return 1.0; }
+    MIRK_HD static constexpr double x_star(int, int) { return 0.0; }
+    MIRK_HD static constexpr double tau_star() { return 0.25; }
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        w[0] = t / 4.0 * (2.0 * t * t - 5.0 * t + 4.0);
+        w[1] = -3.0 / 4.0 * t * t * (2.0 * t - 3.0);
+        w[2] = t * t * (t - 1.0);
+        wp[0] = 3.0 / 2.0 * (t - 2.0 / 3.0) * (t - 1.0);
+        wp[1] = -9.0 / 2.0 * t * (t - 1.0);
+        wp[2] = 3.0 * t * (t - 2.0 / 3.0);
+    }
+};
+
+template <> struct Tableau<5> {
+    static constexpr int order = 5, s = 4, s_star = 6, si = 2;
+    MIRK_HD static constexpr double c(int r) { return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 3.0 / 4.0 : 3.0 / 10.0; }
+    MIRK_HD static constexpr double v(int r) {
+        return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 27.0 / 32.0 : 837.0 / 1250.0;
+    }
+    MIRK_HD static constexpr double b(int r) {
+        return r == 0 ? 5.0 / 54.0 : r == 1 ? 1.0 / 14.0 : r == 2 ? 32.0 / 81.0 : 250.0 / 567.0;
+    }
+    MIRK_HD static constexpr double x(int r, int j) {
+        return r == 2 ? (j == 0 ? 3.0 / 64.0 : j == 1 ? -9.0 / 64.0 : 0.0)
+             : r == 3 ? (j == 0 ? 21.0 / 1000.0 : j == 1 ? 63.0 / 5000.0 : j == 2 ? -252.0 / 625.0 : 0.0)
+                      : 0.0;
+    }
+    MIRK_HD static constexpr double c_star(int r) { return r == 0 ? 4.0 / 5.0 : 13.0 / 23.0; }
+    MIRK_HD static constexpr double v_star(int r) { return c_star(r); }
+    MIRK_HD static constexpr double x_star(int r, int j) {
+        return r == 0 ? (j == 0 ? 14.0 / 1125.0 : j == 1 ? -74.0 / 875.0 : j == 2 ? -128.0 / 3375.0
+                         : j == 3 ? 104.0 / 945.0 : 0.0)
+                      : (j == 0 ? 1.0 / 2.0 : j == 1 ? 4508233.0 / 1958887.0 : j == 2 ? 48720832.0 / 2518569.0
+                         : j == 3 ? -27646420.0 / 17629983.0 : j == 4 ? -11517095.0 / 559682.0 : 0.0);
+    }
+    MIRK_HD static constexpr double tau_star() { return 0.3; }
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2;
+        w[0] = t * (22464.0 - 83910.0 * t + 143041.0 * t2 - 113808.0 * t3 + 33256.0 * t4) / 22464.0;
+        w[1] = t2 * (-2418.0 + 12303.0 * t - 19512.0 * t2 + 10904.0 * t3) / 3360.0;
+        w[2] = -8.0 / 81.0 * t2 * (-78.0 + 209.0 * t - 204.0 * t2 + 8.0 * t3);
+        w[3] = -25.0 / 1134.0 * t2 * (-390.0 + 1045.0 * t - 1020.0 * t2 + 328.0 * t3);
+        w[4] = -25.0 / 5184.0 * t2 * (390.0 + 255.0 * t - 1680.0 * t2 + 2072.0 * t3);
+        w[5] = 279841.0 / 168480.0 * t2 * (-6.0 + 21.0 * t - 24.0 * t2 + 8.0 * t3);
+        wp[0] = 1.0 - 13985.0 / 1872.0 * t + 143041.0 / 7488.0 * t2 - 2371.0 / 117.0 * t3 + 20785.0 / 2808.0 * t4;
+        wp[1] = -403.0 / 280.0 * t + 12303.0 / 1120.0 * t2 - 813.0 / 35.0 * t3 + 1363.0 / 84.0 * t4;
+        wp[2] = 416.0 / 27.0 * t - 1672.0 / 27.0 * t2 + 2176.0 / 27.0 * t3 - 320.0 / 81.0 * t4;
+        wp[3] = 3250.0 / 189.0 * t - 26125.0 / 378.0 * t2 + 17000.0 / 189.0 * t3 - 20500.0 / 567.0 * t4;
+        wp[4] = -1625.0 / 432.0 * t - 2125.0 / 576.0 * t2 + 875.0 / 27.0 * t3 - 32375.0 / 648.0 * t4;
+        wp[5] = -279841.0 / 14040.0 * t + 1958887.0 / 18720.0 * t2 - 279841.0 / 1755.0 * t3 + 279841.0 / 4212.0 * t4;
+    }
+};
 
 template <> struct Tableau<4> {
     static constexpr int order = 4, s = 3, s_star = 4, si = 1;

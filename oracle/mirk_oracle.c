@@ -34,10 +34,50 @@ void orc_default_options(orc_options *o) {
     o->max_outer = 60;
 }
 
-/* MIRK/mirk_tableaus.jl:62-87 (MIRK4) and :120-152 (MIRK6).  Only 1:s of c,v,b is used. */
+/* MIRK/mirk_tableaus.jl:13-34 (MIRK2), :36-60 (MIRK3), :62-87 (MIRK4), :89-118 (MIRK5), :120-152 (MIRK6).
+ * Only 1:s of c,v,b is used; x_star[r][j] is the reference's x_star[(j-1)(s*-s) + r] (interpolation.jl:308-309). */
 int orc_tableau_get(int order, orc_tableau *T) {
     memset(T, 0, sizeof(*T));
     T->order = order;
+    if (order == 2) { /* implicit midpoint rule; interpolant on f(y_i), f(y_{i+1}) */
+        T->s = 1;
+        T->s_star = 3;
+        T->c[0] = 0.5; T->v[0] = 0.5; T->b[0] = 1.0;
+        T->c_star[0] = 0.0; T->v_star[0] = 0.0;
+        T->c_star[1] = 1.0; T->v_star[1] = 1.0;
+        T->tau_star = 0.25;
+        return 0;
+    }
+    if (order == 3) {
+        T->s = 2;
+        T->s_star = 3;
+        T->c[0] = 0.0; T->c[1] = 2.0 / 3.0;
+        T->v[0] = 0.0; T->v[1] = 4.0 / 9.0;
+        T->b[0] = 1.0 / 4.0; T->b[1] = 3.0 / 4.0;
+        T->x[1][0] = 2.0 / 9.0;
+        T->c_star[0] = 1.0; T->v_star[0] = 1.0;
+        T->tau_star = 0.25;
+        return 0;
+    }
+    if (order == 5) {
+        T->s = 4;
+        T->s_star = 6;
+        const double c[4] = {0.0, 1.0, 3.0 / 4.0, 3.0 / 10.0};
+        const double v[4] = {0.0, 1.0, 27.0 / 32.0, 837.0 / 1250.0};
+        const double b[4] = {5.0 / 54.0, 1.0 / 14.0, 32.0 / 81.0, 250.0 / 567.0};
+        for (int r = 0; r < 4; r++) { T->c[r] = c[r]; T->v[r] = v[r]; T->b[r] = b[r]; }
+        T->x[2][0] = 3.0 / 64.0;    T->x[2][1] = -9.0 / 64.0;
+        T->x[3][0] = 21.0 / 1000.0; T->x[3][1] = 63.0 / 5000.0; T->x[3][2] = -252.0 / 625.0;
+        T->c_star[0] = 4.0 / 5.0;   T->v_star[0] = 4.0 / 5.0;
+        T->c_star[1] = 13.0 / 23.0; T->v_star[1] = 13.0 / 23.0;
+        T->x_star[0][0] = 14.0 / 1125.0; T->x_star[0][1] = -74.0 / 875.0;
+        T->x_star[0][2] = -128.0 / 3375.0; T->x_star[0][3] = 104.0 / 945.0;
+        T->x_star[1][0] = 1.0 / 2.0; T->x_star[1][1] = 4508233.0 / 1958887.0;
+        T->x_star[1][2] = 48720832.0 / 2518569.0; T->x_star[1][3] = -27646420.0 / 17629983.0;
+        T->x_star[1][4] = -11517095.0 / 559682.0;
+        T->tau_star = 0.3;
+        return 0;
+    }
     if (order == 4) {
         T->s = 3;
         T->s_star = 4;
@@ -81,9 +121,39 @@ int orc_tableau_get(int order, orc_tableau *T) {
     return -1;
 }
 
-/* MIRK/interpolation.jl:481-499 (order 4) and :528-575 (order 6): weights w(tau), w'(tau). */
+/* MIRK/interpolation.jl:463-527 (orders 2, 3, 4, 5) and :528-575 (order 6): weights w(tau), w'(tau). */
 void orc_interp_weights(int order, double tau, double *w, double *wp) {
     const double t = tau;
+    if (order == 2) {
+        w[0] = 0.0; w[1] = t * (1.0 - t / 2.0); w[2] = t * t / 2.0;
+        wp[0] = 0.0; wp[1] = 1.0 - t; wp[2] = t;
+        return;
+    }
+    if (order == 3) {
+        w[0] = t / 4.0 * (2.0 * t * t - 5.0 * t + 4.0);
+        w[1] = -3.0 / 4.0 * t * t * (2.0 * t - 3.0);
+        w[2] = t * t * (t - 1.0);
+        wp[0] = 3.0 / 2.0 * (t - 2.0 / 3.0) * (t - 1.0);
+        wp[1] = -9.0 / 2.0 * t * (t - 1.0);
+        wp[2] = 3.0 * t * (t - 2.0 / 3.0);
+        return;
+    }
+    if (order == 5) {
+        const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2;
+        w[0] = t * (22464.0 - 83910.0 * t + 143041.0 * t2 - 113808.0 * t3 + 33256.0 * t4) / 22464.0;
+        w[1] = t2 * (-2418.0 + 12303.0 * t - 19512.0 * t2 + 10904.0 * t3) / 3360.0;
+        w[2] = -8.0 / 81.0 * t2 * (-78.0 + 209.0 * t - 204.0 * t2 + 8.0 * t3);
+        w[3] = -25.0 / 1134.0 * t2 * (-390.0 + 1045.0 * t - 1020.0 * t2 + 328.0 * t3);
+        w[4] = -25.0 / 5184.0 * t2 * (390.0 + 255.0 * t - 1680.0 * t2 + 2072.0 * t3);
+        w[5] = 279841.0 / 168480.0 * t2 * (-6.0 + 21.0 * t - 24.0 * t2 + 8.0 * t3);
+        wp[0] = 1.0 - 13985.0 / 1872.0 * t + 143041.0 / 7488.0 * t2 - 2371.0 / 117.0 * t3 + 20785.0 / 2808.0 * t4;
+        wp[1] = -403.0 / 280.0 * t + 12303.0 / 1120.0 * t2 - 813.0 / 35.0 * t3 + 1363.0 / 84.0 * t4;
+        wp[2] = 416.0 / 27.0 * t - 1672.0 / 27.0 * t2 + 2176.0 / 27.0 * t3 - 320.0 / 81.0 * t4;
+        wp[3] = 3250.0 / 189.0 * t - 26125.0 / 378.0 * t2 + 17000.0 / 189.0 * t3 - 20500.0 / 567.0 * t4;
+        wp[4] = -1625.0 / 432.0 * t - 2125.0 / 576.0 * t2 + 875.0 / 27.0 * t3 - 32375.0 / 648.0 * t4;
+        wp[5] = -279841.0 / 14040.0 * t + 1958887.0 / 18720.0 * t2 - 279841.0 / 1755.0 * t3 + 279841.0 / 4212.0 * t4;
+        return;
+    }
     if (order == 4) {
         const double t2 = t * t, tm1 = t - 1.0, t4m3 = t * 4.0 - 3.0, t2m1 = t * 2.0 - 1.0;
         w[0] = -t * (2.0 * t - 3.0) * (2.0 * t2 - 3.0 * t + 2.0) / 6.0;

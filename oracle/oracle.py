@@ -177,7 +177,7 @@ def tableau(order) -> Tableau:
 
 
 def interp_weights(order, tau):
-    ss = 4 if order == 4 else 9
+    ss = {2: 3, 3: 3, 4: 4, 5: 6, 6: 9}[order]
     w, wp = np.zeros(9), np.zeros(9)
     lib().orc_interp_weights(order, float(tau), _d(w), _d(wp))
     return w[:ss], wp[:ss]

@@ -17,6 +17,10 @@ def M():
     return m
 
 
+def _alg(M, order):
+    return {2: M.MIRK2, 3: M.MIRK3, 4: M.MIRK4, 5: M.MIRK5, 6: M.MIRK6}[order]()
+
+
 def _rel(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
@@ -40,8 +44,7 @@ def _perturbed_case(M, O, name, order, p, tspan, nint, seed, u_base=None, mesh_j
     y = base[None, :] + 0.3 * rng.standard_normal((nint + 1, n))
     ws = O.Workspace(P, order, p, mesh, y)
     prob = M.BVProblem(name, y, tspan, p=p, mesh=mesh)
-    alg = M.MIRK4() if order == 4 else M.MIRK6()
-    cache = M.init(prob, alg, adaptive=False)
+    cache = M.init(prob, _alg(M, order), adaptive=False)
     return ws, cache
 
 
@@ -52,6 +55,10 @@ CASES = [
     ("lotka", 6, [7.5, 4.0, 8.5, 5.0], (0.0, 10.0), 50), ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 30),
     ("layer", 6, [0.1], (-1.0, 1.0), 64), ("chain8", 6, None, (0.0, 0.5), 100), ("chain8", 4, None, (0.0, 0.5), 37),
     ("chain16", 6, None, (0.0, 0.5), 41), ("bratu64", 4, [1.0], (0.0, 1.0), 19),
+    # the rest of the MIRK family: MIRK2, MIRK3, MIRK5
+    ("pendulum", 2, [9.81], PENDULUM_T, 32), ("pendulum", 3, [9.81], PENDULUM_T, 32), ("pendulum", 5, [9.81], PENDULUM_T, 32),
+    ("swirling", 5, [0.01], (0.0, 1.0), 31), ("torus", 3, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 20),
+    ("linear2_tp", 2, [1.0, 5.0, 0.0], (0.0, 5.0), 17),
 ]
 
 
@@ -72,8 +79,7 @@ def test_residual_jacobian_and_update_match_oracle(M, oracle, name, order, p, ts
     if scale != 1.0:
         ws.y *= scale
         cache.close()
-        cache = M.init(M.BVProblem(name, ws.y, tspan, p=p, mesh=ws.mesh), M.MIRK4() if order == 4 else M.MIRK6(),
-                       adaptive=False)
+        cache = M.init(M.BVProblem(name, ws.y, tspan, p=p, mesh=ws.mesh), _alg(M, order), adaptive=False)
     # residual and stages
     r_ref = ws.loss()
     r_gpu, nrm = cache.residual()
@@ -147,6 +153,15 @@ SOLVES = [
     ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05, {}),
     ("layer", 4, [0.01], [0.0, 0.0], (-1.0, 1.0), 0.05, {"tol": 1e-8}),               # test/misc/adaptivity_tests.jl
     ("layer", 6, [0.001], [0.0, 0.0], (-1.0, 1.0), 0.05, {"tol": 1e-5}),
+    # MIRK2 / MIRK3 / MIRK5
+    ("pendulum", 5, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {}),
+    ("pendulum", 3, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {}),
+    ("pendulum", 2, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {"abstol": 1e-4}),
+    ("linear2", 5, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),
+    ("linear2", 3, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),
+    ("linear2_tp", 2, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.2, {"abstol": 1e-4}),
+    ("swirling", 5, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),
+    ("torus", 5, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05, {"tol": 1e-9}),  # 2e-10 measured
 ]
 
 
@@ -162,8 +177,7 @@ def test_full_solve_matches_oracle(M, oracle, name, order, p, u0, tspan, dt, kw)
     kw = dict(kw)
     tol = kw.pop("tol", 1e-10)
     ref = O.solve_dt(O.builtin(name), order, p, u0, tspan, dt, **kw)
-    alg = M.MIRK4() if order == 4 else M.MIRK6()
-    sol = M.solve(M.BVProblem(name, u0, tspan, p=p), alg, dt=dt, **kw)
+    sol = M.solve(M.BVProblem(name, u0, tspan, p=p), _alg(M, order), dt=dt, **kw)
     assert sol.retcode == ref.retcode
     assert sol.original["hist_n_mesh"] == ref.hist_N
     assert sol.original["hist_newton"] == ref.hist_newton
@@ -235,7 +249,7 @@ def test_convergence_order_on_gpu(M):
     def exact(t):
         return 5.0 * (np.cos(t) - np.sin(t) / np.tan(5.0))
 
-    for alg, order in ((M.MIRK4(), 4), (M.MIRK6(), 6)):
+    for alg, order in ((M.MIRK2(), 2), (M.MIRK3(), 3), (M.MIRK4(), 4), (M.MIRK5(), 5), (M.MIRK6(), 6)):
         errs = []
         for dt in (0.5, 0.25, 0.125):
             sol = M.solve(M.BVProblem("linear2", [5.0, -3.5], (0.0, 5.0), p=LIN_P), alg, dt=dt, adaptive=False,

@@ -16,7 +16,20 @@ PI = np.pi
 
 # ---------------------------------------------------------------- tableaus (mirk_tableaus.jl:62-152)
 def _exact_tableau(order):
-    if order == 4:
+    if order == 2:   # mirk_tableaus.jl:13-34
+        c = [F(1, 2)]; v = [F(1, 2)]; b = [F(1)]; x = [[0]]
+        cs = [F(0), F(1)]; vs = [F(0), F(1)]; xs = [[0, 0, 0], [0, 0, 0]]
+    elif order == 3:   # :36-60
+        c = [F(0), F(2, 3)]; v = [F(0), F(4, 9)]; b = [F(1, 4), F(3, 4)]; x = [[0, 0], [F(2, 9), 0]]
+        cs = [F(1)]; vs = [F(1)]; xs = [[0, 0, 0]]
+    elif order == 5:   # :89-118
+        c = [F(0), F(1), F(3, 4), F(3, 10)]; v = [F(0), F(1), F(27, 32), F(837, 1250)]
+        b = [F(5, 54), F(1, 14), F(32, 81), F(250, 567)]
+        x = [[0] * 4, [0] * 4, [F(3, 64), F(-9, 64), 0, 0], [F(21, 1000), F(63, 5000), F(-252, 625), 0]]
+        cs = [F(4, 5), F(13, 23)]; vs = cs
+        xs = [[F(14, 1125), F(-74, 875), F(-128, 3375), F(104, 945), 0, 0],
+              [F(1, 2), F(4508233, 1958887), F(48720832, 2518569), F(-27646420, 17629983), F(-11517095, 559682), 0]]
+    elif order == 4:
         c = [F(0), F(1), F(1, 2)]; v = [F(0), F(1), F(1, 2)]
         b = [F(1, 6), F(1, 6), F(2, 3)]
         x = [[0, 0, 0], [0, 0, 0], [F(1, 8), F(-1, 8), 0]]
@@ -35,7 +48,7 @@ def _exact_tableau(order):
     return c, v, b, x, cs, vs, xs
 
 
-@pytest.mark.parametrize("order", [4, 6])
+@pytest.mark.parametrize("order", [2, 3, 4, 5, 6])
 def test_tableau_matches_exact_rationals_and_identities(oracle, order):
     T = oracle.tableau(order)
     c, v, b, x, cs, vs, xs = _exact_tableau(order)
@@ -76,6 +89,29 @@ def test_interp_weights_endpoint_identities(oracle, order):
         wb, _ = oracle.interp_weights(order, tau + h)
         _, wp = oracle.interp_weights(order, tau)
         assert np.allclose((wb - wa) / (2 * h), wp, atol=1e-7)
+
+
+@pytest.mark.parametrize("order", [2, 3, 5])
+def test_interp_weights_low_orders(oracle, order):
+    """MIRK2/3/5 interpolants (interpolation.jl:463-527): w(0) = 0, w' is the derivative of w, the weights
+    reproduce polynomials up to the interpolant's degree (sum_r w_r(tau) c~_r^k = tau^(k+1)/(k+1) with the
+    abscissae of all s* stages), and u'(t_i) = f(y_i)."""
+    T = oracle.tableau(order)
+    w0, wp0 = oracle.interp_weights(order, 0.0)
+    assert np.allclose(w0, 0, atol=1e-15)
+    for tau in (0.25, 0.3, 0.5, 0.75):
+        h = 1e-6
+        wa, _ = oracle.interp_weights(order, tau - h)
+        wb, _ = oracle.interp_weights(order, tau + h)
+        w, wp = oracle.interp_weights(order, tau)
+        assert np.allclose((wb - wa) / (2 * h), wp, atol=1e-7)
+        call = [T.c[r] for r in range(T.s)] + [T.c_star[r] for r in range(T.s_star - T.s)]
+        for k in range(2 if order < 5 else 4):   # quadrature conditions of the continuous extension
+            assert abs(sum(w[r] * call[r] ** k for r in range(T.s_star)) - tau ** (k + 1) / (k + 1)) < 1e-12
+    # the stage evaluated at t_i carries u'(t_i): K~_1 of MIRK2 (c* = 0), K_1 otherwise
+    first = 1 if order == 2 else 0
+    e = np.zeros(T.s_star); e[first] = 1
+    assert np.allclose(wp0, e, atol=1e-14)
 
 
 def test_interval_matches_searchsortedfirst(oracle):
@@ -232,7 +268,7 @@ def _exact_lin(t):  # mirk_basic_tests.jl:54-66
     return np.array([5 * (np.cos(t) - np.sin(t) / np.tan(5)), 5 * (-np.cos(t) / np.tan(5) - np.sin(t))])
 
 
-@pytest.mark.parametrize("order", [4, 6])
+@pytest.mark.parametrize("order", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("name,p", [("linear2", [1.0, 0.0, 5.0, 5.0, 0.0, 0, 0]), ("linear2_tp", [1.0, 5.0, 0.0])])
 def test_convergence_order_on_linear_problem(oracle, order, name, p):
     """mirk_basic_tests.jl:122-139: estimated order within 0.4 of p, dts = 1/8, 1/4, 1/2."""
