@@ -5,11 +5,16 @@ namespace mirk {
 using namespace problems;
 template <class P, int ORDER> struct EnsImpl {
     static void run(cudaStream_t st, const EnsArgs& a) {
-        const long long blocks = (a.ntraj + 63) / 64;
         // n <= 2: cap registers at 96 (10 CTAs of 64 threads per SM): the kernel is memory-latency bound and
         // the extra resident warps buy 17 % (experiments/exp_ens.cu); larger n needs the registers
         constexpr int MINB = P::n <= 2 ? 10 : 1;
-        k_ensemble_solve<P, ORDER, MINB><<<(unsigned)blocks, 64, 0, st>>>(a);
+        // small shards (e.g. 262 144 trajectories strong-scaled over 8 GPUs): one warp per CTA so the CTAs
+        // spread evenly over the SMs instead of leaving some SMs with a whole CTA more than others
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int tpb = (a.ntraj + 63) / 64 < 8LL * sms ? 32 : 64;
+        const long long blocks = (a.ntraj + tpb - 1) / tpb;
+        k_ensemble_solve<P, ORDER, MINB><<<(unsigned)blocks, tpb, 0, st>>>(a);
     }
     static EnsembleOps make() {
         using LY = EnsLayout<P, ORDER>;
