@@ -50,7 +50,17 @@ template <int n> struct WarpABD {
     // receive it is only known after the merge, so it cannot be prefetched into registers)
     static constexpr int stage_stride = 2 * n + 2;  // doubles per staged row [L row | R row | r | pad], 16-byte multiple
     static constexpr int stage_doubles = n * stage_stride;
-    static constexpr int smem_doubles_per_warp = 2 * pb_stride + stage_doubles;
+    // panel elimination (MIRK_ELIM_PANEL): PB pivots per panel; the PB pivot rows of a panel are published
+    // once, as PB shared lines holding columns [SH, cols)
+    static constexpr int PB = 4;
+    static constexpr int SH = n < PB ? n : PB;
+    static constexpr int LS = (cols - SH + 1) & ~1;  // doubles per published line, even
+#if defined(MIRK_ELIM_PANEL)
+    static constexpr int line_doubles = PB * LS;
+#else
+    static constexpr int line_doubles = 2 * pb_stride;
+#endif
+    static constexpr int smem_doubles_per_warp = line_doubles + stage_doubles;
 
     __device__ __forceinline__ static void stage_issue(double* st, const double* Lk, const double* Rk, const double* rk,
                                                        int lane) {
@@ -94,6 +104,70 @@ template <int n> struct WarpABD {
         myq = -1;
         myinv = 0.0;
         bool elig = lane < rows;
+#if defined(MIRK_ELIM_PANEL)
+        // Panel form of the same Gauss-Jordan elimination (same pivots).  Inside a panel of PB columns only the
+        // panel entries are updated, from the pivot lane by warp shuffles (a short dependent chain per pivot:
+        // REDUX -> SHFL -> DFMA), while every lane accumulates the coefficients g[j] of
+        //     current row = row at panel start + sum_j g[j] * (pivot row j at panel start).
+        // The PB pivot lanes then publish their rows at once and every lane applies its PB-term combination to
+        // all later columns: one shared-memory round trip per panel instead of one per pivot.
+        const unsigned la = (unsigned)__cvta_generic_to_shared(pb);
+#pragma unroll
+        for (int q0 = 0; q0 < n; q0 += PB) {
+            const int pw = (n - q0) < PB ? (n - q0) : PB;
+            double g[PB];
+#pragma unroll
+            for (int j = 0; j < PB; j++) g[j] = 0.0;
+            int myrank = -1;
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                if (k < pw) {
+                    const int q = q0 + k;
+                    const double own = w[q];
+                    const double own_inv = fast_rcp(own);
+                    const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
+                    const unsigned mx = __reduce_max_sync(kFullMask, key);
+                    if ((mx >> 5) == 0u || mx >= 0x7ff00000u) return false;
+                    const int pr = 31 - (int)(mx & 31u);
+                    const bool isp = lane == pr;
+                    const double inv = __shfl_sync(kFullMask, own_inv, pr);
+                    const double m = isp ? 0.0 : -(own * inv);
+#pragma unroll
+                    for (int c = q + 1; c < q0 + pw; c++) w[c] = fma(m, __shfl_sync(kFullMask, w[c], pr), w[c]);
+#pragma unroll
+                    for (int j = 0; j < k; j++) g[j] = fma(m, __shfl_sync(kFullMask, g[j], pr), g[j]);
+                    g[k] = m;
+                    if (isp) { elig = false; myq = q; myinv = own_inv; myrank = k; }
+                }
+            }
+            const int c0 = q0 + pw;  // first column behind the panel (even: n and PB are even)
+            if (myrank >= 0) {
+                double* line = pb + myrank * LS;
+#pragma unroll
+                for (int c = c0; c < cols; c += 2) {
+                    const double hi = (c + 1 < cols) ? w[(c + 1 < cols) ? c + 1 : c] : 0.0;
+                    *reinterpret_cast<double2*>(line + (c - SH)) = make_double2(w[c], hi);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = c0; c < cols; c += 2) {
+                double a0 = w[c], a1 = (c + 1 < cols) ? w[(c + 1 < cols) ? c + 1 : c] : 0.0;
+#pragma unroll
+                for (int j = 0; j < PB; j++) {
+                    if (j < pw) {
+                        const double2 v = lds_v2f64(la + 8u * (unsigned)(j * LS + c - SH));
+                        a0 = fma(g[j], v.x, a0);
+                        a1 = fma(g[j], v.y, a1);
+                    }
+                }
+                w[c] = a0;
+                if (c + 1 < cols) w[(c + 1 < cols) ? c + 1 : c] = a1;
+            }
+            __syncwarp();  // the lines are rewritten by the next panel
+        }
+        return true;
+#else
 #pragma unroll
         for (int q = 0; q < n; q++) {
             const double own = w[q];
@@ -141,6 +215,7 @@ template <int n> struct WarpABD {
 #endif
         }
         return true;
+#endif  // MIRK_ELIM_PANEL
     }
 
     // relation row q of (L, R, r) into a carried row  [E | A | B | rhs] = [R | L | 0 | r]
@@ -219,7 +294,7 @@ __device__ __forceinline__ bool warp_reduce_group(int g, const double* inL, cons
     for (int c = 0; c < WA::cols; c++) w[c] = 0.0;
     unsigned carried = (1u << n) - 1u;
     const unsigned rowmask = (WA::rows == 32) ? kFullMask : ((1u << WA::rows) - 1u);
-    double* stage = pbuf + 2 * WA::pb_stride;
+    double* stage = pbuf + WA::line_doubles;
     if (k0 + 1 < k1) WA::stage_issue(stage, inL + (k0 + 1) * nn, inR + (k0 + 1) * nn, inr + (size_t)(k0 + 1) * n, lane);
     if (lane < n) WA::load_carried(w, inL + k0 * nn + (size_t)lane * n, inR + k0 * nn + (size_t)lane * n, inr[(size_t)k0 * n + lane]);
     for (int j = k0 + 1; j < k1; j++) {

@@ -15,6 +15,7 @@
 // loops over the state dimension unroll fully up to n = 32 and by 4 beyond (n = 128 would explode)
 #include "dual.cuh"
 #include "tableau.cuh"
+#include "tape.cuh"
 
 namespace mirk {
 
@@ -305,6 +306,80 @@ k_resjac(int N, const double* __restrict__ mesh, const double* __restrict__ y, c
         }
     }
     block_max_to_global(m, norm_bits);
+}
+
+// ---- K1+K2 taped: values once per interval, tangents replay the tape (tape.cuh) ------------------------
+// One warp per CTA, `ipw` <= 32 consecutive intervals per warp.
+//   pass 1  lane = interval: stages, Phi_i, |Phi|_inf in plain FP64; every sin/cos/exp result goes to the tape
+//   pass 2  lane = (interval, column d of [L_i R_i]): tangent sweep with the elementary functions read back
+//           from the tape.  For right-hand sides whose only non-linearities are elementary functions of the
+//           state (the pendulum chains) the whole value computation of this pass is dead code.
+// The optional `P::tape_calls` (elementary-function calls per f evaluation) sizes the tape; default n.
+template <class P, class = void> struct TapeCalls { static constexpr int value = P::n; };
+template <class P> struct TapeCalls<P, decltype((void)P::tape_calls)> { static constexpr int value = P::tape_calls; };
+template <class P, int ORDER> __host__ __device__ constexpr int tape_cap() {
+    const int want = Tableau<ORDER>::s * TapeCalls<P>::value;
+    return want < 1 ? 1 : (want > 92 ? 92 : want);  // 92 entries x 32 slots x 16 B stays under 48 KB static
+}
+
+template <class P, int ORDER>
+__global__ void __launch_bounds__(32)
+k_resjac_tape(int N, int ipw, const double* __restrict__ mesh, const double* __restrict__ y,
+              const double* __restrict__ p, double* __restrict__ Kd, double* __restrict__ phi_out,
+              unsigned long long* __restrict__ norm_bits, double* __restrict__ Lb, double* __restrict__ Rb) {
+    using TB = Tableau<ORDER>;
+    constexpr int n = P::n, cols = 2 * n, CAP = tape_cap<P, ORDER>();
+    using TP = Tape<CAP>;
+    const int lane = threadIdx.x;
+    const int i0 = blockIdx.x * ipw;
+    unsigned long long m = 0ull;
+    {
+        const int i = i0 + lane;
+        if (lane < ipw && i < N - 1) {
+            using V = RecVal<CAP>;
+            TP::begin(lane);
+            V yi[n], yi1[n], K[TB::s][n], phi[n];
+            const double* yp = y + (size_t)i * n;
+#pragma unroll (unroll_for(n))
+            for (int k = 0; k < n; k++) { yi[k] = V(yp[k]); yi1[k] = V(yp[n + k]); }
+            const double ti = mesh[i], h = mesh[i + 1] - ti;
+            phi_interval<P, ORDER, V>(yi, yi1, h, ti, p, K, phi);
+            double* Ko = Kd + (size_t)i * TB::s * n;
+#pragma unroll (unroll_for(n))
+            for (int r = 0; r < TB::s; r++)
+#pragma unroll (unroll_for(n))
+                for (int k = 0; k < n; k++) Ko[r * n + k] = K[r][k].v;
+            double* po = phi_out + (size_t)i * n;
+#pragma unroll (unroll_for(n))
+            for (int k = 0; k < n; k++) {
+                po[k] = phi[k].v;
+                const unsigned long long b = abs_bits(phi[k].v);
+                m = b > m ? b : m;
+            }
+        }
+    }
+    block_max_to_global(m, norm_bits);
+    __syncwarp();
+    int here = N - 1 - i0;
+    if (here > ipw) here = ipw;
+    const int items = here * cols;
+    for (int e = lane; e < items; e += 32) {
+        using D = TapeDual<CAP>;
+        const int li = e / cols, d = e % cols, i = i0 + li;
+        TP::begin(li);
+        D yi[n], yi1[n], K[TB::s][n], phi[n];
+        const double* yp = y + (size_t)i * n;
+#pragma unroll (unroll_for(n))
+        for (int k = 0; k < n; k++) {
+            yi[k] = D(yp[k], k == d ? 1.0 : 0.0);
+            yi1[k] = D(yp[n + k], (n + k) == d ? 1.0 : 0.0);
+        }
+        const double ti = mesh[i], h = mesh[i + 1] - ti;
+        phi_interval<P, ORDER, D>(yi, yi1, h, ti, p, K, phi);
+        double* out = (d < n ? Lb : Rb) + (size_t)i * n * n + (d < n ? d : d - n);
+#pragma unroll (unroll_for(n))
+        for (int k = 0; k < n; k++) out[k * n] = phi[k].d;
+    }
 }
 
 // ---- K4: defect estimate (Appendix A.5) ---------------------------------------------------------

@@ -3,6 +3,8 @@
 // functors plug in the same way.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "kernels.cuh"
 #include "problems.cuh"
@@ -30,6 +32,14 @@ struct ProblemOps {
     int (*bc_nodes_host)(int N, const double* mesh, const double* p, int* nodes);
 };
 
+// intervals per warp of the taped Jacobian kernel: fill the warp's 32 recording lanes when there are enough
+// intervals for every SM to get a few warps, fewer per warp on short meshes so the work still spreads
+inline int tape_default_ipw(int intervals) {
+    int ipw = 32;
+    while (ipw > 4 && (intervals + ipw - 1) / ipw < 4 * 148) ipw >>= 1;
+    return ipw;
+}
+
 template <class P, int ORDER> struct OpsImpl {
     static void residual(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
                          double* Kd, double* phi_out, unsigned long long* nb) {
@@ -48,8 +58,18 @@ template <class P, int ORDER> struct OpsImpl {
     }
     static void resjac(cudaStream_t st, int N, const double* mesh, const double* y, const double* p, double* Kd,
                        double* phi_out, unsigned long long* nb, double* Lb, double* Rb) {
-        const long long tot = (long long)(N - 1) * 2 * P::n;
-        k_resjac<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Kd, phi_out, nb, Lb, Rb);
+        // default: taped values + tangent replay (k_resjac_tape); MIRK_RESJAC=dual selects the plain dual
+        // sweep per column, MIRK_TAPE_IPW the intervals per warp (tuning / A-B measurements)
+        static const bool use_dual = getenv("MIRK_RESJAC") && !strcmp(getenv("MIRK_RESJAC"), "dual");
+        if (use_dual) {
+            const long long tot = (long long)(N - 1) * 2 * P::n;
+            k_resjac<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Kd, phi_out, nb, Lb, Rb);
+            return;
+        }
+        static const int ipw_env = getenv("MIRK_TAPE_IPW") ? atoi(getenv("MIRK_TAPE_IPW")) : 0;
+        int ipw = ipw_env >= 1 && ipw_env <= 32 ? ipw_env : tape_default_ipw(N - 1);
+        k_resjac_tape<P, ORDER><<<(unsigned)((N - 1 + ipw - 1) / ipw), 32, 0, st>>>(N, ipw, mesh, y, p, Kd, phi_out, nb,
+                                                                                  Lb, Rb);
     }
     static void defect(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
                        const double* Kd, double* Ki, double* errors, double* est,

@@ -143,6 +143,7 @@ struct Layer {
 // 7/8: chain of NP torsionally coupled pendula, two-point,
 //      u = [th_1..th_NP, om_1..om_NP], p = [g, kappa, a_1..a_NP, b_1..b_NP]
 template <int NP> struct Chain {
+    static constexpr int tape_calls = NP;  // one sin per pendulum and f evaluation (sizes the Jacobian tape)
     static constexpr int n = 2 * NP, np = 2 + 2 * NP, n_bc = 2 * NP, n_bca = NP, problem_type = 1,
                          max_bc_pts = 2;
     MIRK_PF f(T* du, const T* u, const double* p, double) {
