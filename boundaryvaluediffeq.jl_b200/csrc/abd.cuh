@@ -194,6 +194,44 @@ k_backsub_generic(int n, const int* __restrict__ nodes, const int* __restrict__ 
     }
 }
 
+// Dense D x D solve (D <= 32) by one warp: lane r holds row r of [M | rhs] (ld doubles apart) in registers;
+// Gauss-Jordan with row pivoting, pivot by one REDUX over the high words of |m[q]|, pivot row by shuffles.
+// The lane that pivoted on column e writes unknown e to delta[kept[e / n] * n + e % n].
+__device__ __forceinline__ void warp_dense_solve32(const double* M, int D, int ld, const int* kept, int n,
+                                                   double* delta, int* status) {
+    const int lane = threadIdx.x & 31;
+    double m[33];
+#pragma unroll
+    for (int c = 0; c < 32; c++) m[c] = (lane < D && c < D) ? M[(size_t)lane * ld + c] : 0.0;
+    m[32] = lane < D ? M[(size_t)lane * ld + D] : 0.0;
+    bool elig = lane < D;
+    int myq = -1;
+    double myinv = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        if (q < D) {
+            const double own = m[q];
+            const double own_inv = 1.0 / own;
+            const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
+            const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+            if ((mx >> 5) == 0u || mx >= 0x7ff00000u) { ok = false; break; }
+            const int pr = 31 - (int)(mx & 31u);
+            const bool isp = lane == pr;
+            const double inv = __shfl_sync(0xffffffffu, own_inv, pr);
+            const double f = isp ? 0.0 : -(own * inv);
+#pragma unroll
+            for (int c = q + 1; c < 33; c++) m[c] = fma(f, __shfl_sync(0xffffffffu, m[c], pr), m[c]);
+            if (isp) { elig = false; myq = q; myinv = own_inv; }
+        }
+    }
+    if (!ok) {
+        if (lane == 0) atomicExch(status, 1);
+        return;
+    }
+    if (myq >= 0) delta[(size_t)kept[myq / n] * n + myq % n] = m[32] * myinv;
+}
+
 // Closing solve on the surviving nodes kept[0..Q): Q-1 relations + L boundary rows, dense
 // Gauss-Jordan with row pivoting in a global scratch matrix M (D x (D+1), D = Q n).  One block.
 __device__ void final_solve_body(int n, int Q, const int* kept, const double* relL, const double* relR,
@@ -232,6 +270,12 @@ __device__ void final_solve_body(int n, int Q, const int* kept, const double* re
     for (int e = tid; e < (Q - 1) * n; e += T) M[(size_t)(L + e) * ld + D] = relr[e];
     for (int r = tid; r < D; r += T) elig[r] = 1;
     __syncthreads();
+    if (D <= 32) {
+        // small closing systems (two-point problems: D = 2n <= 32; the pendulum: D = 6): one warp, one lane
+        // per row in registers, REDUX pivot search and shuffle broadcast — no block barrier per pivot
+        if (tid < 32) warp_dense_solve32(M, D, ld, kept, n, delta, status);
+        return;
+    }
     if (!block_gauss_jordan(M, D, cols, ld, D, elig, pivrow, mult, prow, s_p)) {
         if (tid == 0) atomicExch(status, 1);
         return;

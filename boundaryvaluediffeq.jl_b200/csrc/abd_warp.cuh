@@ -335,34 +335,81 @@ __device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, cons
     double va[n];
 #pragma unroll
     for (int k = 0; k < n; k++) va[k] = da[k];
+    // the factor rows of a node do not depend on the running solution: fetch node j-1's row (and rt) while
+    // node j's products are in flight, so the right-to-left chain only carries the mat-vec, not the loads
+    double rv[n], rtv = 0.0;
+    if (act) {
+        const int c = nodes[k1 - 1];
+        const double* row = (half ? TR : TL) + c * nn + (size_t)q * n;
+#pragma unroll
+        for (int k = 0; k < n; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(row + k);
+            rv[k] = v.x; rv[k + 1] = v.y;
+        }
+        if (lane < n) rtv = rt[(size_t)c * n + lane];
+    }
     for (int j = k1 - 1; j > k0; j--) {
         const int c = nodes[j];
-        const double* row = (half ? TR : TL) + c * nn + (size_t)q * n;
         double acc = 0.0;
-        if (act) {
-            double rv[n];
+        double nx[n], nrt = 0.0;
+        if (act && j - 1 > k0) {
+            const int cn = nodes[j - 1];
+            const double* row = (half ? TR : TL) + cn * nn + (size_t)q * n;
 #pragma unroll
             for (int k = 0; k < n; k += 2) {
                 const double2 v = *reinterpret_cast<const double2*>(row + k);
-                rv[k] = v.x; rv[k + 1] = v.y;
+                nx[k] = v.x; nx[k + 1] = v.y;
             }
+            if (lane < n) nrt = rt[(size_t)cn * n + lane];
+        }
+        if (act) {
+            // four partial sums: the chain is n/4 dependent FMAs instead of n
+            double p4[4] = {0.0, 0.0, 0.0, 0.0};
             if (half == 0) {
 #pragma unroll
-                for (int k = 0; k < n; k++) acc = fma(rv[k], va[k], acc);
+                for (int k = 0; k < n; k++) p4[k & 3] = fma(rv[k], va[k], p4[k & 3]);
             } else {
 #pragma unroll
-                for (int k = 0; k < n; k++) acc = fma(rv[k], dr[k], acc);
+                for (int k = 0; k < n; k++) p4[k & 3] = fma(rv[k], dr[k], p4[k & 3]);
             }
+            acc = (p4[0] + p4[1]) + (p4[2] + p4[3]);
         }
         acc += __shfl_xor_sync(kFullMask, acc, 16);
         __syncwarp();
         if (lane < n) {
-            const double d = rt[(size_t)c * n + lane] - acc;
+            const double d = rtv - acc;
             delta[(size_t)c * n + lane] = d;
             dr[lane] = d;
         }
         __syncwarp();
+        if (j - 1 > k0) {
+#pragma unroll
+            for (int k = 0; k < n; k++) rv[k] = nx[k];
+            rtv = nrt;
+        }
     }
+}
+
+}  // namespace mirk
+#include "abd_mma.cuh"  // n = 16 on the FP64 tensor path (needs WarpABD above; included from here only)
+namespace mirk {
+
+// the merge kernel of a given block size: DMMA-fragment path for n = 16, lane-per-row otherwise
+template <int n, bool STAGE>
+__device__ __forceinline__ bool reduce_group(int g, const double* inL, const double* inR, const double* inr, double* outL,
+                                             double* outR, double* outr, const int* nodes, const int* gs, double* TL,
+                                             double* TR, double* rt, double* pbuf, int lane) {
+#if defined(MIRK_ABD_MMA)
+    if constexpr (n == 16) return mma_reduce_group16<STAGE>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf, lane);
+    else
+#endif
+        return warp_reduce_group<n>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf, lane);
+}
+template <int n, bool STAGE> __host__ __device__ constexpr int reduce_smem_doubles() {
+#if defined(MIRK_ABD_MMA)
+    if (n == 16) return MmaABD16::smem_doubles<STAGE>();
+#endif
+    return WarpABD<n>::smem_doubles_per_warp;
 }
 
 template <int n, int MINB>
@@ -371,11 +418,11 @@ k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ 
               double* __restrict__ outL, double* __restrict__ outR, double* __restrict__ outr,
               const int* __restrict__ nodes, const int* __restrict__ gs, double* __restrict__ TL,
               double* __restrict__ TR, double* __restrict__ rt, int* __restrict__ status) {
-    __shared__ __align__(16) double pbuf[4][WarpABD<n>::smem_doubles_per_warp];
+    __shared__ __align__(16) double pbuf[4][reduce_smem_doubles<n, true>()];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + wib;
     if (g >= G) return;
-    if (!warp_reduce_group<n>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf[wib], lane))
+    if (!reduce_group<n, true>(g, inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, pbuf[wib], lane))
         if (lane == 0) atomicExch(status, 1);
 }
 
@@ -425,13 +472,13 @@ template <int n>
 __global__ void __launch_bounds__(kTailWarps * 32, 1)
 k_tail_warp(const TailArgs a) {
     extern __shared__ double tail_smem[];
-    __shared__ __align__(16) double pbuf[kTailWarps][WarpABD<n>::smem_doubles_per_warp];
+    __shared__ __align__(16) double pbuf[kTailWarps][reduce_smem_doubles<n, false>()];
     __shared__ __align__(16) double dbuf[kTailWarps][2][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (int l = 0; l < a.nlev && (a.mode & 1); l++) {
         for (int g = wib; g < a.G[l]; g += kTailWarps) {
-            if (!warp_reduce_group<n>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
-                                      a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
+            if (!reduce_group<n, false>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
+                                        a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
                 if (lane == 0) atomicExch(a.status, 1);
         }
         __syncthreads();

@@ -36,7 +36,7 @@ struct ProblemOps {
 // intervals for every SM to get a few warps, fewer per warp on short meshes so the work still spreads
 inline int tape_default_ipw(int intervals) {
     int ipw = 32;
-    while (ipw > 4 && (intervals + ipw - 1) / ipw < 4 * 148) ipw >>= 1;
+    while (ipw > 4 && (intervals + ipw - 1) / ipw < 16 * 148) ipw >>= 1;
     return ipw;
 }
 
