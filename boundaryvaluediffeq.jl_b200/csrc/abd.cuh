@@ -194,42 +194,49 @@ k_backsub_generic(int n, const int* __restrict__ nodes, const int* __restrict__ 
     }
 }
 
-// Dense D x D solve (D <= 32) by one warp: lane r holds row r of [M | rhs] (ld doubles apart) in registers;
-// Gauss-Jordan with row pivoting, pivot by one REDUX over the high words of |m[q]|, pivot row by shuffles.
+// 1/x for a pivot: hardware reciprocal seed (MUFU.RCP64H via rcp.approx.ftz.f64) + two Newton steps,
+// branch-free (a full IEEE division drags a slow-path subroutine into the unrolled elimination).
+// Pivots are finite and non-zero here; relative error <= ~2 ulp.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+// Dense D x D solve (D <= 32) by one warp, in place on the shared-memory matrix [M | rhs] (ld doubles per row):
+// Gauss-Jordan with row pivoting, lane r owns row r, pivot by one REDUX over the high words of |M[r][q]|, the
+// pivot row is read by broadcast.  Rolled loops on purpose: the kernel runs this once, from a cold instruction
+// cache, so code size counts more than instruction count (the unrolled register version took ~20 us).
 // The lane that pivoted on column e writes unknown e to delta[kept[e / n] * n + e % n].
-__device__ __forceinline__ void warp_dense_solve32(const double* M, int D, int ld, const int* kept, int n,
-                                                   double* delta, int* status) {
+__device__ __forceinline__ void warp_dense_solve32(double* M, int D, int ld, const int* kept, int n, double* delta,
+                                                   int* status) {
     const int lane = threadIdx.x & 31;
-    double m[33];
-#pragma unroll
-    for (int c = 0; c < 32; c++) m[c] = (lane < D && c < D) ? M[(size_t)lane * ld + c] : 0.0;
-    m[32] = lane < D ? M[(size_t)lane * ld + D] : 0.0;
+    double* row = M + (size_t)(lane < D ? lane : 0) * ld;
     bool elig = lane < D;
     int myq = -1;
     double myinv = 0.0;
-    bool ok = true;
-#pragma unroll
-    for (int q = 0; q < 32; q++) {
-        if (q < D) {
-            const double own = m[q];
-            const double own_inv = 1.0 / own;
-            const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
-            const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-            if ((mx >> 5) == 0u || mx >= 0x7ff00000u) { ok = false; break; }
-            const int pr = 31 - (int)(mx & 31u);
-            const bool isp = lane == pr;
-            const double inv = __shfl_sync(0xffffffffu, own_inv, pr);
-            const double f = isp ? 0.0 : -(own * inv);
-#pragma unroll
-            for (int c = q + 1; c < 33; c++) m[c] = fma(f, __shfl_sync(0xffffffffu, m[c], pr), m[c]);
-            if (isp) { elig = false; myq = q; myinv = own_inv; }
+    for (int q = 0; q < D; q++) {
+        const double own = lane < D ? row[q] : 0.0;
+        const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
+        const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+        if ((mx >> 5) == 0u || mx >= 0x7ff00000u) {  // warp-uniform
+            if (lane == 0) atomicExch(status, 1);
+            return;
         }
+        const int pr = 31 - (int)(mx & 31u);
+        const double* prow = M + (size_t)pr * ld;
+        const double inv = fast_rcp(prow[q]);
+        if (lane == pr) { elig = false; myq = q; myinv = inv; }
+        else if (lane < D) {
+            const double f = -(own * inv);
+#pragma unroll 4
+            for (int c = q + 1; c <= D; c++) row[c] = fma(f, prow[c], row[c]);
+        }
+        __syncwarp();
     }
-    if (!ok) {
-        if (lane == 0) atomicExch(status, 1);
-        return;
-    }
-    if (myq >= 0) delta[(size_t)kept[myq / n] * n + myq % n] = m[32] * myinv;
+    if (myq >= 0) delta[(size_t)kept[myq / n] * n + myq % n] = row[D] * myinv;
 }
 
 // Closing solve on the surviving nodes kept[0..Q): Q-1 relations + L boundary rows, dense
@@ -250,17 +257,20 @@ __device__ void final_solve_body(int n, int Q, const int* kept, const double* re
     for (int e = tid; e < D * cols; e += T) M[e] = 0.0;
     __syncthreads();
     // boundary rows first (the reference's row order), accumulated per pinned node
+    // (one thread per matrix entry: a thread per row would walk its n x m dependent load / add / store chain
+    //  alone — ~15 us of pure latency at n = 16)
     const int m = *m_ptr;
-    if (tid < L) {
-        const int q = tid;
+    for (int e = tid; e < L * n; e += T) {
+        const int q = e / n, c = e % n;
         for (int k = 0; k < m; k++) {
             int slot = -1;
-            for (int s = 0; s < Q; s++) if (kept[s] == bc_nodes[k]) slot = s;
+            const int bn = bc_nodes[k];
+            for (int s = 0; s < Q; s++) if (kept[s] == bn) slot = s;
             if (slot < 0) { atomicExch(status, 2); continue; }
-            for (int c = 0; c < n; c++) M[(size_t)q * ld + slot * n + c] += Bc[((size_t)k * L + q) * n + c];
+            M[(size_t)q * ld + slot * n + c] += Bc[((size_t)k * L + q) * n + c];
         }
-        M[(size_t)q * ld + D] = q < La ? resid[q] : resid[tail_off + (q - La)];
     }
+    if (tid < L) M[(size_t)tid * ld + D] = tid < La ? resid[tid] : resid[tail_off + (tid - La)];
     for (int e = tid; e < (Q - 1) * (int)nn; e += T) {
         const int g = e / (int)nn, q = (e % (int)nn) / n, c = e % n;
         double* row = M + (size_t)(L + g * n + q) * ld;

@@ -26,6 +26,9 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1])
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void sts_f64(unsigned addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
 __device__ __forceinline__ void sts_v2f64(unsigned addr, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
@@ -33,11 +36,12 @@ __device__ __forceinline__ void sts_v2f64(unsigned addr, double x, double y) {
 struct MmaABD16 {
     static constexpr int n = 16, TR = 4, TJ = 6;  // 4 tile rows x 6 tile columns of 8 x 8
     static constexpr int PS = 52;                 // doubles per published pivot row (48 + pad: conflict-free B loads)
-    // per-warp shared memory (doubles): [0,128) panel gather Wp[row][4], later the coefficients Gs[row][4];
-    // [128, 128 + 4*PS) the published pivot rows; then (optional) the cp.async staging buffer of WarpABD<16>
-    static constexpr int oP = 128, core_doubles = 128 + 4 * PS;
+    // per-warp shared memory (doubles): [0, 4*CS) the gathered panel, column-major Wp[c][row] (column stride
+    // CS = 36: every access below is bank-conflict free), later the coefficients Gs[j][row]; then the 4 published
+    // pivot rows; then (optional) the cp.async staging buffer of WarpABD<16>
+    static constexpr int CS = 36, oP = 4 * CS, core_doubles = 4 * CS + 4 * PS;
     static constexpr int stage_stride = WarpABD<16>::stage_stride;
-    template <bool STAGE> static constexpr int smem_doubles() { return core_doubles + (STAGE ? WarpABD<16>::stage_doubles : 0); }
+    template <bool STAGE> __host__ __device__ static constexpr int smem_doubles() { return core_doubles + (STAGE ? WarpABD<16>::stage_doubles : 0); }
 
     // Gauss-Jordan on the 16 E columns.  w: this lane's fragments, rhs: rhs of row `lane`.  On return lane r
     // knows whether row r was a pivot row (myq = its column, myinv = 1 / pivot) or survives (myq = -1).
@@ -54,25 +58,26 @@ struct MmaABD16 {
             // (A) the panel into lane-per-row form
             if (t == t0 || t == t0 + 1) {
 #pragma unroll
-                for (int tr = 0; tr < TR; tr++)
-                    sts_v2f64(sa + 8u * (unsigned)((8 * tr + g) * 4 + 2 * (t - t0)), w[tr][jp][0], w[tr][jp][1]);
+                for (int tr = 0; tr < TR; tr++) {
+                    sts_f64(sa + 8u * (unsigned)((2 * (t - t0)) * CS + 8 * tr + g), w[tr][jp][0]);
+                    sts_f64(sa + 8u * (unsigned)((2 * (t - t0) + 1) * CS + 8 * tr + g), w[tr][jp][1]);
+                }
             }
             __syncwarp();
             double pe[4];
-            {
-                const double2 lo = lds_v2f64(sa + 8u * (unsigned)(4 * lane)), hi = lds_v2f64(sa + 8u * (unsigned)(4 * lane + 2));
-                pe[0] = lo.x; pe[1] = lo.y; pe[2] = hi.x; pe[3] = hi.y;
-            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) pe[c] = lds_f64(sa + 8u * (unsigned)(c * CS + lane));
             // (B) 4 pivot steps on the panel; gc[j] = coefficient of (pivot row j at panel start) in this row
             double gc[4] = {0.0, 0.0, 0.0, 0.0};
             int pr[4];
+            bool bad = false;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const double own = pe[k];
                 const double own_inv = fast_rcp(own);
                 const unsigned key = elig ? (((unsigned)__double2hiint(fabs(own)) & ~31u) | (unsigned)(31 - lane)) : 0u;
                 const unsigned mx = __reduce_max_sync(kFullMask, key);
-                if ((mx >> 5) == 0u || mx >= 0x7ff00000u) return false;
+                bad |= (mx >> 5) == 0u || mx >= 0x7ff00000u;  // zero / non-finite pivot: checked once per panel
                 pr[k] = 31 - (int)(mx & 31u);
                 const bool isp = lane == pr[k];
                 const double inv = __shfl_sync(kFullMask, own_inv, pr[k]);
@@ -84,6 +89,7 @@ struct MmaABD16 {
                 gc[k] = m;
                 if (isp) { elig = false; myq = q0 + k; myinv = own_inv; }
             }
+            if (bad) return false;  // warp-uniform
             {
                 const double rhs0 = rhs;
 #pragma unroll
@@ -91,26 +97,25 @@ struct MmaABD16 {
             }
             // (C) coefficients to shared memory (over the gathered panel: every lane has consumed it, the
             //     last REDUX needed pe[3])
-            sts_v2f64(sa + 8u * (unsigned)(4 * lane), gc[0], gc[1]);
-            sts_v2f64(sa + 8u * (unsigned)(4 * lane + 2), gc[2], gc[3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) sts_f64(sa + 8u * (unsigned)(j * CS + lane), gc[j]);
             // (D) the 4 pivot rows as they are (= as they were at panel start) into shared lines
             const int jlo = cq == 0 ? jp : jp + 1;  // first tile column with live entries behind the panel
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int trk = pr[k] >> 3, gk = pr[k] & 7;
-                if (g == gk) {
-                    const unsigned line = sa + 8u * (unsigned)(oP + k * PS + 2 * t);
-#define MIRK_PUB(TRI)                                                                  \
-    _Pragma("unroll") for (int j = jlo; j < TJ; j++) sts_v2f64(line + 8u * (unsigned)(8 * j), w[TRI][j][0], w[TRI][j][1]);
-                    if (trk == 0) { MIRK_PUB(0) } else if (trk == 1) { MIRK_PUB(1) } else if (trk == 2) { MIRK_PUB(2) } else { MIRK_PUB(3) }
-#undef MIRK_PUB
+            for (int tr = 0; tr < TR; tr++) {
+                const int r = 8 * tr + g;
+                const int kk = r == pr[0] ? 0 : r == pr[1] ? 1 : r == pr[2] ? 2 : r == pr[3] ? 3 : -1;
+                if (kk >= 0) {
+                    const unsigned line = sa + 8u * (unsigned)(oP + kk * PS + 2 * t);
+#pragma unroll
+                    for (int j = jlo; j < TJ; j++) sts_v2f64(line + 8u * (unsigned)(8 * j), w[tr][j][0], w[tr][j][1]);
                 }
             }
             __syncwarp();
             // (E) fragments and the rank-4 update of the live tiles
             double a[TR];
 #pragma unroll
-            for (int tr = 0; tr < TR; tr++) a[tr] = lds_f64(sa + 8u * (unsigned)((8 * tr + g) * 4 + t));
+            for (int tr = 0; tr < TR; tr++) a[tr] = lds_f64(sa + 8u * (unsigned)(t * CS + 8 * tr + g));
 #pragma unroll
             for (int j = jlo; j < TJ; j++) {
                 const double b = lds_f64(sa + 8u * (unsigned)(oP + t * PS + 8 * j + g));

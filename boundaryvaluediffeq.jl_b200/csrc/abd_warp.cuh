@@ -34,13 +34,6 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
 
 template <int n> struct WarpABD {
     static constexpr int rows = 2 * n, cols = 3 * n + 1;
@@ -320,7 +313,7 @@ __device__ __forceinline__ bool warp_reduce_group(int g, const double* inL, cons
 template <int n>
 __device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, const int* gs, const double* TL,
                                                    const double* TR, const double* rt, double* delta, double* da,
-                                                   double* dr, int lane) {
+                                                   double* dr, int lane, double* yup = nullptr) {
     const int k0 = gs[g], k1 = gs[g + 1];
     if (k1 - k0 == 1) return;
     constexpr size_t nn = (size_t)n * n;
@@ -379,6 +372,7 @@ __device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, cons
         if (lane < n) {
             const double d = rtv - acc;
             delta[(size_t)c * n + lane] = d;
+            if (yup) yup[(size_t)c * n + lane] -= d;  // fused Newton update y -= delta (level 0 only)
             dr[lane] = d;
         }
         __syncwarp();
@@ -429,12 +423,22 @@ k_reduce_warp(int G, const double* __restrict__ inL, const double* __restrict__ 
 template <int n>
 __global__ void __launch_bounds__(128)
 k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs, const double* __restrict__ TL,
-               const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta) {
+               const double* __restrict__ TR, const double* __restrict__ rt, double* __restrict__ delta,
+               double* __restrict__ yup) {
     __shared__ __align__(16) double dbuf[4][2][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + wib;
     if (g >= G) return;
-    warp_backsub_group<n>(g, nodes, gs, TL, TR, rt, delta, dbuf[wib][0], dbuf[wib][1], lane);
+    if (yup && lane < n) {
+        // fused update of the nodes this level does not recover: every group's left end, and the last node
+        const int a = nodes[gs[g]];
+        yup[(size_t)a * n + lane] -= delta[(size_t)a * n + lane];
+        if (g == G - 1) {
+            const int b = nodes[gs[g + 1]];
+            yup[(size_t)b * n + lane] -= delta[(size_t)b * n + lane];
+        }
+    }
+    warp_backsub_group<n>(g, nodes, gs, TL, TR, rt, delta, dbuf[wib][0], dbuf[wib][1], lane, yup);
 }
 
 // ---- the tail: every remaining level, the closing solve and the matching back substitutions in ONE
@@ -442,6 +446,10 @@ k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs,
 constexpr int kMaxTail = 20;
 struct TailArgs {
     int mode;  // bit 0: reduce the tail levels, bit 1: closing solve, bit 2: back-substitute the tail levels
+    // multi = 1: a SEGMENT of <= 4 radix-2 levels on many blocks.  Block b owns groups [8b, 8b+8) of the segment's
+    // first level, [4b, 4b+4) of the next, ... so each block walks its own sub-tree with block barriers only
+    // (needs pure pairing after the first level: checked by the host planner).  multi = 0: one block, all groups.
+    int multi;
     int nlev;
     int G[kMaxTail];
     const int* nodes[kMaxTail];
@@ -476,7 +484,10 @@ k_tail_warp(const TailArgs a) {
     __shared__ __align__(16) double dbuf[kTailWarps][2][16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (int l = 0; l < a.nlev && (a.mode & 1); l++) {
-        for (int g = wib; g < a.G[l]; g += kTailWarps) {
+        const int per = a.multi ? ((kTailWarps >> l) > 0 ? (kTailWarps >> l) : 1) : a.G[l];
+        const int gb = a.multi ? (int)blockIdx.x * per : 0;
+        const int ge = gb + per < a.G[l] ? gb + per : a.G[l];
+        for (int g = gb + wib; g < ge; g += kTailWarps) {
             if (!reduce_group<n, false>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
                                         a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
                 if (lane == 0) atomicExch(a.status, 1);
@@ -488,7 +499,10 @@ k_tail_warp(const TailArgs a) {
                          a.tail_off, a.M, a.delta, a.status, tail_smem);
     __syncthreads();
     for (int l = a.nlev - 1; l >= 0 && (a.mode & 4); l--) {
-        for (int g = wib; g < a.G[l]; g += kTailWarps)
+        const int per = a.multi ? ((kTailWarps >> l) > 0 ? (kTailWarps >> l) : 1) : a.G[l];
+        const int gb = a.multi ? (int)blockIdx.x * per : 0;
+        const int ge = gb + per < a.G[l] ? gb + per : a.G[l];
+        for (int g = gb + wib; g < ge; g += kTailWarps)
             warp_backsub_group<n>(g, a.nodes[l], a.gs[l], a.TL, a.TR, a.rt, a.delta, dbuf[wib][0], dbuf[wib][1], lane);
         __syncthreads();
     }
@@ -523,8 +537,7 @@ inline void launch_warp_reduce(cudaStream_t st, int n, int G, const double* inL,
     }
 }
 inline cudaError_t launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, int ctas, int smem_bytes) {
-    (void)ctas;
-    MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<1, kTailWarps * 32, smem_bytes, st>>>(a)));
+    MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<ctas, kTailWarps * 32, smem_bytes, st>>>(a)));
     return cudaGetLastError();
 }
 // opt in to as much dynamic shared memory as fits beside the kernel's static allocation
@@ -539,10 +552,10 @@ inline void set_warp_tail_smem(int n, int bytes) {
     });
 }
 inline void launch_warp_backsub(cudaStream_t st, int n, int G, const int* nodes, const int* gs, const double* TL,
-                                const double* TR, const double* rt, double* delta) {
+                                const double* TR, const double* rt, double* delta, double* yup = nullptr) {
     const int wpb = G < 1024 ? 1 : 4;
     const int blocks = (G + wpb - 1) / wpb;
-    MIRK_WARP_DISPATCH(n, (k_backsub_warp<NN><<<blocks, 32 * wpb, 0, st>>>(G, nodes, gs, TL, TR, rt, delta)));
+    MIRK_WARP_DISPATCH(n, (k_backsub_warp<NN><<<blocks, 32 * wpb, 0, st>>>(G, nodes, gs, TL, TR, rt, delta, yup)));
 }
 
 }  // namespace mirk

@@ -139,11 +139,15 @@ struct Plan {
     double *relL[kMaxLev + 1], *relR[kMaxLev + 1], *relr[kMaxLev + 1];
     std::vector<int> pinned;  // the pinned nodes the plan was built for
     int tail_begin = 0;       // levels [tail_begin, nlev) + the closing solve run in the one-block tail kernel
+    // multi-level launches of the upper levels (warp path): seg = {1, ..., tail_begin}; levels [seg[i], seg[i+1])
+    // run in ONE launch, each block walking its own radix-2 sub-tree (k_tail_warp, TailArgs::multi)
+    std::vector<int> seg;
     int N = 0, chunk = 0;
     bool valid = false;
 };
 
 struct mirk_solver_s {
+    bool update_fused = false;  // linear_solve already applied y -= delta (see can_fuse_update)
     mirk_desc desc;
     const ProblemOps* ops = nullptr;
     int n = 0, L = 0, La = 0, s = 0, si = 0;
@@ -241,7 +245,8 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     // levels, bits 16-31 the relation count from which the remaining levels run radix-2 inside the single-
     // block tail kernel (1 disables it).  Zero fields take the measured defaults (profiles/r01_notes.md): on
     // the warp path level 0 is sized to ONE wave of resident warps (12 per SM at 168 registers), clamped to
-    // [8, 16]; upper levels collapse 4 relations per warp (short dependent chains); the tail takes over at 16.
+    // [8, 16]; the upper levels run radix 2, up to four levels per launch (Plan::seg); the one-block tail takes
+    // over at 8 relations.
     const int chunk = S->desc.chunk;
     const bool warp_path0 = warp_reduce_supported(n);
     int c0 = chunk & 0xff;
@@ -249,8 +254,11 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
         c0 = 8;
         if (warp_path0) c0 = std::min(16, std::max(8, (N - 1 + S->sm_count * 12 - 1) / (S->sm_count * 12)));
     }
-    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : (warp_path0 ? 4 : c0);
-    const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 16;
+    // upper levels: an explicit field keeps one launch per level; the warp-path default is radix 2 with up to
+    // kSegLevels levels per launch (depth log2 instead of 3 merges per radix-4 level, a third of the launches)
+    const bool multi = warp_path0 && ((chunk >> 8) & 0xff) < 2;
+    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : (warp_path0 ? 2 : c0);
+    const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 8;
     const bool warp_path = warp_reduce_supported(n);
     if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
 
@@ -288,6 +296,19 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     }
     P.nlev = (int)nodes_l.size();
     P.tail_begin = (tail_begin < 0 || !warp_path) ? P.nlev : tail_begin;
+    P.seg.clear();
+    if (multi && P.tail_begin > 1) {
+        const int kSegLevels = 4;  // log2(kTailWarps) + 1
+        P.seg.push_back(1);
+        for (int l = 2; l < P.tail_begin; l++) {
+            // level l may join the running segment if it pairs consecutive relations (group g = relations 2g, 2g+1)
+            bool paired = true;
+            const std::vector<int>& gsv = gs_l[l];
+            for (size_t g = 0; g + 1 < gsv.size() && paired; g++) paired = gsv[g] == (int)(2 * g);
+            if (!paired || l - P.seg.back() >= kSegLevels) P.seg.push_back(l);
+        }
+        P.seg.push_back(P.tail_begin);
+    }
     if (P.nlev - P.tail_begin > kMaxTail) return fail(MIRK_ERR_STATE, "reduction tail deeper than kMaxTail");
     P.Q = (int)nodes.size();
     size_t ints = 0, rels = 0;
@@ -419,10 +440,24 @@ struct SolveCtx {
     const double* resid;
     size_t tail_off;
     bool exchange;  // run the partition exchange in place of the closing solve
+    double* y_update = nullptr;  // when set, the level-0 back substitution also applies y -= delta (warp path)
 };
 static SolveCtx main_ctx(mirk_solver_s* S) {
     return SolveCtx{&S->plan, S->TL, S->TR, S->rt, S->delta, S->Bc, S->bc_nodes, S->m_dev, S->resid,
                     (size_t)S->La + (size_t)(S->N - 1) * S->n, S->part};
+}
+
+// levels [l_from, l_to) of plan P into the level table of a tail / segment launch
+static void fill_tail_levels(TailArgs& a, const Plan& P, const SolveCtx& C, int l_from, int l_to, int* status) {
+    memset(&a, 0, sizeof(a));
+    a.nlev = l_to - l_from;
+    for (int t = 0; t < a.nlev; t++) {
+        const int l = l_from + t;
+        a.G[t] = P.G[l]; a.nodes[t] = P.d_nodes[l]; a.gs[t] = P.d_gs[l];
+        a.inL[t] = P.relL[l]; a.inR[t] = P.relR[l]; a.inr[t] = P.relr[l];
+        a.outL[t] = P.relL[l + 1]; a.outR[t] = P.relR[l + 1]; a.outr[t] = P.relr[l + 1];
+    }
+    a.TL = C.TL; a.TR = C.TR; a.rt = C.rt; a.delta = C.delta; a.status = status;
 }
 
 static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int l_end = kMaxLev) {
@@ -430,6 +465,20 @@ static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int 
     const int n = S->n;
     const bool smem_ok = reduce_smem_bytes(n) <= kSmemLimit;
     for (int l = l_begin; l < P.tail_begin && l < l_end; l++) {
+        if (!P.seg.empty() && l >= 1) {
+            // the segment starting at level l: one launch, every block reduces its own sub-tree
+            size_t si = 0;
+            while (si + 1 < P.seg.size() && P.seg[si] != l) si++;
+            if (si + 1 >= P.seg.size()) return fail(MIRK_ERR_STATE, "reduction segment table out of step");
+            TailArgs a;
+            fill_tail_levels(a, P, C, l, P.seg[si + 1], (int*)(S->words + 2));
+            a.mode = 1;
+            a.multi = 1;
+            CK(launch_warp_tail(S->st, n, a, (P.G[l] + kTailWarps - 1) / kTailWarps, 0));
+            S->launches++;
+            l = P.seg[si + 1] - 1;
+            continue;
+        }
         if (warp_reduce_supported(n)) {
             launch_warp_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
                                P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt,
@@ -491,15 +540,8 @@ static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
     if (C.exchange && P.Q != 2) return fail(MIRK_ERR_STATE, "a mesh segment must reduce to one relation");
     if (warp_reduce_supported(n)) {
         TailArgs a;
+        fill_tail_levels(a, P, C, P.tail_begin, P.nlev, (int*)(S->words + 2));
         a.mode = 7;
-        a.nlev = P.nlev - P.tail_begin;
-        for (int t = 0; t < a.nlev; t++) {
-            const int l = P.tail_begin + t;
-            a.G[t] = P.G[l]; a.nodes[t] = P.d_nodes[l]; a.gs[t] = P.d_gs[l];
-            a.inL[t] = P.relL[l]; a.inR[t] = P.relR[l]; a.inr[t] = P.relr[l];
-            a.outL[t] = P.relL[l + 1]; a.outR[t] = P.relR[l + 1]; a.outr[t] = P.relr[l + 1];
-        }
-        a.TL = C.TL; a.TR = C.TR; a.rt = C.rt; a.status = (int*)(S->words + 2);
         a.Q = P.Q; a.kept = P.d_nodes[P.nlev];
         a.relL = P.relL[P.nlev]; a.relR = P.relR[P.nlev]; a.relr = P.relr[P.nlev];
         a.L = S->L; a.La = S->La; a.m_ptr = C.m_dev; a.bc_nodes = C.bc_nodes; a.Bc = C.Bc; a.resid = C.resid;
@@ -529,8 +571,24 @@ static int abd_backsub(mirk_solver_s* S, const SolveCtx& C) {
     Plan& P = *C.P;
     const int n = S->n;
     for (int l = P.tail_begin - 1; l >= 0; l--) {
+        if (!P.seg.empty() && l >= 1) {
+            // the segment ENDING at level l: one launch back-substitutes all its levels, top down
+            size_t si = P.seg.size() - 1;
+            while (si > 0 && P.seg[si] != l + 1) si--;
+            if (si == 0) return fail(MIRK_ERR_STATE, "back-substitution segment table out of step");
+            const int lb = P.seg[si - 1];
+            TailArgs a;
+            fill_tail_levels(a, P, C, lb, l + 1, (int*)(S->words + 2));
+            a.mode = 4;
+            a.multi = 1;
+            CK(launch_warp_tail(S->st, n, a, (P.G[lb] + kTailWarps - 1) / kTailWarps, 0));
+            S->launches++;
+            l = lb;
+            continue;
+        }
         if (warp_reduce_supported(n))
-            launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
+            launch_warp_backsub(S->st, n, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta,
+                                l == 0 ? C.y_update : nullptr);
         else if (pair_reduce_supported(n))
             launch_pair_backsub(S->st, P.G[l], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, C.delta);
         else
@@ -540,10 +598,17 @@ static int abd_backsub(mirk_solver_s* S, const SolveCtx& C) {
     return launch_check("abd_backsub");
 }
 
-static int linear_solve(mirk_solver_s* S) {
+// fused update: the level-0 back substitution of the warp path can apply y -= delta on the fly (every node is
+// either recovered there or the left end of a level-0 group), which saves the separate pass over y and delta
+static bool can_fuse_update(const mirk_solver_s* S) {
+    return warp_reduce_supported(S->n) && !S->part && S->plan.valid && S->plan.tail_begin >= 1 && S->plan.nlev >= 1;
+}
+
+static int linear_solve(mirk_solver_s* S, bool with_update = false) {
     CKS(build_plan(S));
     CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
-    const SolveCtx C = main_ctx(S);
+    SolveCtx C = main_ctx(S);
+    if (with_update && can_fuse_update(S)) { C.y_update = S->y; S->update_fused = true; }
     CKS(abd_reduce(S, C));
     CKS(abd_final(S, C));
     CKS(abd_backsub(S, C));
@@ -551,6 +616,11 @@ static int linear_solve(mirk_solver_s* S) {
 }
 
 static int apply_update(mirk_solver_s* S) {
+    if (S->update_fused) {  // already applied by the level-0 back substitution
+        S->update_fused = false;
+        S->jac_valid = false;
+        return MIRK_OK;
+    }
     const size_t len = (size_t)S->N * S->n;
     k_axpy_neg<<<(unsigned)((len + 255) / 256), 256, 0, S->st>>>(len, S->y, S->delta);
     S->launches++;
@@ -578,7 +648,7 @@ static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* 
     CKS(read_words(S));
     double nrm = bits_to_double(S->h_words[0]);
     while (it < maxiters) {
-        CKS(linear_solve(S));
+        CKS(linear_solve(S, true));
         CKS(apply_update(S));
         it++;
         CKS(eval_resjac(S));  // F and J at the new iterate; J is unused only on the converged last pass
@@ -973,7 +1043,7 @@ int mirk_linear_solve(mirk_handle S, double* delta) {
 int mirk_newton_step(mirk_handle S, double* resid_norm) {
     NEED_GUESS(S);
     if (!S->resid_valid || !S->jac_valid) CKS(eval_resjac(S));
-    CKS(linear_solve(S));
+    CKS(linear_solve(S, true));
     CKS(apply_update(S));
     CKS(eval_residual(S));  // |F| at the new iterate; its Jacobian is built only if another step follows
     CKS(read_words(S));
@@ -1201,7 +1271,8 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
         CKS(eval_resjac(S));
         CK(cudaEventRecord(e[2], S->st));
         CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
-        const SolveCtx C = main_ctx(S);
+        SolveCtx C = main_ctx(S);
+        if (can_fuse_update(S)) { C.y_update = S->y; S->update_fused = true; }
         CKS(abd_reduce(S, C, 0, 1));
         CK(cudaEventRecord(e[3], S->st));
         CKS(abd_reduce(S, C, 1, kMaxLev));

@@ -59,12 +59,14 @@ def merge_mma(W, rhs):
     for pn in range(4):
         q0 = 4 * pn; jp = q0 // 8; cq = q0 % 8; t0 = cq // 2
         # A: gather the panel into lane-per-row form through shared memory
-        Wp = np.zeros((32, 4))
+        CS = 36
+        Wp = np.zeros(4 * CS)             # column-major, column stride CS
         for l in range(32):
             if T_[l] in (t0, t0 + 1):
                 for tr in range(4):
-                    Wp[8 * tr + G_[l], 2 * (T_[l] - t0): 2 * (T_[l] - t0) + 2] = w[l, tr, jp, :]
-        pe = Wp[LANES, :].copy()          # lane i reads row i
+                    Wp[(2 * (T_[l] - t0)) * CS + 8 * tr + G_[l]] = w[l, tr, jp, 0]
+                    Wp[(2 * (T_[l] - t0) + 1) * CS + 8 * tr + G_[l]] = w[l, tr, jp, 1]
+        pe = np.stack([Wp[c * CS + LANES] for c in range(4)], axis=1)   # lane i reads row i
         # B: panel steps, lane per row
         g = np.zeros((32, 4)); prs = []
         for k in range(4):
@@ -83,11 +85,13 @@ def merge_mma(W, rhs):
         for j in range(4):
             rhs = rhs + g[:, j] * rhs0[prs[j]]
         # C: coefficients into A-fragment layout through shared memory
-        Gs = g.copy()                     # Gs[row][j]
+        Gs = np.zeros(4 * CS)             # Gs[j][row], over the gathered panel
+        for j in range(4):
+            Gs[j * CS + LANES] = g[:, j]
         a = np.zeros((32, 4))
         for l in range(32):
             for tr in range(4):
-                a[l, tr] = Gs[8 * tr + G_[l], T_[l]]
+                a[l, tr] = Gs[T_[l] * CS + 8 * tr + G_[l]]
         # D: the 4 pivot rows at panel start into shared lines P[k][col]
         P = np.zeros(4 * PS)
         for k in range(4):
