@@ -309,10 +309,11 @@ k_resjac(int N, const double* __restrict__ mesh, const double* __restrict__ y, c
 }
 
 // ---- K1+K2 taped: values once per interval, tangents replay the tape (tape.cuh) ------------------------
-// One warp per CTA, `ipw` <= 32 consecutive intervals per warp.
-//   pass 1  lane = interval: stages, Phi_i, |Phi|_inf in plain FP64; every sin/cos/exp result goes to the tape
-//   pass 2  lane = (interval, column d of [L_i R_i]): tangent sweep with the elementary functions read back
-//           from the tape.  For right-hand sides whose only non-linearities are elementary functions of the
+// A CTA of 1..4 warps takes `ipw` <= 32 consecutive intervals.
+//   pass 1  first warp, lane = interval: stages, Phi_i, |Phi|_inf in plain FP64; every sin/cos/exp result goes
+//           to the tape (one pass-1 per CTA: with several warps its cost is shared by all of them)
+//   pass 2  all warps, thread = (interval, column d of [L_i R_i]): tangent sweep with the elementary functions
+//           read back from the tape.  For right-hand sides whose only non-linearities are elementary functions of the
 //           state (the pendulum chains) the whole value computation of this pass is dead code.
 // The optional `P::tape_calls` (elementary-function calls per f evaluation) sizes the tape; default n.
 template <class P, class = void> struct TapeCalls { static constexpr int value = P::n; };
@@ -323,19 +324,19 @@ template <class P, int ORDER> __host__ __device__ constexpr int tape_cap() {
 }
 
 template <class P, int ORDER>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kTapeThreads)
 k_resjac_tape(int N, int ipw, const double* __restrict__ mesh, const double* __restrict__ y,
               const double* __restrict__ p, double* __restrict__ Kd, double* __restrict__ phi_out,
               unsigned long long* __restrict__ norm_bits, double* __restrict__ Lb, double* __restrict__ Rb) {
     using TB = Tableau<ORDER>;
     constexpr int n = P::n, cols = 2 * n, CAP = tape_cap<P, ORDER>();
     using TP = Tape<CAP>;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x;  // pass 1 runs on the first warp only
     const int i0 = blockIdx.x * ipw;
     unsigned long long m = 0ull;
     {
         const int i = i0 + lane;
-        if (lane < ipw && i < N - 1) {
+        if (lane < ipw && lane < 32 && i < N - 1) {
             using V = RecVal<CAP>;
             TP::begin(lane);
             V yi[n], yi1[n], K[TB::s][n], phi[n];
@@ -359,11 +360,11 @@ k_resjac_tape(int N, int ipw, const double* __restrict__ mesh, const double* __r
         }
     }
     block_max_to_global(m, norm_bits);
-    __syncwarp();
+    __syncthreads();
     int here = N - 1 - i0;
     if (here > ipw) here = ipw;
     const int items = here * cols;
-    for (int e = lane; e < items; e += 32) {
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {
         using D = TapeDual<CAP>;
         const int li = e / cols, d = e % cols, i = i0 + li;
         TP::begin(li);

@@ -410,9 +410,13 @@ static int eval_residual(mirk_solver_s* S) {
     return launch_check("residual");
 }
 
+static int eval_resjac(mirk_solver_s* S);
+// J(y) on request (mirk_jacobian_blocks / mirk_linear_solve): the same fused kernel the Newton loop runs, so the
+// parity tests on the blocks exercise the production path (the residual it recomputes is the same F(y))
+// (mesh-partitioned handles keep the collective-free plain sweep: eval_resjac all-reduces |F| over the ranks)
 static int eval_jacobian(mirk_solver_s* S) {
+    if (!S->part) return eval_resjac(S);
     S->ops->jac_blocks(S->st, S->N, S->mesh, S->y, S->p, S->Lb, S->Rb);
-    // boundary blocks (reference pattern); rewrites the same boundary residual values
     S->launches++;
     CKS(eval_bc(S, 1, false));
     S->jac_valid = true;

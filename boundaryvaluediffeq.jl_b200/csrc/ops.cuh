@@ -32,12 +32,15 @@ struct ProblemOps {
     int (*bc_nodes_host)(int N, const double* mesh, const double* p, int* nodes);
 };
 
-// intervals per warp of the taped Jacobian kernel: fill the warp's 32 recording lanes when there are enough
-// intervals for every SM to get a few warps, fewer per warp on short meshes so the work still spreads
-inline int tape_default_ipw(int intervals) {
-    int ipw = 32;
+// shape of the taped Jacobian kernel: intervals per CTA (recorded by the lanes of its first warp) and warps per
+// CTA (all of them replay).  Enough intervals: full 32-lane recording shared by 4 warps; short meshes: fewer
+// intervals per CTA, one warp, so the work still spreads over the SMs.
+inline void tape_default_shape(int intervals, int& ipw, int& warps) {
+    ipw = 32;
+    warps = 4;
+    if ((intervals + 31) / 32 >= 4 * 148) return;
+    warps = 1;
     while (ipw > 4 && (intervals + ipw - 1) / ipw < 16 * 148) ipw >>= 1;
-    return ipw;
 }
 
 template <class P, int ORDER> struct OpsImpl {
@@ -67,9 +70,13 @@ template <class P, int ORDER> struct OpsImpl {
             return;
         }
         static const int ipw_env = getenv("MIRK_TAPE_IPW") ? atoi(getenv("MIRK_TAPE_IPW")) : 0;
-        int ipw = ipw_env >= 1 && ipw_env <= 32 ? ipw_env : tape_default_ipw(N - 1);
-        k_resjac_tape<P, ORDER><<<(unsigned)((N - 1 + ipw - 1) / ipw), 32, 0, st>>>(N, ipw, mesh, y, p, Kd, phi_out, nb,
-                                                                                  Lb, Rb);
+        static const int warps_env = getenv("MIRK_TAPE_WARPS") ? atoi(getenv("MIRK_TAPE_WARPS")) : 0;
+        int ipw, warps;
+        tape_default_shape(N - 1, ipw, warps);
+        if (ipw_env >= 1 && ipw_env <= 32) ipw = ipw_env;
+        if (warps_env >= 1 && warps_env <= kTapeThreads / 32) warps = warps_env;
+        k_resjac_tape<P, ORDER><<<(unsigned)((N - 1 + ipw - 1) / ipw), 32 * warps, 0, st>>>(N, ipw, mesh, y, p, Kd,
+                                                                                          phi_out, nb, Lb, Rb);
     }
     static void defect(cudaStream_t st, int N, const double* mesh, const double* y, const double* p,
                        const double* Kd, double* Ki, double* errors, double* est,

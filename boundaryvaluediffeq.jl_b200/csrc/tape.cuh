@@ -22,7 +22,8 @@ namespace mirk {
 
 #ifdef __CUDACC__
 
-constexpr int kTapeSlots = 32;  // intervals recorded per warp; tape kernels run one warp per CTA
+constexpr int kTapeSlots = 32;     // intervals recorded per CTA (by the lanes of its first warp)
+constexpr int kTapeThreads = 128;  // most threads a tape kernel runs per CTA (each has its own cursor)
 
 template <int CAP> struct Tape {
     static_assert(CAP >= 1, "tape needs at least one entry");
@@ -31,11 +32,11 @@ template <int CAP> struct Tape {
         return b;
     }
     __device__ __forceinline__ static unsigned* cursor() {
-        __shared__ unsigned c[kTapeSlots];
+        __shared__ unsigned c[kTapeThreads];
         return c + threadIdx.x;
     }
     __device__ __forceinline__ static unsigned* slot() {
-        __shared__ unsigned s[kTapeSlots];
+        __shared__ unsigned s[kTapeThreads];
         return s + threadIdx.x;
     }
     __device__ __forceinline__ static void begin(int slot_) { *cursor() = 0u; *slot() = (unsigned)slot_; }
