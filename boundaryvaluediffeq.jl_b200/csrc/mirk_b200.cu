@@ -146,8 +146,22 @@ struct Plan {
     bool valid = false;
 };
 
+// A captured launch sequence (CUDA graph) of one piece of the Newton iteration.  The sequences are fixed for a
+// given mesh size, plan and buffer set, so after a few direct runs they are captured once and replayed: the
+// ~10 dependent launches of an iteration then cost one graph launch on the host and shorter gaps on the device.
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    long epoch = -1;       // graph_epoch the slot was counted / captured for
+    int uses = 0;          // direct runs since the epoch changed
+    int64_t launches = 0;  // kernel launches the sequence contains
+};
+enum { kGraphResjac = 0, kGraphSolveUpdate = 1, kGraphSolve = 2, kNumGraphs = 3 };
+
 struct mirk_solver_s {
     bool update_fused = false;  // linear_solve already applied y -= delta (see can_fuse_update)
+    GraphSlot gslot[kNumGraphs];
+    long graph_epoch = 0;  // bumped whenever N, a device buffer or the reduction plan changes
+    bool use_graph = true;
     mirk_desc desc;
     const ProblemOps* ops = nullptr;
     int n = 0, L = 0, La = 0, s = 0, si = 0;
@@ -210,7 +224,7 @@ static int ensure_capacity(mirk_solver_s* S, int Nneed) {
     CK(dalloc(&S->TL, N * nn)); CK(dalloc(&S->TR, N * nn)); CK(dalloc(&S->rt, N * n));
     CK(dalloc(&S->delta, N * n)); CK(dalloc(&S->iold, N));
     S->Ncap = Nneed;
-    S->plan.valid = false;
+    S->plan.valid = false; S->graph_epoch++;
     return MIRK_OK;
 }
 
@@ -261,6 +275,7 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 8;
     const bool warp_path = warp_reduce_supported(n);
     if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
+    S->graph_epoch++;
 
     std::vector<char> is_pinned(N, 0);
     for (int v : pinned) is_pinned[v] = 1;
@@ -378,6 +393,51 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
 }
 
 // ---- pieces of a Newton step ---------------------------------------------------------------------
+static int launch_check(const char* what);
+
+// Run `body` (stream-ordered launches only, no host synchronisation) directly the first times, then capture it
+// into a CUDA graph and replay that.  MIRK_NO_GRAPH=1 keeps direct launches; mesh-partitioned handles (NCCL on
+// the stream) and any capture failure fall back to direct launches too.
+template <class F> static int run_graphed(mirk_solver_s* S, int key, F&& body) {
+    static const bool disabled = getenv("MIRK_NO_GRAPH") && atoi(getenv("MIRK_NO_GRAPH")) != 0;
+    if (disabled || !S->use_graph || S->part) return body();
+    GraphSlot& g = S->gslot[key];
+    if (g.epoch != S->graph_epoch) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+        g.epoch = S->graph_epoch;
+        g.uses = 0;
+    }
+    if (g.exec) {
+        CK(cudaGraphLaunch(g.exec, S->st));
+        S->launches += g.launches;
+        return MIRK_OK;
+    }
+    if (++g.uses < 3) return body();
+    const int64_t l0 = S->launches;
+    if (cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        S->use_graph = false;
+        return body();
+    }
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(S->st, &graph);
+    if (rc != MIRK_OK || e != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g.exec = nullptr;
+        S->use_graph = false;
+        S->launches = l0;
+        return body();
+    }
+    cudaGraphDestroy(graph);
+    g.launches = S->launches - l0;
+    CK(cudaGraphLaunch(g.exec, S->st));
+    return MIRK_OK;
+}
+
 static int launch_check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MIRK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -425,12 +485,15 @@ static int eval_jacobian(mirk_solver_s* S) {
 
 // F(y) and J(y) in one pass over the mesh: the Newton loop's per-iteration evaluation
 static int eval_resjac(mirk_solver_s* S) {
-    CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
-    S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb);
-    S->launches++;
-    CKS(eval_bc(S, 1, true));
+    CKS(run_graphed(S, kGraphResjac, [&]() -> int {
+        CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
+        S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb);
+        S->launches++;
+        CKS(eval_bc(S, 1, true));
+        return launch_check("resjac");
+    }));
     S->resid_valid = S->jac_valid = true;
-    return launch_check("resjac");
+    return MIRK_OK;
 }
 
 // what one almost-block-diagonal solve works on: the mesh system of this handle, or (mesh-partitioned
@@ -610,12 +673,17 @@ static bool can_fuse_update(const mirk_solver_s* S) {
 
 static int linear_solve(mirk_solver_s* S, bool with_update = false) {
     CKS(build_plan(S));
-    CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
     SolveCtx C = main_ctx(S);
-    if (with_update && can_fuse_update(S)) { C.y_update = S->y; S->update_fused = true; }
-    CKS(abd_reduce(S, C));
-    CKS(abd_final(S, C));
-    CKS(abd_backsub(S, C));
+    const bool fuse = with_update && can_fuse_update(S);
+    if (fuse) C.y_update = S->y;
+    CKS(run_graphed(S, fuse ? kGraphSolveUpdate : kGraphSolve, [&]() -> int {
+        CK(cudaMemsetAsync(S->words + 2, 0, sizeof(unsigned long long), S->st));
+        CKS(abd_reduce(S, C));
+        CKS(abd_final(S, C));
+        CKS(abd_backsub(S, C));
+        return MIRK_OK;
+    }));
+    if (fuse) S->update_fused = true;
     return MIRK_OK;
 }
 
@@ -753,7 +821,7 @@ static int refine_mesh(mirk_solver_s* S, int* info_out, int* Nnew_out) {
     CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(Nn - 1) * S->s * n, S->st));
     CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(Nn - 1) * S->si * n, S->st));
     S->jac_valid = S->resid_valid = false;
-    S->plan.valid = false;
+    S->plan.valid = false; S->graph_epoch++;
     return sync_host_mesh(S);
 }
 
@@ -769,7 +837,7 @@ static int halve_and_zero(mirk_solver_s* S) {
     CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(Nn - 1) * S->s * n, S->st));
     CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(Nn - 1) * S->si * n, S->st));
     S->jac_valid = S->resid_valid = false;
-    S->plan.valid = false;
+    S->plan.valid = false; S->graph_epoch++;
     return sync_host_mesh(S);
 }
 
@@ -885,6 +953,7 @@ int mirk_destroy(mirk_handle S) {
     dfree(S->if_L); dfree(S->if_R); dfree(S->if_r); dfree(S->if_TL); dfree(S->if_TR); dfree(S->if_rt);
     dfree(S->if_delta); dfree(S->if_Bc); dfree(S->if_resid); dfree(S->if_bc_nodes); dfree(S->if_m);
     dfree(S->iplan.d_int); dfree(S->iplan.d_rel);
+    for (GraphSlot& g : S->gslot) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
     if (S->h_words) cudaFreeHost(S->h_words);
     if (S->st) cudaStreamDestroy(S->st);
@@ -956,7 +1025,7 @@ int mirk_set_params(mirk_handle S, const double* params, int32_t n_params) {
     CK(cudaMemcpyAsync(S->p, S->h_p.data(), S->h_p.size() * sizeof(double), cudaMemcpyHostToDevice, S->st));
     CK(cudaStreamSynchronize(S->st));
     S->jac_valid = S->resid_valid = false;
-    S->plan.valid = false;
+    S->plan.valid = false; S->graph_epoch++;
     return MIRK_OK;
 }
 
@@ -979,7 +1048,7 @@ int mirk_set_mesh_guess(mirk_handle S, int32_t n_mesh, const double* mesh, const
     CK(cudaStreamSynchronize(S->st));
     S->have_guess = true;
     S->jac_valid = S->resid_valid = false;
-    S->plan.valid = false;
+    S->plan.valid = false; S->graph_epoch++;
     return MIRK_OK;
 }
 
@@ -1266,7 +1335,29 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
     const int NE = 9;
     std::vector<cudaEvent_t> ev((size_t)steps * NE);
     for (auto& e : ev) CK(cudaEventCreate(&e));
+    // (1) the timed region: `steps` Newton steps through the production path (eval_resjac + linear_solve with
+    //     the fused update — graph-replayed once warm), bracketed by two events
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
     const int64_t l0 = S->launches;
+    CK(cudaEventRecord(t0, S->st));
+    for (int it = 0; it < steps; it++) {
+        CK(cudaMemcpyAsync(S->y, S->y_guess, yb, cudaMemcpyDeviceToDevice, S->st));
+        CKS(eval_resjac(S));
+        CKS(linear_solve(S, true));
+        CKS(apply_update(S));
+    }
+    CK(cudaEventRecord(t1, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    const int64_t timed_launches = S->launches - l0;
+    float timed_ms = 0;
+    CK(cudaEventElapsedTime(&timed_ms, t0, t1));
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    // (2) the same steps again with an event after every phase (direct launches): the per-phase breakdown
+    const bool graph_was = S->use_graph;
+    S->use_graph = false;
     for (int it = 0; it < steps; it++) {
         cudaEvent_t* e = &ev[(size_t)it * NE];
         CK(cudaMemcpyAsync(S->y, S->y_guess, yb, cudaMemcpyDeviceToDevice, S->st));
@@ -1290,6 +1381,7 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
         CK(cudaEventRecord(e[8], S->st));
     }
     CK(cudaStreamSynchronize(S->st));
+    S->use_graph = graph_was;
     float ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tot = 0;
     for (int it = 0; it < steps; it++) {
         cudaEvent_t* e = &ev[(size_t)it * NE];
@@ -1299,12 +1391,12 @@ int mirk_bench_newton_steps(mirk_handle S, int32_t steps, float* total_ms, float
             ph[k] += ms;
         }
     }
-    // the whole timed region: first step's start to last step's end (includes the y resets between steps)
-    CK(cudaEventElapsedTime(&tot, ev[0], ev[(size_t)(steps - 1) * NE + 7]));
+    // the whole timed region: loop (1) (includes the y resets between steps)
+    tot = timed_ms;
     for (auto& e : ev) cudaEventDestroy(e);
     if (total_ms) *total_ms = tot;
     if (phase_ms) for (int k = 0; k < 8; k++) phase_ms[k] = ph[k];
-    if (launches) *launches = S->launches - l0;
+    if (launches) *launches = timed_launches;
     CKS(read_words(S));
     return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
 }

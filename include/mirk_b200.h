@@ -134,9 +134,11 @@ int mirk_interp(mirk_handle h, const double* t, int32_t m, int32_t deriv, double
 
 /* -- measurement helpers (bench.py): device-timed Newton steps with inputs resident in HBM ------- */
 /* runs `steps` full Newton steps (residual + Jacobian + ABD solve + update) from the stored guess,
- * resetting y to the guess before each step so every step does identical work; CUDA-event time of the
- * whole region in ms, per-phase sums (residual, jacobian, reduce level 0, upper reduce levels, closing
- * solve, back substitution, update, unused) in phase_ms[8], kernels launched in *launches. */
+ * resetting y to the guess before each step so every step does identical work, through the same code
+ * path as mirk_newton_solve (CUDA-graph replay once warm); CUDA-event time of that region in ms and the
+ * kernels it launched in *launches.  The same steps are then repeated with an event after every phase
+ * (direct launches) for the per-phase sums (unused, residual + jacobian, reduce level 0, upper reduce
+ * levels, tail + closing solve, back substitution, update, unused) in phase_ms[8]. */
 int mirk_bench_newton_steps(mirk_handle h, int32_t steps, float* total_ms, float* phase_ms, int64_t* launches);
 /* roofline denominators measured on the device: FP64 FMA TFLOP/s and HBM copy GB/s */
 int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
