@@ -324,7 +324,10 @@ template <class P, int ORDER> __host__ __device__ constexpr int tape_cap() {
 }
 
 template <class P, int ORDER>
-__global__ void __launch_bounds__(kTapeThreads)
+#ifndef MIRK_TAPE_MINB
+#define MIRK_TAPE_MINB 1
+#endif
+__global__ void __launch_bounds__(kTapeThreads, MIRK_TAPE_MINB)
 k_resjac_tape(int N, int ipw, const double* __restrict__ mesh, const double* __restrict__ y,
               const double* __restrict__ p, double* __restrict__ Kd, double* __restrict__ phi_out,
               unsigned long long* __restrict__ norm_bits, double* __restrict__ Lb, double* __restrict__ Rb) {

@@ -32,15 +32,15 @@ struct ProblemOps {
     int (*bc_nodes_host)(int N, const double* mesh, const double* p, int* nodes);
 };
 
-// shape of the taped Jacobian kernel: intervals per CTA (recorded by the lanes of its first warp) and warps per
-// CTA (all of them replay).  Enough intervals: full 32-lane recording shared by 4 warps; short meshes: fewer
-// intervals per CTA, one warp, so the work still spreads over the SMs.
-inline void tape_default_shape(int intervals, int& ipw, int& warps) {
-    ipw = 32;
-    warps = 4;
-    if ((intervals + 31) / 32 >= 4 * 148) return;
-    warps = 1;
-    while (ipw > 4 && (intervals + ipw - 1) / ipw < 16 * 148) ipw >>= 1;
+// shape of the taped Jacobian kernel (one warp per CTA by default): intervals per CTA chosen so the grid is a
+// whole number of FULL waves of resident CTAs — at C2's size 2500 CTAs of 8 intervals are 2.11 waves (the third
+// round runs 11 % full), 1177 CTAs of 17 intervals are one wave.  `slots` = resident CTAs on the device.
+inline int tape_intervals_per_cta(int intervals, int slots) {
+    if (slots < 1) slots = 1;
+    const int rounds = (intervals + 32 * slots - 1) / (32 * slots);  // waves needed at the maximum of 32 per CTA
+    int ipw = (intervals + slots * rounds - 1) / (slots * rounds);
+    if (ipw < 4) ipw = 4;  // short meshes: keep a few intervals per recording pass
+    return ipw > 32 ? 32 : ipw;
 }
 
 template <class P, int ORDER> struct OpsImpl {
@@ -71,8 +71,14 @@ template <class P, int ORDER> struct OpsImpl {
         }
         static const int ipw_env = getenv("MIRK_TAPE_IPW") ? atoi(getenv("MIRK_TAPE_IPW")) : 0;
         static const int warps_env = getenv("MIRK_TAPE_WARPS") ? atoi(getenv("MIRK_TAPE_WARPS")) : 0;
-        int ipw, warps;
-        tape_default_shape(N - 1, ipw, warps);
+        static const int slots = [] {
+            int occ = 0, dev = 0, sms = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resjac_tape<P, ORDER>, 32, 0);
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return (occ > 0 ? occ : 1) * (sms > 0 ? sms : 1);
+        }();
+        int ipw = tape_intervals_per_cta(N - 1, slots), warps = 1;
         if (ipw_env >= 1 && ipw_env <= 32) ipw = ipw_env;
         if (warps_env >= 1 && warps_env <= kTapeThreads / 32) warps = warps_env;
         k_resjac_tape<P, ORDER><<<(unsigned)((N - 1 + ipw - 1) / ipw), 32 * warps, 0, st>>>(N, ipw, mesh, y, p, Kd,

@@ -131,9 +131,15 @@ template <int C> __host__ __device__ __forceinline__ bool tape_get(double& x, do
     return false;
 #endif
 }
+// One out-of-line copy of sincos per kernel: the recording pass of a pendulum chain calls it s x n/2 times per
+// interval, and inlined (~100 instructions each) that is a 70 KB straight-line pass every warp streams once
+// through the instruction cache (measured as `no_instruction` stalls); as a call it is ~1 KB of hot code.
+#ifdef __CUDACC__
+static __device__ __noinline__ void sincos_outlined(double a, double* s, double* c) { ::sincos(a, s, c); }
+#endif
 __host__ __device__ __forceinline__ void sincos_hd(double a, double& s, double& c) {
 #ifdef __CUDA_ARCH__
-    ::sincos(a, &s, &c);
+    sincos_outlined(a, &s, &c);
 #else
     s = ::sin(a); c = ::cos(a);
 #endif

@@ -134,3 +134,24 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_dmma_fragment_merge_layout_matches_sequential_elimination():
+    """abd_mma.cuh's data movement (fragment layout, panel gather, published pivot rows, rank-4 DMMA updates)
+    restated lane by lane in numpy (experiments/mma_merge_emul.py) reproduces a plain row-pivoted Gauss-Jordan
+    elimination: same pivot rows, same surviving rows, same reciprocals."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mma_merge_emul", os.path.join(ROOT, "experiments", "mma_merge_emul.py"))
+    emul = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emul)
+    rng = np.random.default_rng(11)
+    for _ in range(3):
+        W = rng.standard_normal((32, 48))
+        rhs = rng.standard_normal(32)
+        W[:16, 32:] = 0.0   # carried rows have no B part
+        W[16:, 16:32] = 0.0  # incoming rows have no A part
+        Wa, ra, qa, ia = emul.merge_seq(W, rhs)
+        Wb, rb, qb, ib = emul.merge_mma(W, rhs)
+        assert (qa == qb).all()
+        assert np.abs(Wa[:, 16:] - Wb[:, 16:]).max() < 1e-12
+        assert np.abs(ra - rb).max() < 1e-12 and np.abs(ia - ib).max() < 1e-14
