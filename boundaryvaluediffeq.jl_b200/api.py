@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib as B
 
-__all__ = ["BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "DefectControl",
+__all__ = ["BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
            "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b",
            "EnsembleProblem", "EnsembleSolution", "EnsembleB200", "compile_device_function",
            "successful_retcode"]
@@ -200,6 +200,13 @@ class MIRK6(_AbstractMIRK):
     order = 6
 
 
+@dataclass(frozen=True)
+class MIRK6I(_AbstractMIRK):
+    """The 6th-order tableau with irrational abscissae (MIRK/src/mirk_tableaus.jl:154-194); `order` is the C ABI's
+    tableau code 7, the convergence order is 6."""
+    order = 7
+
+
 # ---- cache / solution ----------------------------------------------------------------------------
 class BVSolution:
     """What `solve` returns (MIRK/src/mirk.jl:324-331): `.u`, `.t`, `sol(t)`, `.retcode`, `.resid`,
@@ -259,7 +266,7 @@ class MIRKCache:
         self.info = prob.f.info
         self.n = self.info.n
         self.order = alg.order
-        self.s, self.s_star = {2: (1, 3), 3: (2, 3), 4: (3, 4), 5: (4, 6), 6: (5, 9)}[alg.order]
+        self.s, self.s_star = {2: (1, 3), 3: (2, 3), 4: (3, 4), 5: (4, 6), 6: (5, 9), 7: (5, 8)}[alg.order]
         p = prob.p
         self._p = p
         desc = B.Desc(prob.f.problem_id, alg.order, float(self.nlsolve_kwargs["abstol"]), int(bool(adaptive)),

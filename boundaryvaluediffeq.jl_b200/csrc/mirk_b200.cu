@@ -62,7 +62,8 @@ static const int kPluginBase = 1000;
 
 static const ProblemOps* find_ops(int id, int order) {
     using namespace problems;
-    if (id >= 0 && id <= kLayer) return (order == 4 || order == 6) ? ops_small(id, order) : ops_small_235(id, order);
+    if (id >= 0 && id <= kLayer)
+        return (order == 4 || order == 6) ? ops_small(id, order) : order == kMIRK6I ? ops_small_6i(id, order) : ops_small_235(id, order);
     if (id == kChain8) return ops_chain8(order);
     if (id == kChain16) return ops_chain16(order);
     if (id == kBratu64) return ops_bratu64(order);
@@ -776,6 +777,7 @@ static int do_interp(mirk_solver_s* S, int N, const double* mesh, const double* 
     case 3: launch_interp<3>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
     case 4: launch_interp<4>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
     case 5: launch_interp<5>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
+    case kMIRK6I: launch_interp<kMIRK6I>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
     default: launch_interp<6>(S, N, mesh, y, nt, ts, deriv, add_base, out, iold); break;
     }
     S->launches++;
@@ -794,7 +796,8 @@ static int refine_mesh(mirk_solver_s* S, int* info_out, int* Nnew_out) {
     const int N = S->N, n = S->n;
     const int smem_needed = (int)(sizeof(double) * 2 * (size_t)N);
     const int use_smem = smem_needed <= kSmemLimit;
-    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0, S->st>>>(S->desc.order, N, S->mesh, S->est, S->desc.abstol,
+    // the mesh selector wants the convergence order p (alg_order): 6 for the MIRK6I code
+    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0, S->st>>>(S->desc.order == kMIRK6I ? 6 : S->desc.order, N, S->mesh, S->est, S->desc.abstol,
                                                                   S->desc.max_num_subintervals, S->Ncap, S->mesh_new,
                                                                   S->sel_out, use_smem);
     S->launches++;
@@ -964,7 +967,8 @@ int mirk_destroy(mirk_handle S) {
 int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     if (!desc || !out) return fail(MIRK_ERR_ARG, "NULL argument");
     *out = nullptr;
-    if (desc->order < 2 || desc->order > 6) return fail(MIRK_ERR_UNSUPPORTED, "order must be 2..6 (MIRK2 .. MIRK6)");
+    if (desc->order < 2 || desc->order > kMIRK6I)
+        return fail(MIRK_ERR_UNSUPPORTED, "order must be 2..6 (MIRK2 .. MIRK6) or 7 (MIRK6I)");
     const ProblemOps* ops = find_ops(desc->problem_id, desc->order);
     if (!ops) return fail(MIRK_ERR_UNSUPPORTED, "unknown problem id, or this order is not instantiated for it");
     if (desc->n_params < ops->np) return fail(MIRK_ERR_ARG, "too few parameters for this problem");

@@ -112,6 +112,7 @@ template <class P, int ORDER> struct OpsImpl {
 // defined one per translation unit group (ops_*.cu) so the registry compiles in parallel
 const ProblemOps* ops_small(int id, int order);      // MIRK4, MIRK6
 const ProblemOps* ops_small_235(int id, int order);  // MIRK2, MIRK3, MIRK5
+const ProblemOps* ops_small_6i(int id, int order);   // MIRK6I (order code kMIRK6I = 7)
 const ProblemOps* ops_chain8(int order);
 const ProblemOps* ops_chain16(int order);
 const ProblemOps* ops_bratu64(int order);

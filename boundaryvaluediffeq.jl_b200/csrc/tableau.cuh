@@ -8,6 +8,7 @@
 //   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:89-118  (MIRK5: s=4, s*=6, tau*=0.3)
 //   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:120-152 (MIRK6: s=5, s*=9, tau*=0.7156)
 //   lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:463-575 (weights w, w' per order)
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:154-194 + interpolation.jl:582-710 (MIRK6I, code 7)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -190,6 +191,84 @@ template <> struct Tableau<6> {
                 683376640.0 / 78057.0 * t4 + 274726912.0 / 78057.0 * t5;
         wp[8] = 16384.0 / 147.0 * t2 - 65536.0 / 147.0 * t3 + 81920.0 / 147.0 * t4 -
                 32768.0 / 147.0 * t5;
+    }
+};
+
+// MIRK6I (`order` code 7): the 6th-order tableau with irrational abscissae, s = 5, s* = 8, tau* = 0.4
+//   lib/BoundaryValueDiffEqMIRK/src/mirk_tableaus.jl:154-194 (the second assignments of `b` and `x_star` are the
+//   ones in force), weights lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:582-710.
+// The expressions keep the reference's evaluation order (several entries are differences of numbers 60x their
+// size), with sqrt(21), sqrt(7), sqrt(3) as correctly rounded literals.
+constexpr int kMIRK6I = 7;
+template <> struct Tableau<kMIRK6I> {
+    static constexpr int order = 6, s = 5, s_star = 8, si = 3;
+    static constexpr double s21 = 4.58257569495584000658804719372800848898, s7 = 2.64575131106459059050161575363926042571,
+                            s3 = 1.73205080756887729352744634150587236694;
+    MIRK_HD static constexpr double c(int r) {
+        return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 0.5 - s21 / 14.0 : r == 3 ? 0.5 + s21 / 14.0 : 0.5;
+    }
+    MIRK_HD static constexpr double v(int r) {
+        return r == 0 ? 0.0 : r == 1 ? 1.0 : r == 2 ? 0.5 - 9.0 * s21 / 98.0 : r == 3 ? 0.5 + 9.0 * s21 / 98.0 : 0.5;
+    }
+    MIRK_HD static constexpr double b(int r) { return r < 2 ? 1.0 / 20.0 : r < 4 ? 49.0 / 180.0 : 16.0 / 45.0; }
+    MIRK_HD static constexpr double x(int r, int j) {
+        return r == 2 ? (j == 0 ? 1.0 / 14.0 + s21 / 98.0 : j == 1 ? -1.0 / 14.0 + s21 / 98.0 : 0.0)
+             : r == 3 ? (j == 0 ? 1.0 / 14.0 - s21 / 98.0 : j == 1 ? -1.0 / 14.0 - s21 / 98.0 : 0.0)
+             : r == 4 ? (j == 0 ? -5.0 / 128.0 : j == 1 ? 5.0 / 128.0 : j == 2 ? 7.0 * s21 / 128.0
+                                                         : j == 3 ? -7.0 * s21 / 128.0 : 0.0)
+                      : 0.0;
+    }
+    MIRK_HD static constexpr double c_star(int r) { return r == 0 ? 0.5 : r == 1 ? 0.5 - s7 / 14.0 : 87.0 / 100.0; }
+    MIRK_HD static constexpr double v_star(int r) { return c_star(r); }
+    MIRK_HD static constexpr double x_star(int r, int j) {
+        return r == 0 ? (j == 0 ? 1.0 / 64.0 : j == 1 ? -1.0 / 64.0 : j == 2 ? 7.0 / 192.0 * s21
+                         : j == 3 ? -7.0 / 192.0 * s21 : 0.0)
+             : r == 1 ? (j == 0 ? 3.0 / 112.0 + 9.0 / 1960.0 * s7 : j == 1 ? -3.0 / 112.0 + 9.0 / 1960.0 * s7
+                         : j == 2 ? 11.0 / 840.0 * s7 + 3.0 / 112.0 * s7 * s3
+                         : j == 3 ? 11.0 / 840.0 * s7 - 3.0 / 112.0 * s7 * s3
+                         : j == 4 ? 88.0 / 5145.0 * s7 : j == 5 ? -18.0 / 343.0 * s7 : 0.0)
+                      : (j == 0 ? 2707592511.0 / 1000000000000.0 - 1006699707.0 / 1000000000000.0 * s7
+                         : j == 1 ? -51527976591.0 / 1000000000000.0 - 1006699707.0 / 1000000000000.0 * s7
+                         : j == 2 ? -610366393.0 / 75000000000.0 + 7046897949.0 / 1000000000000.0 * s7 +
+                                        14508670449.0 / 1000000000000.0 * s7 * s3
+                         : j == 3 ? -610366393.0 / 75000000000.0 + 7046897949.0 / 1000000000000.0 * s7 -
+                                        14508670449.0 / 1000000000000.0 * s7 * s3
+                         : j == 4 ? -12456457.0 / 1171875000.0 + 1006699707.0 / 109375000000.0 * s7
+                         : j == 5 ? 3020099121.0 / 437500000000.0 * s7 + 47328957.0 / 625000000.0
+                         : j == 6 ? -7046897949.0 / 250000000000.0 * s7 : 0.0);
+    }
+    MIRK_HD static constexpr double tau_star() { return 0.4; }
+    MIRK_HD static void weights(double t, double* w, double* wp) {
+        const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t, tm1 = t - 1.0;
+        // the quartic shared by the weights of stages 3, 4 and 5, and the common factor of their derivatives
+        const double q = 14000.0 * t4 - 48216.0 * t3 + 1200.0 * s7 * t3 - 3555.0 * s7 * t2 + 62790.0 * t2 +
+                         3610.0 * s7 * t - 37450.0 * t + 9135.0 - 1305.0 * s7;
+        const double g = (259.0 + 50.0 * s7) * (14.0 * t - 7.0 + s7) * tm1 * (100.0 * t - 87.0) * (2.0 * t - 1.0) * t;
+        w[0] = -(12233.0 + 1450.0 * s7) *
+               (800086000.0 * t5 + 63579600.0 * s7 * t4 - 2936650584.0 * t4 + 4235152620.0 * t3 -
+                201404565.0 * s7 * t3 + 232506630.0 * s7 * t2 - 3033109390.0 * t2 + 1116511695.0 * t -
+                116253315.0 * s7 * t + 22707000.0 * s7 - 191568780.0) * t / 2112984835740.0;
+        w[1] = -(-10799.0 + 650.0 * s7) *
+               (24962000.0 * t4 + 473200.0 * s7 * t3 - 67024328.0 * t3 - 751855.0 * s7 * t2 + 66629600.0 * t2 -
+                29507250.0 * t + 236210.0 * s7 * t + 5080365.0 + 50895.0 * s7) * t2 / 29551834260.0;
+        w[2] = 7.0 / 1274940.0 * (259.0 + 50.0 * s7) * q * t2;
+        w[3] = w[2];
+        w[4] = 16.0 / 2231145.0 * (259.0 + 50.0 * s7) * q * t2;
+        w[5] = 4.0 / 1227278493.0 * (740.0 * s7 - 6083.0) *
+               (1561000.0 * t2 - 2461284.0 * t - 109520.0 * s7 * t + 979272.0 + 86913.0 * s7) * tm1 * tm1 * t2;
+        w[6] = -49.0 / 63747.0 * s7 * (20000.0 * t2 - 20000.0 * t + 3393.0) * tm1 * tm1 * t2;
+        w[7] = -1250000000.0 / 889206903.0 * (28.0 * t2 - 28.0 * t + 9.0) * tm1 * tm1 * t2;
+        wp[0] = (1450.0 * s7 + 12233.0) * (14.0 * t - 7.0 + s7) * tm1 * (-400043.0 * t + 75481.0 + 2083.0 * s7) *
+                (100.0 * t - 87.0) * (2.0 * t - 1.0) / 493029795006.0;
+        wp[1] = -(650.0 * s7 - 10799.0) * (14.0 * t - 7.0 + s7) * (37443.0 * t - 13762.0 - 2083.0 * s7) *
+                (100.0 * t - 87.0) * (2.0 * t - 1.0) * t / 20686283982.0;
+        wp[2] = 7.0 / 42498.0 * g;
+        wp[3] = wp[2];
+        wp[4] = 32.0 / 148743.0 * g;
+        wp[5] = 4.0 / 1227278493.0 * (740.0 * s7 - 6083.0) * (14.0 * t - 7.0 + s7) * tm1 * (100.0 * t - 87.0) *
+                (6690.0 * t - 4085.0 - 869.0 * s7) * t;
+        wp[6] = -98.0 / 21249.0 * s7 * tm1 * (100.0 * t - 13.0) * (100.0 * t - 87.0) * (2.0 * t - 1.0) * t;
+        wp[7] = -1250000000.0 / 2074816107.0 * (14.0 * t - 7.0 + s7) * tm1 * (14.0 * t - 7.0 - s7) * (2.0 * t - 1.0) * t;
     }
 };
 

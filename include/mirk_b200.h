@@ -47,7 +47,7 @@ typedef struct mirk_solver_s* mirk_handle;
  * (MIRK/mirk.jl:49-53, MIRK/algorithms.jl:55-61). */
 typedef struct {
     int32_t problem_id;            /* device functor: id from mirk_problem_lookup()             */
-    int32_t order;                 /* 2..6 = MIRK2() .. MIRK6() (2, 3, 5: built-ins with n <= 6) */
+    int32_t order;                 /* 2..6 = MIRK2() .. MIRK6(), 7 = MIRK6I() (2, 3, 5, 7: built-ins with n <= 6) */
     double abstol;                 /* 1e-6                                                      */
     int32_t adaptive;              /* 1                                                         */
     double defect_threshold;       /* DefectControl().defect_threshold = 0.1                    */

@@ -51,7 +51,7 @@ Base.@kwdef struct MIRK6B200 <: AbstractMIRKB200
     max_num_subintervals::Int = 3000
     device::Int = 0
 end
-for (name, ord) in ((:MIRK2B200, 2), (:MIRK3B200, 3), (:MIRK5B200, 5))
+for (name, ord) in ((:MIRK2B200, 2), (:MIRK3B200, 3), (:MIRK5B200, 5), (:MIRK6IB200, 7))  # 7 = the C ABI's code of MIRK6I
     @eval begin
         Base.@kwdef struct $name <: AbstractMIRKB200
             defect_threshold::Float64 = 0.1
@@ -215,6 +215,6 @@ function SciMLBase.__solve(ens::SciMLBase.AbstractEnsembleProblem, alg::Abstract
     return (; retcodes = RETCODES[ret .+ 1], n_mesh = nm, newton_iters = its, u_first = yfirst, converged)
 end
 
-export BVPDeviceFunction, MIRK2B200, MIRK3B200, MIRK4B200, MIRK5B200, MIRK6B200, EnsembleB200, register_plugin
+export BVPDeviceFunction, MIRK2B200, MIRK3B200, MIRK4B200, MIRK5B200, MIRK6B200, MIRK6IB200, EnsembleB200, register_plugin
 
 end # module

@@ -34,6 +34,9 @@ void orc_default_options(orc_options *o) {
     o->max_outer = 60;
 }
 
+/* alg_order (MIRK/alg_utils.jl:1-11): MIRK6I is a 6th-order method selected by its own code */
+int orc_convergence_order(int order) { return order == ORC_MIRK6I ? 6 : order; }
+
 /* MIRK/mirk_tableaus.jl:13-34 (MIRK2), :36-60 (MIRK3), :62-87 (MIRK4), :89-118 (MIRK5), :120-152 (MIRK6).
  * Only 1:s of c,v,b is used; x_star[r][j] is the reference's x_star[(j-1)(s*-s) + r] (interpolation.jl:308-309). */
 int orc_tableau_get(int order, orc_tableau *T) {
@@ -118,12 +121,80 @@ int orc_tableau_get(int order, orc_tableau *T) {
         T->tau_star = 0.7156;
         return 0;
     }
+    if (order == ORC_MIRK6I) { /* MIRK/mirk_tableaus.jl:154-194: Lobatto-type points with irrational coefficients.
+                                * `b` and `x_star` are assigned twice there; the second assignment is the one in force. */
+        const double s21 = sqrt(21.0), s7 = sqrt(7.0), s3 = sqrt(3.0);
+        T->s = 5;
+        T->s_star = 8;
+        const double c[5] = {0.0, 1.0, 0.5 - s21 / 14.0, 0.5 + s21 / 14.0, 0.5};
+        const double v[5] = {0.0, 1.0, 0.5 - 9.0 * s21 / 98.0, 0.5 + 9.0 * s21 / 98.0, 0.5};
+        const double b[5] = {1.0 / 20.0, 1.0 / 20.0, 49.0 / 180.0, 49.0 / 180.0, 16.0 / 45.0};
+        for (int r = 0; r < 5; r++) { T->c[r] = c[r]; T->v[r] = v[r]; T->b[r] = b[r]; }
+        T->x[2][0] = 1.0 / 14.0 + s21 / 98.0;  T->x[2][1] = -1.0 / 14.0 + s21 / 98.0;
+        T->x[3][0] = 1.0 / 14.0 - s21 / 98.0;  T->x[3][1] = -1.0 / 14.0 - s21 / 98.0;
+        T->x[4][0] = -5.0 / 128.0;             T->x[4][1] = 5.0 / 128.0;
+        T->x[4][2] = 7.0 * s21 / 128.0;        T->x[4][3] = -7.0 * s21 / 128.0;
+        const double cs[3] = {0.5, 0.5 - s7 / 14.0, 87.0 / 100.0};
+        for (int r = 0; r < 3; r++) { T->c_star[r] = cs[r]; T->v_star[r] = cs[r]; }
+        T->x_star[0][0] = 1.0 / 64.0;  T->x_star[0][1] = -1.0 / 64.0;
+        T->x_star[0][2] = 7.0 / 192.0 * s21;  T->x_star[0][3] = -7.0 / 192.0 * s21;
+        T->x_star[1][0] = 3.0 / 112.0 + 9.0 / 1960.0 * s7;
+        T->x_star[1][1] = -3.0 / 112.0 + 9.0 / 1960.0 * s7;
+        T->x_star[1][2] = 11.0 / 840.0 * s7 + 3.0 / 112.0 * s7 * s3;
+        T->x_star[1][3] = 11.0 / 840.0 * s7 - 3.0 / 112.0 * s7 * s3;
+        T->x_star[1][4] = 88.0 / 5145.0 * s7;
+        T->x_star[1][5] = -18.0 / 343.0 * s7;
+        T->x_star[2][0] = 2707592511.0 / 1000000000000.0 - 1006699707.0 / 1000000000000.0 * s7;
+        T->x_star[2][1] = -51527976591.0 / 1000000000000.0 - 1006699707.0 / 1000000000000.0 * s7;
+        T->x_star[2][2] = -610366393.0 / 75000000000.0 + 7046897949.0 / 1000000000000.0 * s7 +
+                          14508670449.0 / 1000000000000.0 * s7 * s3;
+        T->x_star[2][3] = -610366393.0 / 75000000000.0 + 7046897949.0 / 1000000000000.0 * s7 -
+                          14508670449.0 / 1000000000000.0 * s7 * s3;
+        T->x_star[2][4] = -12456457.0 / 1171875000.0 + 1006699707.0 / 109375000000.0 * s7;
+        T->x_star[2][5] = 3020099121.0 / 437500000000.0 * s7 + 47328957.0 / 625000000.0;
+        T->x_star[2][6] = -7046897949.0 / 250000000000.0 * s7;
+        T->tau_star = 0.4;
+        return 0;
+    }
     return -1;
 }
 
-/* MIRK/interpolation.jl:463-527 (orders 2, 3, 4, 5) and :528-575 (order 6): weights w(tau), w'(tau). */
+/* MIRK/interpolation.jl:463-527 (orders 2, 3, 4, 5), :528-575 (order 6) and :582-710 (MIRK6I): weights w(tau), w'(tau). */
 void orc_interp_weights(int order, double tau, double *w, double *wp) {
     const double t = tau;
+    if (order == ORC_MIRK6I) {
+        const double s7 = sqrt(7.0), t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t, tm1 = t - 1.0;
+        /* the quartic shared by the weights of stages 3, 4 and 5, and the common factor of their derivatives */
+        const double q = 14000.0 * t4 - 48216.0 * t3 + 1200.0 * s7 * t3 - 3555.0 * s7 * t2 + 62790.0 * t2 +
+                         3610.0 * s7 * t - 37450.0 * t + 9135.0 - 1305.0 * s7;
+        const double g = (259.0 + 50.0 * s7) * (14.0 * t - 7.0 + s7) * tm1 * (100.0 * t - 87.0) * (2.0 * t - 1.0) * t;
+        w[0] = -(12233.0 + 1450.0 * s7) *
+               (800086000.0 * t5 + 63579600.0 * s7 * t4 - 2936650584.0 * t4 + 4235152620.0 * t3 -
+                201404565.0 * s7 * t3 + 232506630.0 * s7 * t2 - 3033109390.0 * t2 + 1116511695.0 * t -
+                116253315.0 * s7 * t + 22707000.0 * s7 - 191568780.0) * t / 2112984835740.0;
+        w[1] = -(-10799.0 + 650.0 * s7) *
+               (24962000.0 * t4 + 473200.0 * s7 * t3 - 67024328.0 * t3 - 751855.0 * s7 * t2 + 66629600.0 * t2 -
+                29507250.0 * t + 236210.0 * s7 * t + 5080365.0 + 50895.0 * s7) * t2 / 29551834260.0;
+        w[2] = 7.0 / 1274940.0 * (259.0 + 50.0 * s7) * q * t2;
+        w[3] = w[2];
+        w[4] = 16.0 / 2231145.0 * (259.0 + 50.0 * s7) * q * t2;
+        w[5] = 4.0 / 1227278493.0 * (740.0 * s7 - 6083.0) *
+               (1561000.0 * t2 - 2461284.0 * t - 109520.0 * s7 * t + 979272.0 + 86913.0 * s7) * tm1 * tm1 * t2;
+        w[6] = -49.0 / 63747.0 * s7 * (20000.0 * t2 - 20000.0 * t + 3393.0) * tm1 * tm1 * t2;
+        w[7] = -1250000000.0 / 889206903.0 * (28.0 * t2 - 28.0 * t + 9.0) * tm1 * tm1 * t2;
+        wp[0] = (1450.0 * s7 + 12233.0) * (14.0 * t - 7.0 + s7) * tm1 * (-400043.0 * t + 75481.0 + 2083.0 * s7) *
+                (100.0 * t - 87.0) * (2.0 * t - 1.0) / 493029795006.0;
+        wp[1] = -(650.0 * s7 - 10799.0) * (14.0 * t - 7.0 + s7) * (37443.0 * t - 13762.0 - 2083.0 * s7) *
+                (100.0 * t - 87.0) * (2.0 * t - 1.0) * t / 20686283982.0;
+        wp[2] = 7.0 / 42498.0 * g;
+        wp[3] = wp[2];
+        wp[4] = 32.0 / 148743.0 * g;
+        wp[5] = 4.0 / 1227278493.0 * (740.0 * s7 - 6083.0) * (14.0 * t - 7.0 + s7) * tm1 * (100.0 * t - 87.0) *
+                (6690.0 * t - 4085.0 - 869.0 * s7) * t;
+        wp[6] = -98.0 / 21249.0 * s7 * tm1 * (100.0 * t - 13.0) * (100.0 * t - 87.0) * (2.0 * t - 1.0) * t;
+        wp[7] = -1250000000.0 / 2074816107.0 * (14.0 * t - 7.0 + s7) * tm1 * (14.0 * t - 7.0 - s7) * (2.0 * t - 1.0) * t;
+        return;
+    }
     if (order == 2) {
         w[0] = 0.0; w[1] = t * (1.0 - t / 2.0); w[2] = t * t / 2.0;
         wp[0] = 0.0; wp[1] = 1.0 - t; wp[2] = t;
@@ -705,7 +776,7 @@ int orc_mesh_select(int order, int n, int N, const double *mesh, const double *e
     for (int i = 0; i < ni; i++) {
         double e = 0.0;
         for (int k = 0; k < n; k++) if (fabs(errors[(size_t)i * n + k]) > e) e = fabs(errors[(size_t)i * n + k]);
-        sh[i] = pow(e / abstol, 1.0 / (order + 1));
+        sh[i] = pow(e / abstol, 1.0 / (orc_convergence_order(order) + 1));
         if (sh[i] > r1) r1 = sh[i];
         r2 += sh[i];
     }

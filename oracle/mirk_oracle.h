@@ -91,6 +91,8 @@ typedef struct {
 } orc_result;
 
 void orc_default_options(orc_options *o);
+#define ORC_MIRK6I 7 /* `order` code of MIRK6I (irrational 6th-order tableau); 2..6 are MIRK2..MIRK6 */
+int orc_convergence_order(int order);
 int orc_tableau_get(int order, orc_tableau *T);
 void orc_interp_weights(int order, double tau, double *w, double *wp);
 void orc_mesh_uniform(double t0, double t1, int nint, double *mesh);

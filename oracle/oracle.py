@@ -169,6 +169,9 @@ def custom_problem(n, n_p, f, dfdu, bc_times, bc, dbc, problem_type=0, n_bc=None
     return P
 
 
+MIRK6I = 7  # `order` code of the irrational 6th-order tableau (ORC_MIRK6I)
+
+
 def tableau(order) -> Tableau:
     T = Tableau()
     if lib().orc_tableau_get(order, C.byref(T)) != 0:
@@ -177,7 +180,7 @@ def tableau(order) -> Tableau:
 
 
 def interp_weights(order, tau):
-    ss = {2: 3, 3: 3, 4: 4, 5: 6, 6: 9}[order]
+    ss = {2: 3, 3: 3, 4: 4, 5: 6, 6: 9, MIRK6I: 8}[order]
     w, wp = np.zeros(9), np.zeros(9)
     lib().orc_interp_weights(order, float(tau), _d(w), _d(wp))
     return w[:ss], wp[:ss]

@@ -395,3 +395,94 @@ def test_reinterp_quirk_Q3_changes_only_the_newton_path(oracle):
     assert a.retcode == b.retcode == oracle.SUCCESS and a.hist_N == b.hist_N
     assert np.array_equal(a.t, b.t) and np.abs(a.u - b.u).max() < 5e-6  # both stop at |F|<=1e-6 on a linearly convergent path (Q2)
     assert sum(b.hist_newton) >= sum(a.hist_newton)
+
+
+def _mirk6i_mp():
+    """MIRK6I constants (mirk_tableaus.jl:154-194) in 60-digit arithmetic: the tableau is irrational, so the pin is
+    'correctly rounded from a high-precision evaluation of the reference's expressions' instead of exact rationals."""
+    import mpmath as mp
+    mp.mp.dps = 60
+    s21, s7, s3 = mp.sqrt(21), mp.sqrt(7), mp.sqrt(3)
+    q = mp.mpf
+    c = [q(0), q(1), q(1) / 2 - s21 / 14, q(1) / 2 + s21 / 14, q(1) / 2]
+    v = [q(0), q(1), q(1) / 2 - 9 * s21 / 98, q(1) / 2 + 9 * s21 / 98, q(1) / 2]
+    b = [q(1) / 20, q(1) / 20, q(49) / 180, q(49) / 180, q(16) / 45]
+    x = [[q(0)] * 5 for _ in range(5)]
+    x[2][0], x[2][1] = q(1) / 14 + s21 / 98, -q(1) / 14 + s21 / 98
+    x[3][0], x[3][1] = q(1) / 14 - s21 / 98, -q(1) / 14 - s21 / 98
+    x[4][0], x[4][1], x[4][2], x[4][3] = -q(5) / 128, q(5) / 128, 7 * s21 / 128, -7 * s21 / 128
+    cs = [q(1) / 2, q(1) / 2 - s7 / 14, q(87) / 100]
+    xs = [[q(0)] * 8 for _ in range(3)]
+    xs[0][:4] = [q(1) / 64, -q(1) / 64, q(7) / 192 * s21, -q(7) / 192 * s21]
+    xs[1][:6] = [q(3) / 112 + q(9) / 1960 * s7, -q(3) / 112 + q(9) / 1960 * s7,
+                 q(11) / 840 * s7 + q(3) / 112 * s7 * s3, q(11) / 840 * s7 - q(3) / 112 * s7 * s3,
+                 q(88) / 5145 * s7, -q(18) / 343 * s7]
+    T12 = q(10) ** 12
+    xs[2][:7] = [q(2707592511) / T12 - q(1006699707) / T12 * s7, -q(51527976591) / T12 - q(1006699707) / T12 * s7,
+                 -q(610366393) / 75000000000 + q(7046897949) / T12 * s7 + q(14508670449) / T12 * s7 * s3,
+                 -q(610366393) / 75000000000 + q(7046897949) / T12 * s7 - q(14508670449) / T12 * s7 * s3,
+                 -q(12456457) / 1171875000 + q(1006699707) / 109375000000 * s7,
+                 q(3020099121) / 437500000000 * s7 + q(47328957) / 625000000, -q(7046897949) / 250000000000 * s7]
+    return c, v, b, x, cs, xs
+
+
+def test_mirk6i_tableau_and_interpolant(oracle):
+    """MIRK6I (`order` code 7).  Constants within 1 ulp of the reference's expressions, stage consistency
+    c = v + sum x (also for the interpolation stages), quadrature conditions up to order 6, and for the continuous
+    extension (interpolation.jl:582-710): w(0) = 0, w(1) = [b; 0], u'(t_i) = K_1, u'(t_{i+1}) = K_2, w' = dw/dtau and
+    sum_r w_r(tau) c~_r^k = tau^(k+1)/(k+1) for k < 6 over all s* = 8 abscissae."""
+    import mpmath as mp
+    O = oracle
+    T = O.tableau(O.MIRK6I)
+    c, v, b, x, cs, xs = _mirk6i_mp()
+    assert (T.s, T.s_star) == (5, 8) and T.tau_star == 0.4
+
+    def close(a, exact):
+        # a few ulps of the largest term: some entries are differences of two numbers 60x their size, and the
+        # reference evaluates them in Float64 too
+        return abs(a - float(exact)) <= 4 * np.spacing(max(abs(float(exact)), 0.1))
+
+    for r in range(5):
+        assert close(T.c[r], c[r]) and close(T.v[r], v[r]) and close(T.b[r], b[r])
+        for j in range(5):
+            assert close(T.x[r][j], x[r][j])
+        assert abs(c[r] - v[r] - sum(x[r])) < mp.mpf(10) ** -50
+    for r in range(3):
+        assert close(T.c_star[r], cs[r]) and close(T.v_star[r], cs[r])
+        for j in range(8):
+            assert close(T.x_star[r][j], xs[r][j])
+        assert abs(sum(xs[r])) < mp.mpf(10) ** -11   # c* = v*: the row sums vanish (to the reference's 12 printed digits)
+    for k in range(6):
+        assert abs(sum(b[r] * c[r] ** k for r in range(5)) - mp.mpf(1) / (k + 1)) < mp.mpf(10) ** -50
+    w0, wp0 = O.interp_weights(O.MIRK6I, 0.0)
+    w1, wp1 = O.interp_weights(O.MIRK6I, 1.0)
+    bfull = np.zeros(8); bfull[:5] = [float(q) for q in b]
+    assert np.allclose(w0, 0, atol=1e-15) and np.allclose(w1, bfull, atol=1e-13)
+    e1 = np.zeros(8); e1[0] = 1
+    e2 = np.zeros(8); e2[1] = 1
+    assert np.allclose(wp0, e1, atol=1e-13) and np.allclose(wp1, e2, atol=1e-12)
+    call = np.array([float(q) for q in c] + [float(q) for q in cs])
+    for tau in (0.1, 0.4, 0.6, 0.93):
+        h = 1e-6
+        wa, _ = O.interp_weights(O.MIRK6I, tau - h)
+        wb, _ = O.interp_weights(O.MIRK6I, tau + h)
+        w, wp = O.interp_weights(O.MIRK6I, tau)
+        assert np.allclose((wb - wa) / (2 * h), wp, atol=1e-7)
+        for k in range(6):
+            assert abs(w @ call ** k - tau ** (k + 1) / (k + 1)) < 1e-13
+
+
+@pytest.mark.parametrize("name,p", [("linear2", [1.0, 0.0, 5.0, 5.0, 0.0, 0, 0]), ("linear2_tp", [1.0, 5.0, 0.0])])
+def test_mirk6i_convergence_order_and_interpolation(oracle, name, p):
+    """mirk_basic_tests.jl:122-139 for MIRK6I, plus the dense output against the analytic solution."""
+    O = oracle
+    P = O.builtin(name)
+    errs = []
+    for dt in (0.5, 0.25, 0.125):
+        s = O.solve_dt(P, O.MIRK6I, p, [5.0, -3.5], (0.0, 5.0), dt, adaptive=0, abstol=1e-8)
+        assert s.retcode == O.SUCCESS
+        errs.append(max(np.abs(s.u[i] - _exact_lin(s.t[i])).max() for i in range(s.N)))
+    assert abs(np.log2(errs[1] / errs[2]) - 6) < 0.4
+    s = O.solve_dt(P, O.MIRK6I, p, [5.0, -3.5], (0.0, 5.0), 0.1)
+    for t in (0.37, 2.51, 4.99):
+        assert np.abs(s(t) - _exact_lin(t)).max() < 1e-6
