@@ -111,8 +111,11 @@ def compile_device_function(name: str, struct_name: str, source: str, workdir: O
 @dataclass
 class BVProblem:
     """BVProblem(f, u0, tspan, p).  `u0` is a state vector (constant guess, CORE/utils.jl:766-769),
-    an (N, n) array (guess on a uniform mesh of N nodes, CORE/utils.jl:339-348,701-704) or a callable
-    `u0(p, t)`; `mesh=` overrides the node positions of an (N, n) guess."""
+    an (N, n) array / list of state vectors (guess on a uniform mesh of N nodes, CORE/utils.jl:339-348,
+    694), a callable `u0(p, t)`, or an object carrying its own mesh — a previous solution (`BVSolution`)
+    or anything with `.t` and `.u` like the reference's DiffEqArray / ODESolution guesses, whose nodes
+    become the initial mesh (CORE/utils.jl:701-704).  `mesh=` overrides the node positions of an (N, n)
+    guess.  The guess object is copied, never mutated (mirk_basic_tests.jl:717-719)."""
     f: BVPDeviceFunction
     u0: object
     tspan: Sequence[float]
@@ -124,6 +127,11 @@ class BVProblem:
             self.f = BVPDeviceFunction(self.f)
         self.tspan = (float(self.tspan[0]), float(self.tspan[1]))
         self.p = _arr(self.p).ravel()
+        if not callable(self.u0) and hasattr(self.u0, "t") and hasattr(self.u0, "u"):
+            # guess AND mesh from a previous solution / DiffEqArray-like object
+            if self.mesh is None:
+                self.mesh = np.array(self.u0.t, dtype=np.float64)
+            self.u0 = np.array([np.asarray(v, dtype=np.float64).ravel() for v in self.u0.u])
         if not callable(self.u0):
             self.u0 = _arr(self.u0)
 

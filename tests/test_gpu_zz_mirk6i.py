@@ -78,3 +78,28 @@ def test_mirk6i_convergence_order_on_gpu(M):
         errs.append(np.max(np.abs(sol.u[:, 0] - exact(sol.t))))
     rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert abs(np.mean(rates) - 6) < 0.5
+
+
+def test_previous_solution_as_initial_guess_carries_its_mesh(M, oracle):
+    """CORE/utils.jl:701-704: a DiffEqArray / ODESolution guess brings its own mesh.  Restarting
+    from a converged adaptive solution on its final mesh needs no refinement and at most one Newton step, and
+    the guess object is left untouched."""
+    O = oracle
+    p = [9.81]
+    u0 = [math.pi / 2, math.pi / 2]
+    first = M.solve(M.BVProblem("pendulum", u0, PENDULUM_T, p=p), M.MIRK4(), dt=0.05)
+    assert first.retcode == 0
+    keep_t, keep_u = first.t.copy(), first.u.copy()
+    again = M.solve(M.BVProblem("pendulum", first, PENDULUM_T, p=p), M.MIRK4())
+    ref = O.solve(O.builtin("pendulum"), 4, p, keep_t, keep_u)
+    assert again.retcode == ref.retcode == 0
+    assert again.original["hist_n_mesh"] == ref.hist_N and again.original["hist_newton"] == ref.hist_newton
+    assert len(again.original["hist_n_mesh"]) == 1 and again.original["hist_newton"][0] <= 1
+    assert np.array_equal(again.t, keep_t) and _rel(again.u, ref.u) < 1e-10
+    assert np.array_equal(first.t, keep_t) and np.array_equal(first.u, keep_u)
+
+    class DiffEqArrayLike:   # the reference's other mesh-carrying guess type
+        def __init__(self, t, u):
+            self.t, self.u = list(t), [list(v) for v in u]
+    third = M.solve(M.BVProblem("pendulum", DiffEqArrayLike(keep_t, keep_u), PENDULUM_T, p=p), M.MIRK4())
+    assert third.retcode == 0 and np.array_equal(third.t, keep_t)
