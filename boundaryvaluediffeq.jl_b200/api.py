@@ -127,7 +127,7 @@ class BVProblem:
             self.f = BVPDeviceFunction(self.f)
         self.tspan = (float(self.tspan[0]), float(self.tspan[1]))
         self.p = _arr(self.p).ravel()
-        if not callable(self.u0) and hasattr(self.u0, "t") and hasattr(self.u0, "u"):
+        if hasattr(self.u0, "t") and hasattr(self.u0, "u"):   # (a BVSolution is callable too: check this first)
             # guess AND mesh from a previous solution / DiffEqArray-like object
             if self.mesh is None:
                 self.mesh = np.array(self.u0.t, dtype=np.float64)
