@@ -1,16 +1,17 @@
-// abd_warp.cuh — register-resident warp path of the ABD reduction for small blocks (2n <= 32).
+// abd_warp.cuh — warp-level paths of the ABD reduction for small blocks (2n <= 32) and the multi-level kernel.
 //
-// Same algorithm, relation format and factor layout as abd.cuh (Wright-style stable block cyclic
-// reduction), but one WARP per group of relations and one LANE per row of the stacked
-// 2n x (3n+1) working matrix  [E | A | B | rhs]:
-//   * each lane keeps its row in registers (3n+1 doubles, 98 registers at n = 16);
-//   * the pivot of column q is found with one REDUX.MAX over the high words of |w[q]| plus a ballot
-//     (partial pivoting to ~2^-20 relative, plenty for stability);
-//   * the pivot row is broadcast through a double-buffered shared-memory line (one __syncwarp per
-//     pivot; broadcast LDS has no bank penalty), every other lane then does one DFMA per column;
-//   * pivot rows stay unscaled in registers and are scaled once when written out as factors.
-// The merge is a device function so the fused "Jacobian blocks + level-0 reduction" kernel in
-// kernels_fused.cuh shares it.
+// Same algorithm, relation format and factor layout as abd.cuh (Wright-style stable block cyclic reduction).
+//   * n = 2, 4, 6, 8: one WARP per group of relations and one LANE per row of the stacked 2n x (3n+1) working
+//     matrix [E | A | B | rhs] (WarpABD): each lane keeps its row in registers; the pivot of a column is one
+//     REDUX.MAX over the high words of |w[q]| (partial pivoting to ~2^-20 relative, plenty for stability); pivot
+//     rows stay unscaled and are scaled once when written out as factors.  MIRK_ELIM_PANEL (the build default)
+//     takes the pivots in panels of 4: inside a panel the pivot lane's few entries travel by shuffle, and the 4
+//     pivot rows are published once per panel through shared memory; without it every pivot row is broadcast
+//     through a double-buffered shared line.
+//   * n = 16: the merge runs in DMMA fragment layout (abd_mma.cuh, included below), MIRK_ABD_MMA (build default).
+//   * k_tail_warp: several radix-2 levels per launch — one block for the tail (plus the closing solve and the
+//     matching back substitutions), many blocks for a segment of upper levels, each walking its own sub-tree.
+// The next relation of a group is staged with cp.async while the current merge runs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
