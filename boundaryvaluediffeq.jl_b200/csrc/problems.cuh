@@ -7,8 +7,11 @@
 //     template<class T> static void f(T* du, const T* u, const double* p, double t)
 //     static int  bc_times(double* times, const double* p, double t0, double t1)
 //     template<class T> static void bc(T* res, const T* U /* m×n */, const double* p)
-// `T` is double for residuals and mirk::Dual for Jacobians (one templated source serves both,
-// like ForwardDiff on the Julia side).  bc reads the solution only through U[k] = sol(times[k]),
+// `T` is double for residuals; for Jacobians it is mirk::Dual (plain forward mode) or the pair mirk::RecVal /
+// mirk::TapeDual of the taped kernel (tape.cuh) — one templated source serves all, like ForwardDiff on the
+// Julia side.  Write elementary functions unqualified after `using namespace mirk::fn;` (sin, cos, exp, log,
+// sqrt, tanh, square, value) so they resolve on every scalar type; arithmetic with double constants is defined
+// on both sides of + - * /.  bc reads the solution only through U[k] = sol(times[k]),
 // which covers every access style the reference's tests use.  TwoPoint problems
 // have times = {t0, t1}, rows [0,n_bca) depend on U[0] only and the rest on U[1] only.
 //
