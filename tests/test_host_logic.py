@@ -155,3 +155,22 @@ def test_dmma_fragment_merge_layout_matches_sequential_elimination():
         assert (qa == qb).all()
         assert np.abs(Wa[:, 16:] - Wb[:, 16:]).max() < 1e-12
         assert np.abs(ra - rb).max() < 1e-12 and np.abs(ia - ib).max() < 1e-14
+
+
+def test_dmma_fragment_merge_n32_four_warps_matches_sequential_elimination():
+    """csrc/abd_mma32.cuh's data movement (four warps per merge, warp-local panels, block-wide pivot records and
+    pivot rows) restated thread by thread in numpy (experiments/mma32_merge_emul.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mma32_merge_emul", os.path.join(ROOT, "experiments", "mma32_merge_emul.py"))
+    emul = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emul)
+    rng = np.random.default_rng(12)
+    W = rng.standard_normal((64, 96))
+    rhs = rng.standard_normal(64)
+    W[:32, 64:] = 0.0
+    W[32:, 32:64] = 0.0
+    Wa, ra, qa, ia = emul.merge_seq(W, rhs)
+    Wb, rb, qb, ib = emul.merge_mma32(W, rhs)
+    assert (qa == qb).all()
+    assert np.abs(Wa[:, 32:] - Wb[:, 32:]).max() < 1e-11
+    assert np.abs(ra - rb).max() < 1e-11 and np.abs(ia - ib).max() < 1e-13
