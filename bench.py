@@ -3,25 +3,42 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-A "step" is one Newton step of the collocation system on the fixed C2 mesh: residual Phi + boundary
-rows, all (N-1) Jacobian blocks [L_i R_i] + boundary blocks, the almost-block-diagonal solve, the
-update y -= delta, and |F|_inf (unit of work M1).  Every step starts from the same
-stored guess so each does identical work.
+A "step" is one Newton step of the collocation system on a fixed mesh of C2's shape: residual Phi + boundary
+rows, all Jacobian blocks [L_i R_i] + boundary blocks, the almost-block-diagonal solve, the update
+y -= delta, and |F|_inf (unit of work M1).  Every step starts from the same stored guess so
+each does identical work.
 
-  value    device-resident throughput: K steps timed with CUDA events on the solver's stream
-  e2e      the same step through the C ABI with HOST buffers: mesh + guess copied host->device from
-           pinned memory, one Newton step, solution and |F|_inf copied back, every step
-  roofline the dominant kernel's algorithmic bytes / its CUDA-event duration vs measured HBM copy peak
-  cpu_baseline  the CPU oracle (a restatement of the reference's algorithm; the Julia reference
-           cannot run in this image) timed on this box's host cores, 1 thread like the reference
+  N = 1   one C2 problem on one GPU.
+  N > 1   (torchrun, one rank per GPU) the MESH-PARTITIONED mode the north star names: ONE boundary value
+          problem on 19 999 x N intervals, every rank holding a C2-sized segment (weak scaling).  Per Newton
+          step every rank reduces its segment to one interface relation, the relations are exchanged (remote
+          stores into peer memory over NVLink from inside the pack kernel — `--exchange nccl` selects
+          ncclAllGather instead), every rank solves the interface system and back-substitutes its segment; one
+          more 24-byte exchange max-reduces |F|_inf and the status word.  A step over N segments counts as N units
+          (C2-sized Newton steps), so `value` = N x steps / time and ideal weak scaling is N x the 1-GPU value.
+          Rank 0 also solves the whole problem on one GPU and the line carries the partitioned iterate's distance
+          from it (`parity_vs_single_gpu`, asserted <= 1e-10 relative).
 
-N > 1 (torchrun, one rank per GPU): the Newton path of ONE problem this size does not need more than
-one GPU, so ranks run independent C2 problems (an ensemble of large BVPs: independent units, no
-data-path collective), weak scaling; the timed region is bracketed by barriers and the slowest rank
-counts.  `--impl reference` runs the CPU oracle on rank 0 only.
+  value    device-resident throughput: K steps timed with CUDA events on the solver's stream (max over ranks)
+  e2e      the same step through the C ABI with HOST buffers: (this rank's segment of) mesh + guess copied
+           host->device from pinned memory, one Newton step, solution copied back, every step.  Two handles on
+           two host threads keep two independent problem instances in flight so copies overlap kernels
+           (`e2e.serial_value` is the one-handle, one-thread figure).
+  roofline the dominant kernel's algorithmic bytes (its share of SURVEY §8d's B = 32 n^2 N + 16 n N) / its
+           CUDA-event duration against the measured HBM copy peak, plus the FP64 fraction (C2 sits at
+           machine balance) for that kernel and for the whole step
+  cpu_baseline  the CPU oracle (a restatement of the reference's algorithm; the Julia reference cannot run in
+           this image) timed on this box's host cores, 1 thread like the reference's hot path
+  extra    `c3_strong` (BASELINE config C3: 262 144 pendulum BVPs sharded over the ranks, solves/s, converged
+           fraction) and `c5part` (config C5: n = 32, 2 000 000 nodes, mesh-partitioned over the ranks, ms per
+           Newton step) measured in the same run (`--no-extra` skips them)
+
+`--impl reference` runs the CPU oracle on rank 0 only and never maps libmirkb200.so.
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -35,6 +52,7 @@ if ROOT not in sys.path:
 
 METRIC = "mirk_newton_steps_per_sec"
 UNIT = "newton_steps/s"
+C2_NINT = 19999
 
 
 def _peaks():
@@ -44,6 +62,18 @@ def _peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_sha16():
+    """Hash of the CUDA sources: profiles/r02_traffic.json is only trusted for the build it was captured on."""
+    d = os.path.join(ROOT, "boundaryvaluediffeq.jl_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".cpp")) or f == "Makefile":
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode())
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -90,6 +120,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---- the CPU arm ------------------------------------------------------------------------------------
 def cpu_steps(cfg, steps):
     """K Newton steps of the CPU oracle on the full C2 problem (abstol = 0 so it never stops early)."""
     from oracle import oracle as O
@@ -100,10 +131,20 @@ def cpu_steps(cfg, steps):
     return it, dt, nrm
 
 
-def run_reference(args, cfg):
+CPU_NOTE = ("oracle/mirk_oracle.c orc_newton: an untuned C restatement of the reference algorithm (gcc -O3 "
+            "-march=x86-64-v3, FMA contraction off, naive dense products), single thread like the reference's hot "
+            "path; the Julia reference cannot run in this image, so this is context, not a tuned-CPU comparison")
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import mirk_b200  # noqa: F401  (package alias only; the shared library is NOT loaded on this arm)
+    from boundaryvaluediffeq_jl_b200 import configs
+    from oracle import oracle as O
+    configs.set_mesh_provider(O.mesh_uniform)
+    cfg = configs.c2_chain8(args.nint)
     if args.warmup > 0:
         cpu_steps(cfg, min(args.warmup, 2))
     it, dt, nrm = cpu_steps(cfg, args.steps)
@@ -112,193 +153,74 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / it, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(cfg, args.gpus),
+        "config": _config(cfg, args.gpus, None),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{it} full-size Newton steps (oracle/mirk_oracle.c orc_newton; the reference's "
-                                   "hot path is single-threaded and Julia is absent from this image)"},
+                         "sample": f"{it} full-size C2 Newton steps; " + CPU_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def _config(cfg, n_gpus):
+def _config(cfg, n_gpus, exchange):
+    if n_gpus <= 1 or exchange is None:
+        par = "one problem on one GPU" if n_gpus <= 1 else f"(CPU arm) 1 thread; the GPU arm partitions one mesh over {n_gpus} GPUs"
+        nodes_total = cfg.N
+    else:
+        par = (f"mesh-partitioned x{n_gpus}: one BVP on {cfg.nint * n_gpus + 1} nodes, one C2-sized segment per GPU; "
+               f"interface relations exchanged by {'peer-memory pushes over NVLink (CUDA IPC)' if exchange == 'p2p' else 'ncclAllGather'}")
+        nodes_total = cfg.nint * n_gpus + 1
     return {"workload": f"C2: {cfg.desc}; Newton step = residual + ABD Jacobian + block-cyclic-reduction solve + update",
             "problem": cfg.problem, "order": cfg.order, "n_states": cfg.n, "mesh_nodes": cfg.N,
-            "unknowns": cfg.N * cfg.n, "problems_per_gpu": 1, "parallelism": f"independent problems x{n_gpus}",
-            "l2_policy": "per-step working set (Jacobian blocks + elimination factors, ~4 x 82 MB) exceeds the 126 MB L2"}
+            "mesh_nodes_total": nodes_total, "unknowns": nodes_total * cfg.n, "parallelism": par,
+            "unit_of_value": "C2-sized Newton steps/s (a partitioned step over N segments counts N)",
+            "l2_policy": "per-step working set (Jacobian blocks + elimination factors, ~4 x 82 MB per GPU) exceeds the 126 MB L2"}
 
 
-def run_ensemble(args):
-    """BASELINE config C3: EnsembleProblem pendulum sweep, 262 144 BVPs, MIRK4, dt = 0.05, adaptive.
-    A step = one complete batched solve of this rank's shard.  strong scaling: the 262 144 trajectories are
-    block-partitioned over the ranks (no data-path collective); weak: 262 144 per rank."""
-    import math
+# ---- work model -------------------------------------------------------------------------
+def work_model(n, N, order):
+    """Algorithmic bytes and flops of one Newton step, split over the kernels so that the parts SUM to §8(d)'s
+    B = 8 [2 n N + N + 2 * 2 n^2 (N-1)] and F = F_f + F_J + F_S.  Factor write-back / re-reads of the elimination
+    are overhead traffic, not algorithmic bytes."""
+    ni, nn = N - 1, n * n
+    s, g = (5, 6) if order == 6 else (3, 2)
+    cf = 6 * n + (n // 2) * 20       # RHS flop count of the pendulum chain (sin ~ 20 flops)
+    Ff = ni * (s * cf + 2 * n * (s * (s + 1) // 2) + (2 * s + 1) * n)
+    FJ = ni * (s * 4 * n + 2 * g * n ** 3)
+    FS = (14.0 / 3.0) * n ** 3 * ni
+    bytes_ = {
+        "residual+jacobian_blocks": 8 * (n * N + N + 2 * nn * ni),   # read y, mesh; write L_i, R_i
+        "abd_reduce_level0": 8 * 2 * nn * ni,                          # read L_i, R_i
+        "abd_reduce_upper": 0, "abd_tail+closing_solve": 0,
+        "abd_backsub": 8 * n * N,                                      # write y_new (update fused)
+        "update": 0, "(unused)": 0,
+    }
+    # F_S = 14/3 n^3 per eliminated node (sequential partial-pivoting count; the ~1.65x extra of cyclic reduction is
+    # not credited), attributed to the level that eliminates the node: level 0 collapses groups of c0 intervals
+    c0 = min(16, max(8, -(-ni // (148 * 12)))) if n <= 16 else 8
+    f0 = (c0 - 1.0) / c0
+    flops = {
+        "residual+jacobian_blocks": Ff + FJ,
+        "abd_reduce_level0": FS * f0, "abd_reduce_upper": FS * (1.0 - f0) * 0.99, "abd_tail+closing_solve": FS * (1.0 - f0) * 0.01,
+        "abd_backsub": 4.0 * n * n * N, "update": 0, "(unused)": 0,
+    }
+    return bytes_, flops, sum(bytes_.values()), Ff + FJ + FS + 4.0 * n * n * N
 
-    import numpy as np
+
+PHASES = ["(unused)", "residual+jacobian_blocks", "abd_reduce_level0", "abd_reduce_upper", "abd_tail+closing_solve",
+          "abd_backsub", "update"]
+
+
+def _dist_setup():
     import torch
     import torch.distributed as dist
-
-    import mirk_b200 as M
-    from boundaryvaluediffeq_jl_b200 import configs, ensemble as E
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    total = args.trajectories * (world if args.ensemble_scaling == "weak" else 1)
-    params_all = configs.c3_ensemble_params(total)
-    first, count = E.partition(total, world)[rank]
-    prob = M.BVProblem("pendulum", [math.pi / 2, math.pi / 2], (0.0, math.pi / 2), p=[9.81])
-    h = E.EnsembleHandle(prob, M.MIRK4(), count, 0.05, device=local)
-    pin = torch.empty(count, 1, dtype=torch.float64).pin_memory()
-    pin.numpy()[:] = params_all[first:first + count]
-    h.set_inputs(pin.numpy(), prob.u0)
-    for _ in range(args.warmup):
-        h.run()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    ms = sum(h.run() for _ in range(args.steps))
-    barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value = total * args.steps / (float(t.item()) * 1e-3)
-    res = h.results()
-    conv = torch.tensor([int(np.sum(res["retcodes"] == 0))], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(conv)
-    # end to end: parameters from pinned host memory, batched solve, outcomes back to the host, every step
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        h.set_inputs(pin.numpy(), prob.u0)
-        h.run()
-        res = h.results()
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        cpu = None
-        if world == 1:
-            from oracle import oracle as O
-            nthreads = os.cpu_count() or 1
-            sample = 8192
-            t1 = time.perf_counter()
-            O.ensemble_solve(O.builtin("pendulum"), 4, params_all[:sample], prob.u0, prob.tspan, 32, nthreads=nthreads)
-            dt = time.perf_counter() - t1
-            cpu = {"value": sample / dt, "unit": "bvp_solves/s", "cores": nthreads, "kind": "port",
-                   "sample": f"first {sample} trajectories of the sweep, OpenMP over {nthreads} host threads (mirrors EnsembleThreads)"}
-        its = float(np.mean(res["newton_iters"]))
-        nm = float(np.mean(res["n_mesh"]))
-        print(json.dumps({
-            "metric": "ensemble_bvp_solves_per_sec", "value": value, "unit": "bvp_solves/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t.item()) / args.steps,
-            "higher_is_better": True, "scaling": args.ensemble_scaling, "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "C3: EnsembleProblem pendulum parameter sweep, g/L ~ U(8,12), MIRK4, dt=0.05, adaptive, abstol=1e-6",
-                       "trajectories_total": total, "trajectories_per_gpu": count, "parallelism": f"trajectory shards x{world}",
-                       "l2_policy": "per-trajectory state slab (8.3 GB per 262144 trajectories) exceeds L2"},
-            "converged_fraction": float(conv.item()) / total, "mean_newton_iters": its, "mean_final_nodes": nm,
-            "e2e": {"value": total * args.steps / float(te.item()), "unit": "bvp_solves/s",
-                    "h2d_bytes_per_step": 8 * count + 16, "d2h_bytes_per_step": count * (4 * 4 + 8 * 2 + 16)},
-            "gpu_launches": 2 * args.steps, "cpu_baseline": cpu, "clocks": clocks}), flush=True)
-    h.close()
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_partitioned(args):
-    """Mesh-partitioned single problem: C2's chain (n = 16, MIRK6), `--nint` intervals PER RANK (weak scaling),
-    one NCCL all-gather of the reduced interface relation + one 8-byte all-reduce per Newton step."""
-    import torch
-    import torch.distributed as dist
-
-    import mirk_b200 as M
-    from boundaryvaluediffeq_jl_b200 import configs, partition
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    maker = configs.c5_chain16 if args.workload == "c5part" else configs.c2_chain8
-    c = maker(args.nint * world + (world - 1))
-    prob = M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh)
-    cache, (lo, hi) = partition.init_partitioned(prob, M.MIRK6(), device=local, chunk=args.chunk)
-    cache.bench_newton_steps(max(args.warmup, 5))
-    dist.barrier()
-    torch.cuda.synchronize()
-    st, ms, ph, launches = cache.bench_newton_steps(args.steps)
-    dist.barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        per_step = float(t.item()) / args.steps
-        print(json.dumps({
-            "metric": "mirk_newton_steps_per_sec_mesh_partitioned", "value": 1e3 / per_step, "unit": "newton_steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
-            "scaling": "weak", "dtype": "f64", "data": "synthetic",
-            "mesh_interval_updates_per_sec": (c.N - 1) * 1e3 / per_step,
-            "config": {"workload": f"{c.desc}; mesh partitioned into {world} segments", "mesh_nodes_total": c.N,
-                       "mesh_nodes_per_gpu": hi - lo + 1, "n_states": c.n,
-                       "collectives_per_step": "1 all-reduce(max) of 8 B + 1 all-gather of (2n^2+n+2Ln+L) doubles per rank"},
-            "phases_us_rank0": [round(1e3 * p / args.steps, 1) for p in ph[:7]], "gpu_launches": int(launches)}), flush=True)
-    cache.close()
-    dist.destroy_process_group()
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nint", type=int, default=19999, help="mesh intervals (default: C2's 19 999)")
-    ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2part", "c5part"],
-                    help="c2: the headline Newton-step metric (default); c3: ensemble sweep; c2part/c5part: mesh-partitioned")
-    ap.add_argument("--trajectories", type=int, default=262144)
-    ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "b200" and args.workload == "c3":
-        return run_ensemble(args)
-    if args.impl == "b200" and args.workload in ("c2part", "c5part"):
-        return run_partitioned(args)
-
-    import numpy as np
-
-    import mirk_b200 as M
-    from boundaryvaluediffeq_jl_b200 import configs
-
-    cfg = configs.c2_chain8(args.nint)
-    if args.impl == "reference":
-        return run_reference(args, cfg)
-
-    import torch
-    import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -306,18 +228,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n, N = cfg.n, cfg.N
-    mesh_pinned = torch.empty(N, dtype=torch.float64).pin_memory()
-    y_pinned = torch.empty(N, n, dtype=torch.float64).pin_memory()
-    out_t = torch.empty(N, dtype=torch.float64).pin_memory()
-    out_y = torch.empty(N, n, dtype=torch.float64).pin_memory()
-    mesh_pinned.numpy()[:] = cfg.mesh
-    y_pinned.numpy()[:] = cfg.y0
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    cache = M.init(M.BVProblem(cfg.problem, y_pinned.numpy(), cfg.tspan, p=cfg.p, mesh=mesh_pinned.numpy()),
-                   M.MIRK6(), adaptive=False, device=local, chunk=args.chunk)
+    return rank, world, local, barrier, allmax
+
+
+def _make_cache(M, partition, cfg_full, world, local, args, pinned=None):
+    """A C2-shaped handle: the whole problem (world = 1) or this rank's segment of the partitioned one."""
+    if world == 1:
+        y, mesh = (pinned if pinned is not None else (cfg_full.y0, cfg_full.mesh))
+        prob = M.BVProblem(cfg_full.problem, y, cfg_full.tspan, p=cfg_full.p, mesh=mesh)
+        return M.init(prob, M.MIRK6() if cfg_full.order == 6 else M.MIRK4(), adaptive=False, device=local,
+                      chunk=args.chunk), (0, cfg_full.N - 1)
+    prob = M.BVProblem(cfg_full.problem, cfg_full.y0, cfg_full.tspan, p=cfg_full.p, mesh=cfg_full.mesh)
+    return partition.init_partitioned(prob, M.MIRK6() if cfg_full.order == 6 else M.MIRK4(), device=local,
+                                      chunk=args.chunk, exchange=args.exchange)
+
+
+def run_newton(args):
+    """The headline line: C2 Newton steps (one GPU) / mesh-partitioned C2-sized segments (N GPUs)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import _lib as B
+    from boundaryvaluediffeq_jl_b200 import configs, partition
+
+    rank, world, local, barrier, allmax = _dist_setup()
+    cfg1 = configs.c2_chain8(args.nint)                       # one segment's shape (for the work model / CPU arm)
+    cfg = cfg1 if world == 1 else configs.c2_chain8(args.nint * world)   # the whole problem
+    n = cfg.n
+    L = B.lib()
+    cache, (lo, hi) = _make_cache(M, partition, cfg, world, local, args)
+    Nloc = hi - lo + 1
+
     # ---- device-resident timing ------------------------------------------------------------------
-    st, _, _, _ = cache.bench_newton_steps(args.warmup)
+    st, _, _, _ = cache.bench_newton_steps(max(args.warmup, 3))
     assert st == 0, "warm-up Newton step failed"
     sampler = ClockSampler(local)
     if rank == 0:
@@ -327,100 +279,302 @@ def main():
     barrier()
     assert st == 0
     if args.profile:
-        print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps,
-                          "phases_us": [round(1e3 * p / args.steps, 1) for p in phases[:7]]}))
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps,
+                              "phases_us": [round(1e3 * p / args.steps, 1) for p in phases[:7]]}))
         cache.close()
         return
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = allmax(total_ms)
     value = world * args.steps / (total_ms_max * 1e-3)
 
+    # ---- parity of the partitioned iterate against the single-GPU solve of the same problem ---------
+    parity = None
+    if world > 1:
+        import torch.distributed as dist
+        B.check(L.mirk_set_mesh_guess(cache._h, Nloc, cfg.mesh[lo:hi + 1].ctypes.data_as(B.dp),
+                                      np.ascontiguousarray(cfg.y0[lo:hi + 1]).ctypes.data_as(B.dp)))
+        norms = []
+        for _ in range(3):
+            st, nrm = cache.newton_step()
+            norms.append(nrm)
+        full = partition.gather_solution(cache, cfg.N)
+        if rank == 0:
+            ref = M.init(M.BVProblem(cfg.problem, cfg.y0, cfg.tspan, p=cfg.p, mesh=cfg.mesh), M.MIRK6(), adaptive=False,
+                         device=local, chunk=args.chunk)
+            ref_norms = [ref.newton_step()[1] for _ in range(3)]
+            _, u = ref.solution()
+            ref.close()
+            rel = float(np.max(np.abs(full - u)) / np.max(np.abs(u)))
+            parity = {"newton_steps": 3, "max_rel_diff": rel, "resid_norms_partitioned": norms,
+                      "resid_norms_single_gpu": ref_norms, "tolerance": 1e-10}
+            assert rel <= 1e-10, f"partitioned iterate differs from the single-GPU one: {rel:.3e}"
+        dist.barrier()
+
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
-    import ctypes as C
-    from boundaryvaluediffeq_jl_b200 import _lib as B
-    L = B.lib()
     dptr = lambda tns: C.cast(tns.data_ptr(), B.dp)  # noqa: E731
-    nrm = C.c_double(0)
 
-    def e2e_step():
-        B.check(L.mirk_set_mesh_guess(cache._h, N, dptr(mesh_pinned), dptr(y_pinned)))
-        B.check(L.mirk_newton_step(cache._h, C.byref(nrm)))
-        B.check(L.mirk_get_solution(cache._h, dptr(out_t), dptr(out_y)))
+    def pinned_set():
+        mp = torch.empty(Nloc, dtype=torch.float64).pin_memory()
+        yp = torch.empty(Nloc, n, dtype=torch.float64).pin_memory()
+        ot = torch.empty(Nloc, dtype=torch.float64).pin_memory()
+        oy = torch.empty(Nloc, n, dtype=torch.float64).pin_memory()
+        mp.numpy()[:] = cfg.mesh[lo:hi + 1]
+        yp.numpy()[:] = cfg.y0[lo:hi + 1]
+        return mp, yp, ot, oy
 
-    for _ in range(args.warmup):
-        e2e_step()
+    def e2e_loop(handle, bufs, count):
+        mp, yp, ot, oy = bufs
+        nrm = C.c_double(0)
+        for _ in range(count):
+            B.check(L.mirk_set_mesh_guess(handle, Nloc, dptr(mp), dptr(yp)))
+            B.check(L.mirk_newton_step(handle, C.byref(nrm)))
+            B.check(L.mirk_get_solution(handle, dptr(ot), dptr(oy)))
+
+    bufs0 = pinned_set()
+    e2e_loop(cache._h, bufs0, args.warmup)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(cache._h, bufs0, args.steps)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(te.item())
+    e2e_serial = world * args.steps / allmax(time.perf_counter() - t0)
+    # two independent problem instances in flight (handles are re-entrant, one stream each): copies of one
+    # overlap the kernels of the other.  Partitioned handles are collective, so both host threads of every rank
+    # would have to interleave identically — the pipelined figure is taken at N = 1 only.
+    e2e_value, e2e_mode = e2e_serial, "one handle, one host thread"
+    if world == 1:
+        cache2, _ = _make_cache(M, partition, cfg, 1, local, args)
+        bufs1 = pinned_set()
+        e2e_loop(cache2._h, bufs1, args.warmup)
+        half = (args.steps + 1) // 2
+        th = [threading.Thread(target=e2e_loop, args=(h, b, half)) for h, b in ((cache._h, bufs0), (cache2._h, bufs1))]
+        barrier()
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        e2e_value = 2 * half / (time.perf_counter() - t0)
+        e2e_mode = "two handles on two host threads (copies of one instance overlap kernels of the other)"
+        cache2.close()
     clocks = sampler.stop() if rank == 0 else None
 
+    line = None
     if rank == 0:
         # ---- roofline of the dominant kernel -------------------------------------------------------
-        names = ["(unused)", "residual+jacobian_blocks", "abd_reduce_level0", "abd_reduce_upper", "abd_tail+closing_solve",
-                 "abd_backsub", "update"]
         per_step_ms = [p / args.steps for p in phases[:7]]
         k = int(np.argmax(per_step_ms))
-        nn, ni = n * n, N - 1
-        s = 5 if cfg.order == 6 else 3
-        alg_bytes = {
-            "(unused)": 0,
-            "residual+jacobian_blocks": 8 * (n * N + N + (s + 1) * n * ni + 2 * nn * ni),
-            # reads L_i, R_i, Phi_i; writes the elimination factors of every eliminated node and the
-            # collapsed relations: together again (2 n^2 + n) doubles per interval
-            "abd_reduce_level0": 8 * 2 * (2 * nn + n) * ni,
-            "abd_reduce_upper": 8 * 2 * (2 * nn + n) * ni // 7,
-            "abd_tail+closing_solve": 8 * 2 * (2 * nn + n) * 64,
-            "abd_backsub": 8 * ((2 * nn + n) * ni + n * N),
-            "update": 8 * 3 * n * N,
-        }
+        kb, kf, step_bytes, step_flops = work_model(n, Nloc, cfg.order)
         hbm_peak, peak_src = _peaks()
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and cfg.N == 20000:   # ncu-measured DRAM bytes per launch of that kernel (static capture)
-            with open(tpath) as fh:
-                traffic = json.load(fh).get(names[k])
-        achieved = alg_bytes[names[k]] / (per_step_ms[k] * 1e-3) * 1e-9
-        step_bytes = 8 * (2 * n * N + N + 2 * 2 * nn * ni)  # B = 32 n^2 N + 16 n N
-        # ---- CPU baseline (bounded sample: a few full-size steps, ~1 s each) ---------------------------
-        cpu = None
-        if world == 1:
-            it, dt, _ = cpu_steps(cfg, 8)
-            cpu = {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{it} full-size C2 Newton steps of the CPU oracle (restatement of the reference "
-                             "algorithm, single thread like the reference's hot path; Julia is absent here)"}
         fp64, hbm_live = C.c_double(0), C.c_double(0)
         B.check(L.mirk_measure_peaks(local, C.byref(fp64), C.byref(hbm_live)))
+        traffic, traffic_note = None, "no capture for this build"
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            if tj.get("src_sha16") == kernel_source_sha16() and Nloc == tj.get("mesh_nodes"):
+                traffic = tj.get("dram_bytes_per_launch", {}).get(PHASES[k])
+                traffic_note = f"ncu --set full capture of this build ({tj.get('capture')})"
+            else:
+                traffic_note = "profiles/r02_traffic.json was captured on another build or mesh size: not used"
+        step_s = total_ms_max / args.steps * 1e-3
+        kern_s = per_step_ms[k] * 1e-3
+        achieved = kb[PHASES[k]] / kern_s * 1e-9
+        cpu = None
+        if world == 1:
+            it, dt, _ = cpu_steps(cfg1, 8)
+            cpu = {"value": it / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{it} full-size C2 Newton steps; " + CPU_NOTE}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": _config(cfg, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (N + N * n),
-                    "d2h_bytes_per_step": 8 * (N + N * n) + 8},
+            "config": _config(cfg1, world, getattr(cache, "exchange", None)),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (Nloc + Nloc * n) * world,
+                    "d2h_bytes_per_step": (8 * (Nloc + Nloc * n) + 8) * world, "mode": e2e_mode,
+                    "serial_value": e2e_serial},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": names[k], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes[names[k]], "kernel_ms": per_step_ms[k],
-                         "whole_step": {"algorithmic_bytes": step_bytes,
-                                        "achieved_gbs": step_bytes / (total_ms_max / args.steps * 1e-3) * 1e-9},
+            "roofline": {"bound": "hbm", "kernel": PHASES[k], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": traffic_note,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": kb[PHASES[k]], "kernel_ms": per_step_ms[k],
+                         "fp64": {"achieved_tflops": kf[PHASES[k]] / kern_s * 1e-12, "peak_tflops": fp64.value,
+                                  "frac": kf[PHASES[k]] / kern_s * 1e-12 / fp64.value,
+                                  "algorithmic_flops_per_launch": kf[PHASES[k]]},
+                         "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / step_s * 1e-9,
+                                        "hbm_frac": step_bytes / step_s * 1e-9 / hbm_peak,
+                                        "algorithmic_flops": step_flops, "achieved_tflops": step_flops / step_s * 1e-12,
+                                        "fp64_frac": step_flops / step_s * 1e-12 / fp64.value,
+                                        "note": "per GPU (per segment when partitioned); the per-kernel algorithmic bytes sum to this"},
                          "live_peaks": {"fp64_fma_tflops": fp64.value, "hbm_copy_gbs": hbm_live.value}},
-            "phases_ms_per_step": dict(zip(names, per_step_ms)),
+            "phases_ms_per_step": dict(zip(PHASES, per_step_ms)),
+            "parity_vs_single_gpu": parity,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
     cache.close()
+    return line
+
+
+# ---- BASELINE config C3: the ensemble sweep -----------------------------------------------------------
+def measure_ensemble(args, scaling="strong", with_cpu=True):
+    """EnsembleProblem pendulum sweep, 262 144 BVPs, MIRK4, dt = 0.05, adaptive.  A step = one complete batched
+    solve of this rank's shard.  strong: the trajectories are block-partitioned over the ranks (no data-path
+    collective); weak: `--trajectories` per rank."""
+    import numpy as np
+    import torch
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import configs, ensemble as E
+
+    rank, world, local, barrier, allmax = _dist_setup()
+    total = args.trajectories * (world if scaling == "weak" else 1)
+    params_all = configs.c3_ensemble_params(total)
+    first, count = E.partition(total, world)[rank]
+    prob = M.BVProblem("pendulum", [math.pi / 2, math.pi / 2], (0.0, math.pi / 2), p=[9.81])
+    h = E.EnsembleHandle(prob, M.MIRK4(), count, 0.05, device=local)
+    pin = torch.empty(count, 1, dtype=torch.float64).pin_memory()
+    pin.numpy()[:] = params_all[first:first + count]
+    h.set_inputs(pin.numpy(), prob.u0)
+    steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        h.run()
+    barrier()
+    ms = sum(h.run() for _ in range(steps))
+    barrier()
+    ms = allmax(ms)
+    value = total * steps / (ms * 1e-3)
+    res = h.results()
+    conv = torch.tensor([int(np.sum(res["retcodes"] == 0))], dtype=torch.int64, device="cuda")
+    its = torch.tensor([float(np.sum(res["newton_iters"])), float(np.sum(res["n_mesh"]))], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        dist.all_reduce(conv)
+        dist.all_reduce(its)
+    # end to end: parameters from pinned host memory, batched solve, outcomes back to the host, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h.set_inputs(pin.numpy(), prob.u0)
+        h.run()
+        res = h.results()
+    barrier()
+    te = allmax(time.perf_counter() - t0)
+    h.close()
+    out = {"metric": "ensemble_bvp_solves_per_sec", "value": value, "unit": "bvp_solves/s", "n_gpus": world,
+           "steps": steps, "ms_per_step": ms / steps, "scaling": scaling, "trajectories_total": total,
+           "trajectories_per_gpu": count, "converged_fraction": float(conv.item()) / total,
+           "mean_newton_iters": float(its[0].item()) / total, "mean_final_nodes": float(its[1].item()) / total,
+           "e2e": {"value": total * steps / te, "unit": "bvp_solves/s", "h2d_bytes_per_step": 8 * total + 16,
+                   "d2h_bytes_per_step": total * (4 * 4 + 8 * 2 + 16)},
+           "workload": "C3: EnsembleProblem pendulum parameter sweep, g/L ~ U(8,12), MIRK4, dt=0.05, adaptive, abstol=1e-6"}
+    if rank == 0 and with_cpu and world == 1:
+        from oracle import oracle as O
+        nthreads = os.cpu_count() or 1
+        sample = 8192
+        t1 = time.perf_counter()
+        O.ensemble_solve(O.builtin("pendulum"), 4, params_all[:sample], prob.u0, prob.tspan, 32, nthreads=nthreads)
+        dt = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": sample / dt, "unit": "bvp_solves/s", "cores": nthreads, "kind": "port",
+                               "sample": f"first {sample} trajectories of the sweep, OpenMP over {nthreads} host threads (mirrors EnsembleThreads)"}
+    return out
+
+
+# ---- BASELINE config C5: n = 32, 2 000 000 nodes, mesh-partitioned ------------------------------------------
+def measure_c5(args):
+    import numpy as np  # noqa: F401
+
+    import mirk_b200 as M
+    from boundaryvaluediffeq_jl_b200 import configs, partition
+
+    rank, world, local, barrier, allmax = _dist_setup()
+    c = configs.c5_chain16(args.c5_nint)
+    cache, (lo, hi) = _make_cache(M, partition, c, world, local, args)
+    steps = max(1, min(args.steps, 5))
+    st, _, _, _ = cache.bench_newton_steps(2)
+    assert st == 0
+    barrier()
+    st, ms, ph, launches = cache.bench_newton_steps(steps)
+    barrier()
+    ms = allmax(ms)
+    cache.close()
+    per = ms / steps
+    n, ni = c.n, c.N - 1
+    _, _, B_, F_ = work_model(n, c.N, c.order)
+    return {"metric": "mirk_newton_steps_per_sec_mesh_partitioned", "ms_per_step": per, "value": 1e3 / per,
+            "unit": "newton_steps/s", "n_gpus": world, "steps": steps, "n_states": n, "mesh_nodes_total": c.N,
+            "mesh_nodes_per_gpu": hi - lo + 1, "mesh_interval_updates_per_sec": ni * 1e3 / per,
+            "algorithmic_gflop_per_step": F_ * 1e-9, "achieved_tflops_all_gpus": F_ / (per * 1e-3) * 1e-12,
+            "algorithmic_gb_per_step": B_ * 1e-9, "achieved_gbs_all_gpus": B_ / (per * 1e-3) * 1e-9,
+            "exchange": getattr(cache, "exchange", None),
+            "phases_ms_rank0": dict(zip(PHASES, [p / steps for p in ph[:7]])), "gpu_launches": int(launches),
+            "workload": f"C5: {c.desc}; mesh partitioned into {world} segment(s)"}
+
+
+def _guarded(fn, *a, **kw):
+    """extras must not take the headline line down with them"""
+    try:
+        return fn(*a, **kw)
+    except BaseException as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nint", type=int, default=C2_NINT, help="mesh intervals per GPU (default: C2's 19 999)")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"], help="interface exchange of the partitioned mode")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5part"],
+                    help="c2: the headline Newton-step line (default, with the extras); c3 / c5part: that workload alone")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C5 extras of the default run")
+    ap.add_argument("--trajectories", type=int, default=262144)
+    ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--c5-nint", type=int, default=1999999)
+    ap.add_argument("--extra-timeout", type=float, default=300.0)
+    ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    if args.workload == "c3":
+        out = measure_ensemble(args, args.ensemble_scaling)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    elif args.workload == "c5part":
+        out = measure_c5(args)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    else:
+        line = run_newton(args)
+        if not args.profile:
+            extra = None
+            if not args.no_extra:
+                # the extras are collective: if one rank fails the others would wait forever, so a watchdog prints the
+                # headline line without them and ends the process
+                def give_up():
+                    if rank == 0:
+                        line["extra"] = {"error": f"extras did not finish within {args.extra_timeout} s"}
+                        print(json.dumps(line), flush=True)
+                    os._exit(0)
+                dog = threading.Timer(args.extra_timeout, give_up)
+                dog.daemon = True
+                dog.start()
+                extra = {"c3_strong": _guarded(measure_ensemble, args, "strong", True), "c5part": _guarded(measure_c5, args)}
+                dog.cancel()
+            if rank == 0:
+                line["extra"] = extra
+                print(json.dumps(line), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except ImportError:
+        pass
 
 
 if __name__ == "__main__":

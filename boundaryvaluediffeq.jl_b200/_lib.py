@@ -68,6 +68,9 @@ SYMBOLS = {
     "mirk_destroy": (C.c_int, [Handle]),
     "mirk_set_params": (C.c_int, [Handle, dp, C.c_int32]),
     "mirk_set_mesh_guess": (C.c_int, [Handle, C.c_int32, dp, dp]),
+    "mirk_set_mesh_guess_device": (C.c_int, [Handle, C.c_int32, dp, C.c_void_p]),
+    "mirk_get_solution_device": (C.c_int, [Handle, C.c_void_p]),
+    "mirk_ensemble_set_inputs_device": (C.c_int, [Handle, C.c_void_p, C.c_void_p, C.c_int32]),
     "mirk_set_uniform_guess": (C.c_int, [Handle, C.c_double, C.c_double, C.c_double, dp]),
     "mirk_residual": (C.c_int, [Handle, dp, dp]),
     "mirk_jacobian_blocks": (C.c_int, [Handle, dp, dp, ip, dp, ip]),
@@ -86,11 +89,14 @@ SYMBOLS = {
     "mirk_measure_peaks": (C.c_int, [C.c_int32, dp, dp]),
     "mirk_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mirk_partition_attach": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p, C.c_char_p]),
+    "mirk_partition_p2p_export": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p]),
+    "mirk_partition_attach_p2p": (C.c_int, [Handle, C.c_int32, C.c_int32, C.c_void_p]),
     "mirk_ensemble_create": (C.c_int, [C.POINTER(EnsembleDesc), C.c_int64, C.POINTER(Handle)]),
     "mirk_ensemble_destroy": (C.c_int, [Handle]),
     "mirk_ensemble_set_inputs": (C.c_int, [Handle, dp, dp, C.c_int32]),
     "mirk_ensemble_run": (C.c_int, [Handle, fp]),
     "mirk_ensemble_get_results": (C.c_int, [Handle, ip, ip, ip, ip, dp, dp, dp]),
+    "mirk_ensemble_node_cap": (C.c_int, [Handle, ip]),
     "mirk_ensemble_get_trajectory": (C.c_int, [Handle, C.c_int64, ip, dp, dp]),
     "mirk_ensemble_solve": (C.c_int, [C.POINTER(EnsembleDesc), C.c_int64, dp, dp, C.c_int32, ip, ip, ip, dp]),
 }

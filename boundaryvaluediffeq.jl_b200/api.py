@@ -292,15 +292,25 @@ class MIRKCache:
         if callable(u0):
             nint = int(math.ceil((t1 - t0) / dt))
             mesh = mesh_uniform(t0, t1, nint)
-            y = np.stack([_arr(u0(p, t)) for t in mesh])
-            B.check(B.lib().mirk_set_mesh_guess(self._h, len(mesh), _d(mesh), _d(_arr(y))))
+            y = _arr(np.stack([_arr(u0(p, t)).ravel() for t in mesh]))
+            if y.shape[1] != self.n:
+                self.close()
+                raise ValueError(f"u0(p, t) returns {y.shape[1]} states, the device function expects {self.n}")
+            B.check(B.lib().mirk_set_mesh_guess(self._h, len(mesh), _d(mesh), _d(y)))
         elif u0.ndim == 1:
             if u0.size != self.n:
                 self.close()
                 raise ValueError(f"u0 has {u0.size} states, the device function expects {self.n}")
             B.check(B.lib().mirk_set_uniform_guess(self._h, t0, t1, float(dt), _d(u0)))
         else:
-            mesh = _arr(prob.mesh) if prob.mesh is not None else mesh_uniform(t0, t1, u0.shape[0] - 1)
+            # the C ABI copies n_mesh * n doubles from the host buffer: check the shapes before it does
+            if u0.ndim != 2 or u0.shape[1] != self.n or u0.shape[0] < 2:
+                self.close()
+                raise ValueError(f"a guess on a mesh must be an (N >= 2, {self.n}) array, got shape {u0.shape}")
+            mesh = _arr(prob.mesh).ravel() if prob.mesh is not None else mesh_uniform(t0, t1, u0.shape[0] - 1)
+            if len(mesh) != u0.shape[0]:
+                self.close()
+                raise ValueError(f"the guess has {u0.shape[0]} nodes, its mesh {len(mesh)}")
             B.check(B.lib().mirk_set_mesh_guess(self._h, len(mesh), _d(mesh), _d(u0)))
 
     def close(self):

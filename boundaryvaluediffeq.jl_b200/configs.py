@@ -11,6 +11,17 @@ from dataclasses import dataclass
 import numpy as np
 
 
+_MESH_PROVIDER = None
+
+
+def set_mesh_provider(fn) -> None:
+    """Use `fn(t0, t1, nint) -> ndarray` for the uniform meshes instead of the C ABI's host helper.  bench.py's
+    reference arm passes the oracle's twin (oracle.mesh_uniform, same correctly rounded values) so that the CPU
+    arm never maps libmirkb200.so."""
+    global _MESH_PROVIDER
+    _MESH_PROVIDER = fn
+
+
 @dataclass
 class Config:
     key: str            # C1..C5
@@ -32,7 +43,8 @@ class Config:
     def mesh(self) -> np.ndarray:
         # correctly rounded uniform mesh (Julia `range` is twice-precision): the C ABI's
         # host helper mirk_mesh_uniform (binary128; needs no GPU)
-        import ctypes as C
+        if _MESH_PROVIDER is not None:
+            return np.ascontiguousarray(_MESH_PROVIDER(float(self.tspan[0]), float(self.tspan[1]), int(self.nint)))
         from . import _lib as B
         m = np.zeros(self.nint + 1)
         B.check(B.lib().mirk_mesh_uniform(float(self.tspan[0]), float(self.tspan[1]), int(self.nint),

@@ -336,6 +336,128 @@ __global__ void k_part_unpack(int n, int G, int L, int La, const double* __restr
     }
     for (int q = tid; q < L; q += T) oresid[q] = q < La ? b0[2 * L * n + q] : bG[2 * L * n + q];
 }
+// ---- the same exchange over NVLink peer memory (no library collective) ---------------------------------
+// Every rank owns one exchange buffer `xbuf` (cudaMalloc + CUDA IPC, mapped by all peers):
+//     payload slots [2][G][P] doubles | norm slots [2][G][4] words | payload flags [2][G] | norm flags [2][G]
+// A rank PUSHES its packed relation straight into slot [parity][rank] of every peer's buffer (remote stores
+// through NVSwitch), fences system-wide and then stores the epoch into the peers' flag [parity][rank]; the
+// consumer spins on its OWN (local) flags, so waiting costs no fabric traffic.  The pack of the relation and the
+// all-gather are one kernel, the wait and the unpack into the interface system another; epochs live in device
+// memory, so both replay inside CUDA graphs.  Double buffering by epoch parity is enough: a peer can only be one
+// exchange ahead, because its next push waits on this rank's flag for the current one.
+constexpr int kMaxPeers = 16;
+struct XchgLayout {
+    int G;
+    size_t P;
+    __host__ __device__ size_t off_nslot() const { return (size_t)2 * G * P; }
+    __host__ __device__ size_t off_pflag() const { return off_nslot() + (size_t)2 * G * 4; }
+    __host__ __device__ size_t off_nflag() const { return off_pflag() + (size_t)2 * G; }
+    __host__ __device__ size_t total() const { return off_nflag() + (size_t)2 * G; }
+};
+struct XchgPeers {
+    double* buf[kMaxPeers];
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= epoch; gives up after ~2 s of SM clocks (a peer that died must not hang the device)
+__device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsigned long long epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > 4000000000ll) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// pack this segment's collapsed relation (+ the boundary blocks and rows it owns) and push it to every rank
+__global__ void __launch_bounds__(1024)
+k_part_push(int n, int L, int La, const double* __restrict__ relL, const double* __restrict__ relR,
+            const double* __restrict__ relr, const double* __restrict__ Bc, const double* __restrict__ resid,
+            size_t tail_off, XchgPeers peers, XchgLayout lay, int rank, const unsigned long long* __restrict__ epoch_ptr) {
+    const int nn = n * n, tid = threadIdx.x, T = blockDim.x;
+    const unsigned long long e = *epoch_ptr + 1ull;
+    const size_t slot = ((size_t)(e & 1ull) * lay.G + rank) * lay.P;
+    const int tot = (int)lay.P;
+    for (int i = tid; i < tot; i += T) {
+        double v;
+        if (i < nn) v = relL[i];
+        else if (i < 2 * nn) v = relR[i - nn];
+        else if (i < 2 * nn + n) v = relr[i - 2 * nn];
+        else if (i < 2 * nn + n + 2 * L * n) v = Bc[i - 2 * nn - n];
+        else {
+            const int q = i - 2 * nn - n - 2 * L * n;
+            v = q < La ? resid[q] : resid[tail_off + (q - La)];
+        }
+        for (int r = 0; r < lay.G; r++) peers.buf[r][slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < lay.G)
+        st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[tid] + lay.off_pflag()) + (e & 1ull) * lay.G + rank, e);
+}
+// wait for every rank's relation of this epoch, then unpack into the interface system (as k_part_unpack)
+__global__ void __launch_bounds__(1024)
+k_part_wait_unpack(int n, int L, int La, double* __restrict__ xbuf, XchgLayout lay, double* __restrict__ oL,
+                   double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
+                   double* __restrict__ oresid, unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
+    const int nn = n * n, tid = threadIdx.x, T = blockDim.x, G = lay.G;
+    const unsigned long long e = *epoch_ptr + 1ull;
+    if (tid < G) {
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xbuf + lay.off_pflag()) + (e & 1ull) * G + tid;
+        if (!xchg_wait(fl, e)) atomicExch(status, 3);
+    }
+    __syncthreads();
+    const double* recv = xbuf + (size_t)(e & 1ull) * G * lay.P;
+    const size_t P = lay.P;
+    for (int i = tid; i < G * nn; i += T) {
+        const int g = i / nn, k = i % nn;
+        oL[i] = __ldcg(recv + (size_t)g * P + k);  // peer-written data: read through L2
+        oR[i] = __ldcg(recv + (size_t)g * P + nn + k);
+    }
+    for (int i = tid; i < G * n; i += T) orr[i] = __ldcg(recv + (size_t)(i / n) * P + 2 * nn + i % n);
+    const double* b0 = recv + 2 * nn + n;
+    const double* bG = recv + (size_t)(G - 1) * P + 2 * nn + n;
+    for (int i = tid; i < L * n; i += T) {
+        const int q = i / n;
+        oBc[i] = q < La ? __ldcg(b0 + i) : 0.0;
+        oBc[L * n + i] = q < La ? 0.0 : __ldcg(bG + L * n + i);
+    }
+    for (int q = tid; q < L; q += T) oresid[q] = q < La ? __ldcg(b0 + 2 * L * n + q) : __ldcg(bG + 2 * L * n + q);
+    __syncthreads();
+    if (tid == 0) *epoch_ptr = e;
+}
+// all-reduce(max) of words[0..3) (|F|_inf bits, defect bits, status) over the ranks: push, wait, reduce — one warp
+__global__ void __launch_bounds__(32)
+k_words_allmax(unsigned long long* __restrict__ words, double* __restrict__ xbuf, XchgPeers peers, XchgLayout lay, int rank,
+               unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
+    const int lane = threadIdx.x, G = lay.G;
+    const unsigned long long e = *epoch_ptr + 1ull, par = e & 1ull;
+    unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;
+    if (lane < G) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(peers.buf[lane] + lay.off_nslot()) + (par * G + rank) * 4;
+        dst[0] = words[0]; dst[1] = words[1]; dst[2] = words[2];
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[lane] + lay.off_nflag()) + par * G + rank, e);
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xbuf + lay.off_nflag()) + par * G + lane;
+        if (!xchg_wait(fl, e)) atomicExch(status, 3);
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xbuf + lay.off_nslot()) + (par * G + lane) * 4;
+        w0 = __ldcg(src); w1 = __ldcg(src + 1); w2 = __ldcg(src + 2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, w0, o), b = __shfl_xor_sync(0xffffffffu, w1, o),
+                                 c = __shfl_xor_sync(0xffffffffu, w2, o);
+        w0 = a > w0 ? a : w0; w1 = b > w1 ? b : w1; w2 = c > w2 ? c : w2;
+    }
+    if (lane == 0) { words[0] = w0; words[1] = w1; words[2] = w2; *epoch_ptr = e; }
+}
+
 // |bc rows|_inf of the rows this rank owns (a-rows on rank 0, b-rows on the last rank) into norm_bits
 __global__ void k_bc_norm_masked(int L, int La, const double* __restrict__ resid, size_t tail_off, int own_a, int own_b,
                                  unsigned long long* __restrict__ norm_bits) {

@@ -1,7 +1,7 @@
 // abd_mma32.cuh — the n = 32 merge of the ABD reduction in DMMA fragment layout, four warps per merge.
-// STATUS: validated against k_reduce_pair<32> on synthetic relations (experiments/exp_mma32.cu, B200: factors equal
-// to 7e-15, 1.8x faster at 100 groups, 1.25x at 2000 groups — profiles/r01_s3_final/exp_mma32.log) but NOT yet
-// run through the library's GPU tests: it is compiled into the library only with -DMIRK_ABD_MMA32 (off by default).
+// The library's default n = 32 reduction (launch_pair_reduce; MIRK_ABD_MMA32=0 selects k_reduce_pair for A/B runs).
+// Against k_reduce_pair<32> on synthetic relations (experiments/exp_mma32.cu, B200): factors equal to 7e-15, 1.8x
+// faster at 100 groups, 1.25x at 2000 groups (profiles/r01_s3_final/exp_mma32.log); the C5 golden tests run through it.
 //
 // Extends abd_mma.cuh (n = 16, one warp): the 64 x 96 matrix [E | A | B] of a merge is 8 x 12 tiles of 8 x 8; warp w
 // owns tile rows 2w, 2w+1 (rows 16w .. 16w+15) in the C-fragment layout of mma.sync.m8n8k4.f64 (48 doubles per lane,

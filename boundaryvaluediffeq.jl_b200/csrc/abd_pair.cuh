@@ -170,9 +170,7 @@ k_backsub_pair(const int* __restrict__ nodes, const int* __restrict__ gs, const 
 }
 
 }  // namespace mirk
-#if defined(MIRK_ABD_MMA32)
-#include "abd_mma32.cuh"  // four-warp DMMA-fragment merge (validated in experiments/exp_mma32.cu; off by default)
-#endif
+#include "abd_mma32.cuh"  // four-warp DMMA-fragment merge: the default n = 32 reduction (MIRK_ABD_MMA32=0 selects k_reduce_pair)
 namespace mirk {
 
 inline bool pair_reduce_supported(int n) { return n == 32; }
@@ -180,11 +178,11 @@ inline bool pair_reduce_supported(int n) { return n == 32; }
 inline void launch_pair_reduce(cudaStream_t st, int G, const double* inL, const double* inR, const double* inr,
                                double* outL, double* outR, double* outr, const int* nodes, const int* gs, double* TL,
                                double* TR, double* rt, int* status) {
-#if defined(MIRK_ABD_MMA32)
-    k_reduce_mma32<<<G, 128, 0, st>>>(inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, status);
-#else
-    k_reduce_pair<32><<<G, 64, 0, st>>>(inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, status);
-#endif
+    // default: the four-warp DMMA-fragment merge (abd_mma32.cuh); MIRK_ABD_MMA32=0 keeps the two-warp
+    // thread-per-row kernel for A/B measurements (same pivots, relation and factor formats)
+    static const bool use_mma = !(getenv("MIRK_ABD_MMA32") && atoi(getenv("MIRK_ABD_MMA32")) == 0);
+    if (use_mma) k_reduce_mma32<<<G, 128, 0, st>>>(inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, status);
+    else k_reduce_pair<32><<<G, 64, 0, st>>>(inL, inR, inr, outL, outR, outr, nodes, gs, TL, TR, rt, status);
 }
 inline void launch_pair_backsub(cudaStream_t st, int G, const int* nodes, const int* gs, const double* TL,
                                 const double* TR, const double* rt, double* delta) {

@@ -126,6 +126,7 @@ template <class T> static void dfree(T*& p) {
 }
 
 static const int kMaxLev = 40;
+static const int kMaxOuter = 1000;  // safety net of the adaptive outer loop, see mirk_solve
 
 struct Plan {
     int nlev = 0;
@@ -189,12 +190,22 @@ struct mirk_solver_s {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     double *sendbuf = nullptr, *recvbuf = nullptr;
+    // peer-memory exchange (mirk_partition_p2p_*): this rank's exchange buffer, every rank's mapping of it, and the
+    // two device-resident epoch counters (payload exchange, words all-reduce)
+    bool p2p = false;
+    double* xbuf = nullptr;
+    XchgPeers peers;
+    XchgLayout xlay;
+    unsigned long long* xepoch = nullptr;
     // interface system on the nranks+1 segment end nodes
     Plan iplan;
     double *if_L = nullptr, *if_R = nullptr, *if_r = nullptr, *if_TL = nullptr, *if_TR = nullptr, *if_rt = nullptr,
            *if_delta = nullptr, *if_Bc = nullptr, *if_resid = nullptr;
     int *if_bc_nodes = nullptr, *if_m = nullptr;
     bool jac_valid = false, resid_valid = false;
+    // lazy zeroing of the stage arrays after a guess upload: Kd is fully rewritten by the first residual pass (only a
+    // reader that runs before any residual needs the zeros), Ki only has to be cleared if something wrote it
+    bool kd_stale = true, ki_dirty = true;
     double last_resid_norm = NAN;
 };
 
@@ -397,11 +408,12 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
 static int launch_check(const char* what);
 
 // Run `body` (stream-ordered launches only, no host synchronisation) directly the first times, then capture it
-// into a CUDA graph and replay that.  MIRK_NO_GRAPH=1 keeps direct launches; mesh-partitioned handles (NCCL on
-// the stream) and any capture failure fall back to direct launches too.
+// into a CUDA graph and replay that.  MIRK_NO_GRAPH=1 keeps direct launches; mesh-partitioned handles that exchange
+// through NCCL and any capture failure fall back to direct launches too (the peer-memory exchange is plain kernels
+// with device-resident epochs, so it replays like everything else).
 template <class F> static int run_graphed(mirk_solver_s* S, int key, F&& body) {
     static const bool disabled = getenv("MIRK_NO_GRAPH") && atoi(getenv("MIRK_NO_GRAPH")) != 0;
-    if (disabled || !S->use_graph || S->part) return body();
+    if (disabled || !S->use_graph || (S->part && !S->p2p)) return body();
     GraphSlot& g = S->gslot[key];
     if (g.epoch != S->graph_epoch) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -451,12 +463,21 @@ static int eval_bc(mirk_solver_s* S, int want_jac, bool into_norm) {
     unsigned long long* nb = (into_norm && !S->part) ? S->words : S->words + 3;
     S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev, nb, want_jac);
     S->launches++;
+    if (S->ops->problem_type == 0) S->ki_dirty = true;  // interior boundary times fill their interval's Ki
     if (S->part && into_norm) {
         const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * S->n;
         k_bc_norm_masked<<<1, 128, 0, S->st>>>(S->L, S->La, S->resid, tail_off, S->rank == 0, S->rank == S->nranks - 1,
                                                S->words);
         S->launches++;
-        CKN(g_nccl.AllReduce(S->words, S->words, 1, ncclUint64, ncclMax, S->comm, S->st));
+        // |F|_inf, the defect word and the singular-pivot status word travel together, so every rank sees the same
+        // values and takes the same exit from the Newton loop (a rank-local failure would otherwise leave the
+        // other ranks waiting in the next collective)
+        if (S->p2p) {
+            k_words_allmax<<<1, 32, 0, S->st>>>(S->words, S->xbuf, S->peers, S->xlay, S->rank, S->xepoch + 1, (int*)(S->words + 2));
+            S->launches++;
+        } else {
+            CKN(g_nccl.AllReduce(S->words, S->words, 3, ncclUint64, ncclMax, S->comm, S->st));
+        }
     }
     return MIRK_OK;
 }
@@ -468,6 +489,7 @@ static int eval_residual(mirk_solver_s* S) {
     S->launches++;
     CKS(eval_bc(S, 0, true));
     S->resid_valid = true;
+    S->kd_stale = false;
     return launch_check("residual");
 }
 
@@ -494,6 +516,7 @@ static int eval_resjac(mirk_solver_s* S) {
         return launch_check("resjac");
     }));
     S->resid_valid = S->jac_valid = true;
+    S->kd_stale = false;
     return MIRK_OK;
 }
 
@@ -584,10 +607,18 @@ static int part_exchange_and_close(mirk_solver_s* S) {
     Plan& P = S->plan;
     const int n = S->n, G = S->nranks;
     const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * n, pay = part_payload_doubles(n, S->L);
-    k_part_pack<<<8, 256, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
-                                      tail_off, S->sendbuf);
-    CKN(g_nccl.AllGather(S->sendbuf, S->recvbuf, pay, ncclDouble, S->comm, S->st));
-    k_part_unpack<<<8, 256, 0, S->st>>>(n, G, S->L, S->La, S->recvbuf, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid);
+    if (S->p2p) {
+        // pack + all-gather as ONE kernel pushing into every peer's exchange buffer over NVLink; wait + unpack the other
+        k_part_push<<<1, 1024, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
+                                           tail_off, S->peers, S->xlay, S->rank, S->xepoch);
+        k_part_wait_unpack<<<1, 1024, 0, S->st>>>(n, S->L, S->La, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc,
+                                                  S->if_resid, S->xepoch, (int*)(S->words + 2));
+    } else {
+        k_part_pack<<<8, 256, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
+                                          tail_off, S->sendbuf);
+        CKN(g_nccl.AllGather(S->sendbuf, S->recvbuf, pay, ncclDouble, S->comm, S->st));
+        k_part_unpack<<<8, 256, 0, S->st>>>(n, G, S->L, S->La, S->recvbuf, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid);
+    }
     S->launches += 2;
     SolveCtx I{&S->iplan, S->if_TL, S->if_TR, S->if_rt, S->if_delta, S->if_Bc, S->if_bc_nodes, S->if_m, S->if_resid,
                (size_t)S->La, false};
@@ -757,6 +788,7 @@ static int eval_defect(mirk_solver_s* S, double* defect_norm) {
     CK(cudaMemsetAsync(S->words + 1, 0, sizeof(unsigned long long), S->st));
     S->ops->defect(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->errors, S->est, S->words + 1);
     S->launches++;
+    S->ki_dirty = true;
     CKS(launch_check("defect"));
     CKS(read_words(S));
     *defect_norm = bits_to_double(S->h_words[1]);
@@ -907,20 +939,9 @@ int mirk_nccl_unique_id(void* id128, const char* libnccl_path) {
     return MIRK_OK;
 }
 
-int mirk_partition_attach(mirk_handle S, int32_t rank, int32_t nranks, const void* id128, const char* libnccl_path) {
-    if (!S || !id128) return fail(MIRK_ERR_ARG, "NULL argument");
-    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MIRK_ERR_ARG, "bad rank / nranks");
-    if (S->ops->problem_type != 1) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning needs a TwoPointBVProblem");
-    if (S->desc.adaptive) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning runs on a fixed mesh (adaptive = false)");
-    if (S->part) return fail(MIRK_ERR_STATE, "already attached");
-    CKS(load_nccl(libnccl_path));
-    CK(cudaSetDevice(S->desc.device));
-    ncclUniqueId id;
-    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
-    CKN(g_nccl.CommInitRank(&S->comm, nranks, id, rank));
-    const size_t pay = part_payload_doubles(S->n, S->L), nn = (size_t)S->n * S->n, Q = (size_t)nranks + 1;
-    CK(dalloc(&S->sendbuf, pay));
-    CK(dalloc(&S->recvbuf, pay * nranks));
+// interface system on the nranks + 1 segment end nodes (shared by both exchange flavours)
+static int part_setup_interface(mirk_solver_s* S, int rank, int nranks) {
+    const size_t nn = (size_t)S->n * S->n, Q = (size_t)nranks + 1;
     CK(dalloc(&S->if_L, nn * nranks)); CK(dalloc(&S->if_R, nn * nranks)); CK(dalloc(&S->if_r, (size_t)S->n * nranks));
     CK(dalloc(&S->if_TL, nn * Q)); CK(dalloc(&S->if_TR, nn * Q)); CK(dalloc(&S->if_rt, (size_t)S->n * Q));
     CK(dalloc(&S->if_delta, (size_t)S->n * Q));
@@ -935,7 +956,66 @@ int mirk_partition_attach(mirk_handle S, int32_t rank, int32_t nranks, const voi
     CKS(build_plan_for(S, S->iplan, nranks + 1, std::vector<int>{0, nranks}, S->if_L, S->if_R, S->if_r));
     S->part = true;
     S->jac_valid = S->resid_valid = false;
+    S->graph_epoch++;
     return MIRK_OK;
+}
+static int part_check(mirk_solver_s* S, int rank, int nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MIRK_ERR_ARG, "bad rank / nranks");
+    if (S->ops->problem_type != 1) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning needs a TwoPointBVProblem");
+    if (S->desc.adaptive) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning runs on a fixed mesh (adaptive = false)");
+    if (S->part) return fail(MIRK_ERR_STATE, "already attached");
+    return MIRK_OK;
+}
+
+int mirk_partition_attach(mirk_handle S, int32_t rank, int32_t nranks, const void* id128, const char* libnccl_path) {
+    if (!S || !id128) return fail(MIRK_ERR_ARG, "NULL argument");
+    CKS(part_check(S, rank, nranks));
+    CKS(load_nccl(libnccl_path));
+    CK(cudaSetDevice(S->desc.device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    CKN(g_nccl.CommInitRank(&S->comm, nranks, id, rank));
+    const size_t pay = part_payload_doubles(S->n, S->L);
+    CK(dalloc(&S->sendbuf, pay));
+    CK(dalloc(&S->recvbuf, pay * nranks));
+    return part_setup_interface(S, rank, nranks);
+}
+
+int mirk_partition_p2p_export(mirk_handle S, int32_t rank, int32_t nranks, void* ipc64) {
+    if (!S || !ipc64) return fail(MIRK_ERR_ARG, "NULL argument");
+    CKS(part_check(S, rank, nranks));
+    if (nranks > kMaxPeers) return fail(MIRK_ERR_UNSUPPORTED, "peer-memory exchange supports at most 16 ranks");
+    if (S->xbuf) return fail(MIRK_ERR_STATE, "exchange buffer already exported");
+    CK(cudaSetDevice(S->desc.device));
+    S->xlay = XchgLayout{nranks, part_payload_doubles(S->n, S->L)};
+    CK(dalloc(&S->xbuf, S->xlay.total()));
+    CK(cudaMemset(S->xbuf, 0, S->xlay.total() * sizeof(double)));
+    CK(dalloc(&S->xepoch, 2));
+    CK(cudaMemset(S->xepoch, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaDeviceSynchronize());  // flags are zero before any peer can learn the handle
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, S->xbuf));
+    memcpy(ipc64, &hnd, sizeof(hnd));
+    return MIRK_OK;
+}
+
+int mirk_partition_attach_p2p(mirk_handle S, int32_t rank, int32_t nranks, const void* ipc_handles) {
+    if (!S || !ipc_handles) return fail(MIRK_ERR_ARG, "NULL argument");
+    CKS(part_check(S, rank, nranks));
+    if (!S->xbuf || S->xlay.G != nranks) return fail(MIRK_ERR_STATE, "call mirk_partition_p2p_export first (same nranks)");
+    CK(cudaSetDevice(S->desc.device));
+    for (int r = 0; r < kMaxPeers; r++) S->peers.buf[r] = nullptr;
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { S->peers.buf[r] = S->xbuf; continue; }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const char*)ipc_handles + (size_t)r * sizeof(hnd), sizeof(hnd));
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        S->peers.buf[r] = (double*)ptr;
+    }
+    S->p2p = true;
+    return part_setup_interface(S, rank, nranks);
 }
 
 int mirk_mesh_uniform(double t0, double t1, int32_t nint, double* mesh) {
@@ -958,6 +1038,11 @@ int mirk_destroy(mirk_handle S) {
     dfree(S->iplan.d_int); dfree(S->iplan.d_rel);
     for (GraphSlot& g : S->gslot) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
+    if (S->p2p)
+        for (int r = 0; r < S->nranks; r++)
+            if (r != S->rank && S->peers.buf[r]) cudaIpcCloseMemHandle(S->peers.buf[r]);
+    dfree(S->xbuf);
+    dfree(S->xepoch);
     if (S->h_words) cudaFreeHost(S->h_words);
     if (S->st) cudaStreamDestroy(S->st);
     delete S;
@@ -1051,12 +1136,61 @@ int mirk_set_mesh_guess(mirk_handle S, int32_t n_mesh, const double* mesh, const
     CK(cudaMemcpyAsync(S->mesh, mesh, sizeof(double) * n_mesh, cudaMemcpyHostToDevice, S->st));
     CK(cudaMemcpyAsync(S->y, y, yb, cudaMemcpyHostToDevice, S->st));
     CK(cudaMemcpyAsync(S->y_guess, S->y, yb, cudaMemcpyDeviceToDevice, S->st));
-    CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->s * S->n, S->st));
-    CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->si * S->n, S->st));
+    // a fresh cache has all-zero stage arrays (MIRK/mirk.jl:79-109).  Kd is zeroed lazily (kd_stale: the first
+    // residual pass rewrites all of it), Ki only when something has written it since it was last cleared
+    S->kd_stale = true;
+    if (!same_shape || S->ki_dirty) {
+        CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->si * S->n, S->st));
+        S->ki_dirty = false;
+    }
     CK(cudaStreamSynchronize(S->st));
     S->have_guess = true;
     S->jac_valid = S->resid_valid = false;
     if (!same_shape) { S->plan.valid = false; S->graph_epoch++; }
+    return MIRK_OK;
+}
+
+// same as mirk_set_mesh_guess with the guess already resident on this handle's device (a CuArray on the Julia
+// side): device-to-device copy on the solver's stream, no host round trip.  The mesh stays a host array (the host
+// planner needs it).
+int mirk_set_mesh_guess_device(mirk_handle S, int32_t n_mesh, const double* mesh, const double* d_y) {
+    if (!S || !mesh || !d_y) return fail(MIRK_ERR_ARG, "NULL argument");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_y) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(MIRK_ERR_ARG, "d_y is not a device pointer");
+    }
+    if (n_mesh < 2) return fail(MIRK_ERR_ARG, "a mesh needs at least two nodes");
+    for (int i = 1; i < n_mesh; i++)
+        if (!(mesh[i] > mesh[i - 1])) return fail(MIRK_ERR_ARG, "mesh must be strictly increasing");
+    CK(cudaSetDevice(S->desc.device));
+    const int cap = S->desc.adaptive ? std::max(n_mesh, S->desc.max_num_subintervals + 1) : n_mesh;
+    CKS(ensure_capacity(S, cap));
+    const bool same_shape = S->plan.valid && S->N == n_mesh;
+    S->N = n_mesh;
+    S->h_mesh.assign(mesh, mesh + n_mesh);
+    const size_t yb = sizeof(double) * (size_t)n_mesh * S->n;
+    CK(cudaMemcpyAsync(S->mesh, mesh, sizeof(double) * n_mesh, cudaMemcpyHostToDevice, S->st));
+    CK(cudaMemcpyAsync(S->y, d_y, yb, cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaMemcpyAsync(S->y_guess, S->y, yb, cudaMemcpyDeviceToDevice, S->st));
+    S->kd_stale = true;
+    if (!same_shape || S->ki_dirty) {
+        CK(cudaMemsetAsync(S->Ki, 0, sizeof(double) * (size_t)(n_mesh - 1) * S->si * S->n, S->st));
+        S->ki_dirty = false;
+    }
+    CK(cudaStreamSynchronize(S->st));
+    S->have_guess = true;
+    S->jac_valid = S->resid_valid = false;
+    if (!same_shape) { S->plan.valid = false; S->graph_epoch++; }
+    return MIRK_OK;
+}
+// sol.u into a device buffer (N x n doubles on this handle's device)
+int mirk_get_solution_device(mirk_handle S, double* d_y) {
+    if (!S || !d_y) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (!S->have_guess) return fail(MIRK_ERR_STATE, "no mesh/guess set");
+    CK(cudaSetDevice(S->desc.device));
+    CK(cudaMemcpyAsync(d_y, S->y, sizeof(double) * (size_t)S->N * S->n, cudaMemcpyDeviceToDevice, S->st));
+    CK(cudaStreamSynchronize(S->st));
     return MIRK_OK;
 }
 
@@ -1170,7 +1304,10 @@ int mirk_solve(mirk_handle S, mirk_result* out) {
     const double abstol = S->desc.abstol;
     int info = MIRK_RET_SUCCESS;
     double error_norm = 2.0 * abstol, resid_norm = 0.0;
-    const int max_outer = 100;
+    // the reference's loop has no cap (MIRK/mirk.jl:296-322): it ends by convergence or by a mesh that would exceed
+    // max_num_subintervals.  kMaxOuter is a safety net against a non-terminating refinement cycle only (same value
+    // in the oracle, orc_options_default); reaching it reports MaxIters.
+    const int max_outer = kMaxOuter;
     do {
         int iters = 0, nret = 0;
         CKS(newton_solve(S, &iters, &resid_norm, &nret));
@@ -1189,6 +1326,7 @@ int mirk_solve(mirk_handle S, mirk_result* out) {
             if (S->ops->problem_type == 0) {
                 S->ops->interp_setup(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki);
                 S->launches++;
+                S->ki_dirty = true;
             }
             break;
         }
@@ -1234,8 +1372,17 @@ int mirk_get_solution(mirk_handle S, double* mesh, double* y) {
     return MIRK_OK;
 }
 
+static int zero_stale_stages(mirk_solver_s* S) {
+    if (S->kd_stale) {
+        CK(cudaMemsetAsync(S->Kd, 0, sizeof(double) * (size_t)(S->N - 1) * S->s * S->n, S->st));
+        S->kd_stale = false;
+    }
+    return MIRK_OK;
+}
+
 int mirk_get_stages(mirk_handle S, double* Kd, double* Ki) {
     NEED_GUESS(S);
+    CKS(zero_stale_stages(S));
     const size_t per = (size_t)(S->N - 1) * S->n;
     if (Kd) CK(cudaMemcpyAsync(Kd, S->Kd, sizeof(double) * per * S->s, cudaMemcpyDeviceToHost, S->st));
     if (Ki) CK(cudaMemcpyAsync(Ki, S->Ki, sizeof(double) * per * S->si, cudaMemcpyDeviceToHost, S->st));
@@ -1257,6 +1404,7 @@ int mirk_interp(mirk_handle S, const double* t, int32_t m, int32_t deriv, double
     if (!t || !out || m < 0) return fail(MIRK_ERR_ARG, "bad argument");
     if (deriv != 0 && deriv != 1) return fail(MIRK_ERR_ARG, "deriv must be 0 or 1");
     if (m == 0) return MIRK_OK;
+    CKS(zero_stale_stages(S));
     if ((size_t)m * (S->n + 1) > S->tbuf_cap) {
         dfree(S->tbuf);
         CK(dalloc(&S->tbuf, (size_t)m * (S->n + 1)));
@@ -1515,6 +1663,20 @@ int mirk_ensemble_set_inputs(mirk_ensemble_handle E, const double* params, const
     return MIRK_OK;
 }
 
+// params / u0 already resident on the handle's device (CuArrays on the Julia side): device-to-device copies
+int mirk_ensemble_set_inputs_device(mirk_ensemble_handle E, const double* d_params, const double* d_u0, int32_t u0_per_traj) {
+    if (!E || !d_u0 || (E->ops->np > 0 && !d_params)) return fail(MIRK_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(E->desc.device));
+    if (E->ops->np > 0)
+        CK(cudaMemcpyAsync(E->params, d_params, sizeof(double) * (size_t)E->ntraj * E->ops->np, cudaMemcpyDeviceToDevice, E->st));
+    CK(cudaMemcpyAsync(E->u0, d_u0, sizeof(double) * (size_t)(u0_per_traj ? E->ntraj : 1) * E->ops->n,
+                       cudaMemcpyDeviceToDevice, E->st));
+    CK(cudaStreamSynchronize(E->st));
+    E->u0_per_traj = u0_per_traj ? 1 : 0;
+    E->have_inputs = true;
+    return MIRK_OK;
+}
+
 int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
     if (!E) return fail(MIRK_ERR_ARG, "NULL handle");
     if (!E->have_inputs) return fail(MIRK_ERR_STATE, "no inputs set");
@@ -1525,7 +1687,7 @@ int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
     a.abstol = E->desc.abstol; a.defect_threshold = E->desc.defect_threshold;
     a.adaptive = E->desc.adaptive; a.max_sub = E->desc.max_num_subintervals;
     a.maxiters = E->desc.maxiters < 0 ? 0 : E->desc.maxiters; a.reinterp_inplace = E->desc.reinterp_inplace;
-    a.max_outer = 100;
+    a.max_outer = kMaxOuter;
     a.work = E->work;
     a.retcode = E->retcode; a.n_mesh = E->n_mesh; a.newton_iters = E->newton_iters; a.outer_iters = E->outer_iters;
     a.resid_norm = E->resid_norm; a.defect_norm = E->defect_norm;
@@ -1562,6 +1724,12 @@ int mirk_ensemble_get_results(mirk_ensemble_handle E, int32_t* retcodes, int32_t
     if (defect_norm) CK(cudaMemcpyAsync(defect_norm, E->defect_norm, sizeof(double) * nt, cudaMemcpyDeviceToHost, E->st));
     if (y_first) CK(cudaMemcpyAsync(y_first, E->y_first, sizeof(double) * nt * E->ops->n, cudaMemcpyDeviceToHost, E->st));
     CK(cudaStreamSynchronize(E->st));
+    return MIRK_OK;
+}
+
+int mirk_ensemble_node_cap(mirk_ensemble_handle E, int32_t* node_cap) {
+    if (!E || !node_cap) return fail(MIRK_ERR_ARG, "NULL argument");
+    *node_cap = E->NC;
     return MIRK_OK;
 }
 

@@ -147,20 +147,25 @@ def solve_ensemble(ens: EnsembleProblem, alg: _AbstractMIRK, ensemblealg, trajec
         import os
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
     nk = dict(nlsolve_kwargs or {})
-    h = EnsembleHandle(ens.prob, alg, max(count, 1), dt, abstol=nk.get("abstol", abstol), adaptive=adaptive,
-                       defect_threshold=(controller.defect_threshold if controller is not None else 0.1),
-                       maxiters=nk.get("maxiters", 1000), device=device, node_cap=node_cap)
-    sl = slice(first, first + max(count, 1))
-    h.set_inputs(params[sl], u0[sl] if per_traj else u0, per_traj)
-    h.run()
-    res = h.results()
-    if count == 0:
-        res = {k: v[:0] for k, v in res.items()}
+    n = ens.prob.f.info.n
     u = t = None
-    if keep_solutions:
-        pairs = [h.trajectory(i) for i in range(count)]
-        t, u = [a for a, _ in pairs], [b for _, b in pairs]
-    h.close()
+    if count == 0:
+        # more ranks than trajectories: this rank holds nothing and creates no handle, but still joins the gather
+        res = {"retcodes": np.zeros(0, dtype=np.int32), "n_mesh": np.zeros(0, dtype=np.int32),
+               "newton_iters": np.zeros(0, dtype=np.int32), "outer_iters": np.zeros(0, dtype=np.int32),
+               "resid_norm": np.zeros(0), "defect_norm": np.zeros(0), "y_first": np.zeros((0, n))}
+    else:
+        h = EnsembleHandle(ens.prob, alg, count, dt, abstol=nk.get("abstol", abstol), adaptive=adaptive,
+                           defect_threshold=(controller.defect_threshold if controller is not None else 0.1),
+                           maxiters=nk.get("maxiters", 1000), device=device, node_cap=node_cap)
+        sl = slice(first, first + count)
+        h.set_inputs(params[sl], u0[sl] if per_traj else u0, per_traj)
+        h.run()
+        res = h.results()
+        if keep_solutions:
+            pairs = [h.trajectory(i) for i in range(count)]
+            t, u = [a for a, _ in pairs], [b for _, b in pairs]
+        h.close()
     if gather and world > 1:
         counts = [c for _, c in parts]
         res = {k: gather_outcomes(v, counts) for k, v in res.items()}

@@ -59,9 +59,25 @@ def _share_unique_id(group=None) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def init_partitioned(prob: BVProblem, alg: _AbstractMIRK, group=None, device: Optional[int] = None, **kw):
+def _gather_ipc_handles(mine: bytes, group=None) -> bytes:
+    """all-gather of the 64-byte CUDA IPC handles, rank order"""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).clone().to(dev)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(outs, t, group=group)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs)
+
+
+def init_partitioned(prob: BVProblem, alg: _AbstractMIRK, group=None, device: Optional[int] = None,
+                     exchange: Optional[str] = None, **kw):
     """Collective.  `prob.u0` is the full (N, n) guess and `prob.mesh` the full mesh (every rank passes the
-    same arrays); each rank keeps its segment on its GPU.  Returns (cache, (lo, hi))."""
+    same arrays); each rank keeps its segment on its GPU.  Returns (cache, (lo, hi)).
+
+    exchange = "p2p" (default; MIRK_PART_XCHG overrides): the reduced interface relations travel by remote stores
+    into peer memory from inside the pack kernel (CUDA IPC over NVLink, whole step graph-replayed);
+    "nccl": one ncclAllGather + one ncclAllReduce per Newton step on the solver's stream."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if prob.f.info.problem_type != 1:
@@ -74,10 +90,20 @@ def init_partitioned(prob: BVProblem, alg: _AbstractMIRK, group=None, device: Op
     kw = dict(kw)
     kw["adaptive"] = False
     cache = MIRKCache(local, alg, device=device, **kw)
-    uid = _share_unique_id(group)
-    path = default_nccl_path()
-    B.check(B.lib().mirk_partition_attach(cache._h, rank, world, C.cast(C.c_char_p(uid), C.c_void_p),
-                                          path.encode() if path else None))
+    exchange = exchange or os.environ.get("MIRK_PART_XCHG", "p2p")
+    if exchange not in ("p2p", "nccl"):
+        raise ValueError("exchange must be 'p2p' or 'nccl'")
+    if exchange == "p2p":
+        mine = (C.c_char * 64)()
+        B.check(B.lib().mirk_partition_p2p_export(cache._h, rank, world, C.cast(mine, C.c_void_p)))
+        allh = _gather_ipc_handles(bytes(mine), group)
+        B.check(B.lib().mirk_partition_attach_p2p(cache._h, rank, world, C.cast(C.c_char_p(allh), C.c_void_p)))
+    else:
+        uid = _share_unique_id(group)
+        path = default_nccl_path()
+        B.check(B.lib().mirk_partition_attach(cache._h, rank, world, C.cast(C.c_char_p(uid), C.c_void_p),
+                                              path.encode() if path else None))
+    cache.exchange = exchange
     return cache, (lo, hi)
 
 

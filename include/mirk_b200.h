@@ -99,6 +99,9 @@ int mirk_destroy(mirk_handle h);
 int mirk_set_params(mirk_handle h, const double* params, int32_t n_params);
 /* mesh + initial guess: __extract_mesh / __initial_guess_on_mesh (CORE/utils.jl:694,750-773) */
 int mirk_set_mesh_guess(mirk_handle h, int32_t n_mesh, const double* mesh, const double* y);
+/* the same with the guess already on the handle's device (a CuArray on the Julia side; ext/ CUDA extension): no
+ * host round trip for y; the mesh stays a host array */
+int mirk_set_mesh_guess_device(mirk_handle h, int32_t n_mesh, const double* mesh, const double* d_y);
 /* uniform mesh of cld(t1 - t0, dt) intervals with u0 copied to every node (CORE/utils.jl:349-363,766-769) */
 int mirk_set_uniform_guess(mirk_handle h, double t0, double t1, double dt, const double* u0);
 
@@ -128,6 +131,7 @@ int mirk_solve(mirk_handle h, mirk_result* result);
 /* -- solution access: sol.t, sol.u, sol(t), sol(t, Val{1}) (MIRK/interpolation.jl:17-204) -------- */
 int mirk_get_mesh_size(mirk_handle h, int32_t* n_mesh);
 int mirk_get_solution(mirk_handle h, double* mesh, double* y);
+int mirk_get_solution_device(mirk_handle h, double* d_y); /* sol.u into a device buffer [n_mesh][n] */
 int mirk_get_stages(mirk_handle h, double* Kd, double* Ki);
 int mirk_get_residual(mirk_handle h, double* resid);
 int mirk_interp(mirk_handle h, const double* t, int32_t m, int32_t deriv, double* out);
@@ -152,6 +156,16 @@ int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
  *    NCCL is dlopen'ed on first use (libnccl_path or the default soname), never at link time. */
 int mirk_nccl_unique_id(void* id128 /* 128 bytes */, const char* libnccl_path);
 int mirk_partition_attach(mirk_handle h, int32_t rank, int32_t nranks, const void* id128, const char* libnccl_path);
+/*    The same exchange over NVLink peer memory, without a library collective (the default of the host layer):
+ *    every rank allocates an exchange buffer and exports its CUDA IPC handle (64 bytes); the caller gathers the
+ *    handles of all ranks (rank order) by any means and attaches.  Per Newton step each rank then PUSHES its packed
+ *    relation into every peer's buffer from inside the pack kernel and spins on local flags (k_part_push /
+ *    k_part_wait_unpack / k_words_allmax in csrc/abd.cuh); these are plain kernels with device-resident epochs, so the
+ *    whole partitioned step replays as a CUDA graph.  All ranks must make the same sequence of collective calls;
+ *    a rank that waits longer than ~2 s for a peer gives up and reports MIRK_RET_FAILURE.  Ranks must be processes
+ *    on one node whose GPUs have peer access (NVLink / NVSwitch). */
+int mirk_partition_p2p_export(mirk_handle h, int32_t rank, int32_t nranks, void* ipc_handle64 /* 64 bytes out */);
+int mirk_partition_attach_p2p(mirk_handle h, int32_t rank, int32_t nranks, const void* ipc_handles /* nranks x 64 bytes */);
 
 /* -- ensembles: solve(EnsembleProblem(prob; prob_func), alg; trajectories, dt)
  *    (SciMLBase driver; usage lib/BoundaryValueDiffEqMIRK/test/Core/ensemble_tests.jl:20-38).
@@ -172,11 +186,15 @@ int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ens
 int mirk_ensemble_destroy(mirk_ensemble_handle h);
 /* params[ntraj][n_params]; u0[n] shared by all trajectories or u0[ntraj][n] when u0_per_traj != 0 */
 int mirk_ensemble_set_inputs(mirk_ensemble_handle h, const double* params, const double* u0, int32_t u0_per_traj);
+/* the same from device-resident arrays (CuArray params / u0 on the handle's device) */
+int mirk_ensemble_set_inputs_device(mirk_ensemble_handle h, const double* d_params, const double* d_u0, int32_t u0_per_traj);
 int mirk_ensemble_run(mirk_ensemble_handle h, float* device_ms);
 /* per-trajectory outcomes (any pointer may be NULL): sol.retcode, length(sol.t), Newton steps, outer
  * iterations, |sol.resid|_inf, last defect, sol.u[1] */
 int mirk_ensemble_get_results(mirk_ensemble_handle h, int32_t* retcodes, int32_t* n_mesh, int32_t* newton_iters,
                               int32_t* outer_iters, double* resid_norm, double* defect_norm, double* y_first);
+/* the per-trajectory mesh capacity in nodes the handle was created with (sizes the buffers below) */
+int mirk_ensemble_node_cap(mirk_ensemble_handle h, int32_t* node_cap);
 /* sol.t / sol.u of one trajectory; mesh[node_cap], y[node_cap][n] */
 int mirk_ensemble_get_trajectory(mirk_ensemble_handle h, int64_t traj, int32_t* n_mesh, double* mesh, double* y);
 /* one-shot convenience: create + set_inputs + run + get_results + destroy */

@@ -3,15 +3,26 @@
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia`.  It is the thin, mechanical
 # `ccall` layer over include/mirk_b200.h that a maintainer drops next to
 # lib/BoundaryValueDiffEqMIRK; the same C ABI is exercised end to end by the Python mirror
-# (boundaryvaluediffeq.jl_b200/api.py) and the tests.  Reference entry points it replaces:
+# (boundaryvaluediffeq.jl_b200/api.py) and the tests.  The struct layouts below are checked against the
+# header by tests/test_host_logic.py (it parses this file).  Reference entry points it replaces:
 #   SciMLBase.__init(prob::BVProblem, alg::AbstractMIRK; dt, ...)   lib/BoundaryValueDiffEqMIRK/src/mirk.jl:49-53
 #   SciMLBase.solve!(cache)                                          lib/BoundaryValueDiffEqMIRK/src/mirk.jl:286-332
 #   EnsembleProblem driver                                           SciMLBase (usage test/Core/ensemble_tests.jl:20-38)
+#
+# How `solve(prob, MIRK4(); dt)` reaches this backend.  The right-hand side and boundary conditions of a device
+# problem are a *device functor* named by `BVPDeviceFunction` (Julia closures cannot run inside a CUDA kernel), put
+# where the closure goes: `BVProblem(BVPFunction(BVPDeviceFunction("pendulum"), nothing), u0, tspan, p)`.
+#   (a) this module's own `MIRK2 … MIRK6, MIRK6I` carry the reference's fields (`nlsolve`, `optimize`, `jac_alg`,
+#       `defect_threshold`, `max_num_subintervals`, algorithms.jl:55-61) plus `device`; with
+#       `using BoundaryValueDiffEqMIRKB200: MIRK4, MIRK6` a reference script runs unchanged.
+#   (b) with BoundaryValueDiffEqMIRK loaded, ext/BoundaryValueDiffEqMIRKB200MIRKExt.jl adds an `__init` method for
+#       the REFERENCE's own `MIRK4()/MIRK6()` that is more specific in the problem's function type, so the
+#       reference algorithms dispatch here whenever `prob.f.f isa BVPDeviceFunction`.
 module BoundaryValueDiffEqMIRKB200
 
 using SciMLBase, Libdl
 import BoundaryValueDiffEqCore: AbstractBoundaryValueDiffEqAlgorithm, AbstractBoundaryValueDiffEqCache,
-                                DefectControl
+                                DefectControl, BVPJacobianAlgorithm, BVPVerbosity, DEFAULT_VERBOSE
 
 const libmirkb200 = Ref{String}(get(ENV, "MIRK_B200_LIB", "libmirkb200.so"))
 
@@ -19,17 +30,33 @@ const libmirkb200 = Ref{String}(get(ENV, "MIRK_B200_LIB", "libmirkb200.so"))
 """
     BVPDeviceFunction(name)
 
-Stands where `BVPFunction(f!, bc!)` stands: the registry name of a device functor (RHS + boundary
-conditions, csrc/problems.cuh).  Arbitrary Julia closures cannot run inside a CUDA kernel.
+Stands where the closure `f!` stands in `BVPFunction(f!, bc!)`: the registry name of a device functor (RHS +
+boundary conditions + boundary times, csrc/problems.cuh).  Arbitrary Julia closures cannot run inside a CUDA kernel.
 """
 struct BVPDeviceFunction
     name::String
+end
+# a device function is never called on the host
+(f::BVPDeviceFunction)(args...) = error("BVPDeviceFunction($(f.name)) runs on the device only")
+
+struct MirkProblemInfo
+    n::Int32
+    n_params::Int32
+    problem_type::Int32
+    n_bc::Int32
+    n_bca::Int32
+    max_bc_pts::Int32
 end
 
 function problem_id(f::BVPDeviceFunction)
     id = Ref{Int32}(-1)
     check(ccall((:mirk_problem_lookup, libmirkb200[]), Cint, (Cstring, Ref{Int32}), f.name, id))
     return id[]
+end
+function problem_info(f::BVPDeviceFunction)
+    info = Ref{MirkProblemInfo}()
+    check(ccall((:mirk_problem_info_get, libmirkb200[]), Cint, (Int32, Ref{MirkProblemInfo}), problem_id(f), info))
+    return info[]
 end
 
 "register a functor compiled with nvcc from the plugin template (INTEGRATION.md)"
@@ -39,30 +66,26 @@ function register_plugin(name::AbstractString, so_path::AbstractString)
     return BVPDeviceFunction(String(name))
 end
 
-# ---- algorithms (same fields as MIRK4()/MIRK6(), lib/BoundaryValueDiffEqMIRK/src/algorithms.jl:55-61)
+device_function(prob) = prob.f.f isa BVPDeviceFunction ? prob.f.f : nothing
+
+# ---- algorithms: the reference's fields (lib/BoundaryValueDiffEqMIRK/src/algorithms.jl:55-61) + `device` ------
 abstract type AbstractMIRKB200 <: AbstractBoundaryValueDiffEqAlgorithm end
-Base.@kwdef struct MIRK4B200 <: AbstractMIRKB200
-    defect_threshold::Float64 = 0.1
-    max_num_subintervals::Int = 3000
-    device::Int = 0
-end
-Base.@kwdef struct MIRK6B200 <: AbstractMIRKB200
-    defect_threshold::Float64 = 0.1
-    max_num_subintervals::Int = 3000
-    device::Int = 0
-end
-for (name, ord) in ((:MIRK2B200, 2), (:MIRK3B200, 3), (:MIRK5B200, 5), (:MIRK6IB200, 7))  # 7 = the C ABI's code of MIRK6I
+for (name, ord) in ((:MIRK2, 2), (:MIRK3, 3), (:MIRK4, 4), (:MIRK5, 5), (:MIRK6, 6), (:MIRK6I, 7))  # 7 = the C ABI's code of MIRK6I
     @eval begin
-        Base.@kwdef struct $name <: AbstractMIRKB200
+        Base.@kwdef struct $name{N, O, J <: BVPJacobianAlgorithm} <: AbstractMIRKB200
+            nlsolve::N = nothing
+            optimize::O = nothing
+            jac_alg::J = BVPJacobianAlgorithm()
             defect_threshold::Float64 = 0.1
             max_num_subintervals::Int = 3000
             device::Int = 0
         end
-        alg_order(::$name) = $ord
+        tableau_code(::$name) = $ord
     end
 end
-alg_order(::MIRK4B200) = 4
-alg_order(::MIRK6B200) = 6
+# the pre-rename spellings of round 1 stay as aliases
+const MIRK2B200 = MIRK2; const MIRK3B200 = MIRK3; const MIRK4B200 = MIRK4
+const MIRK5B200 = MIRK5; const MIRK6B200 = MIRK6; const MIRK6IB200 = MIRK6I
 
 # ---- C structs (layout of include/mirk_b200.h) -------------------------------------------------
 struct MirkDesc
@@ -102,46 +125,78 @@ end
 
 const RETCODES = (ReturnCode.Success, ReturnCode.Failure, ReturnCode.MaxIters, ReturnCode.Unstable, ReturnCode.Stalled)
 
-# ---- cache -----------------------------------------------------------------------------------
-mutable struct MIRKB200Cache{P, A} <: AbstractBoundaryValueDiffEqCache
+# ---- cache: the fields the reference's tests read (.prob, .alg, .nlsolve_kwargs, .optimize_kwargs, .verbose) ----
+mutable struct MIRKB200Cache{P, A, NK, OK} <: AbstractBoundaryValueDiffEqCache
     prob::P
     alg::A
     handle::Ptr{Cvoid}
     n::Int
-    nlsolve_kwargs::Any
-    optimize_kwargs::Any
-    verbose::Any
+    nlsolve_kwargs::NK
+    optimize_kwargs::OK
+    verbose::BVPVerbosity
 end
 
-function SciMLBase.__init(prob::BVProblem, alg::AbstractMIRKB200; dt = 0.0, abstol = 1e-6, adaptive = true,
+# verbose = true / false / a BVPVerbosity, as the reference normalises it (CORE/src/utils.jl:882-895)
+_verbosity(v::BVPVerbosity) = v
+_verbosity(v::Bool) = v ? DEFAULT_VERBOSE : BVPVerbosity(SciMLBase.SciMLLogging.None())
+_verbosity(v) = BVPVerbosity(v)
+
+# Initial guess -> (mesh, node-major n x N matrix).  The cases of CORE/src/utils.jl:339-388,694-704,750-773:
+#   vector of numbers          constant guess on range(t0, t1, cld(t1 - t0, dt) + 1)     (needs dt > 0)
+#   function u0(p, t) / u0(t)  evaluated on the same uniform mesh                          (needs dt > 0)
+#   vector of vectors / VectorOfArray   guess on range(t0, t1, length(u0))
+#   DiffEqArray / ODESolution / any object with .t and .u   guess AND mesh
+function _guess(u0, p, t0, t1, dt)
+    if u0 isa AbstractVector{<:Number}
+        return nothing, collect(Float64, u0)                       # handled by mirk_set_uniform_guess
+    elseif u0 isa Function
+        dt > 0 || throw(ArgumentError("dt must be positive"))
+        mesh = collect(range(t0; stop = t1, length = Int(cld(t1 - t0, dt)) + 1))
+        f = applicable(u0, p, t0) ? (t -> u0(p, t)) : u0            # u0(t) is deprecated upstream but accepted
+        return mesh, reduce(hcat, (collect(Float64, f(t)) for t in mesh))
+    elseif hasproperty(u0, :t) && hasproperty(u0, :u)               # DiffEqArray, ODESolution, a previous BVP solution
+        return collect(Float64, u0.t), reduce(hcat, (collect(Float64, ui) for ui in u0.u))
+    else                                                            # vector of vectors / VectorOfArray
+        us = hasproperty(u0, :u) ? u0.u : u0
+        mesh = collect(range(t0; stop = t1, length = length(us)))
+        return mesh, reduce(hcat, (collect(Float64, ui) for ui in us))
+    end
+end
+
+function __init_b200(prob::BVProblem, alg, order::Integer, device::Integer; dt = 0.0, abstol = 1e-6, adaptive = true,
         controller = DefectControl(), nlsolve_kwargs = (; abstol = abstol), optimize_kwargs = (;),
-        verbose = nothing, kwargs...)
-    f = prob.f.f
-    f isa BVPDeviceFunction || throw(ArgumentError("the B200 backend needs prob.f to wrap a BVPDeviceFunction"))
+        verbose = DEFAULT_VERBOSE, kwargs...)
+    f = device_function(prob)
+    f === nothing && throw(ArgumentError("the B200 backend needs prob.f to wrap a BVPDeviceFunction"))
+    (alg.nlsolve === nothing && alg.optimize === nothing) ||
+        throw(ArgumentError("a user-supplied nlsolve / optimize is not supported by the B200 backend (its Newton polyalgorithm runs on the device)"))
+    controller isa DefectControl || throw(ArgumentError("the B200 backend implements DefectControl and the global-error controllers through `controller_code`"))
     p = prob.p isa SciMLBase.NullParameters ? Float64[] : collect(Float64, prob.p)
-    desc = MirkDesc(problem_id(f), alg_order(alg), get(nlsolve_kwargs, :abstol, abstol), adaptive,
+    desc = MirkDesc(problem_id(f), order, get(nlsolve_kwargs, :abstol, abstol), adaptive,
         controller.defect_threshold, alg.max_num_subintervals, get(nlsolve_kwargs, :maxiters, 1000), 0, 0,
-        alg.device, length(p), pointer(p))
+        device, length(p), pointer(p))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve p check(ccall((:mirk_create, libmirkb200[]), Cint, (Ref{MirkDesc}, Ref{Ptr{Cvoid}}), desc, h))
     t0, t1 = prob.tspan
-    u0 = prob.u0
-    if u0 isa AbstractVector{<:Number}            # constant guess on a uniform mesh, CORE/src/utils.jl:766-769
-        u = collect(Float64, u0)                   # prob.u0 is never mutated (mirk_basic_tests.jl:717-719)
+    mesh, y = _guess(prob.u0, prob.p, t0, t1, dt)    # copies: prob.u0 is never mutated (mirk_basic_tests.jl:717-719)
+    if mesh === nothing
         check(ccall((:mirk_set_uniform_guess, libmirkb200[]), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Float64}),
-            h[], t0, t1, dt, u))
-        n = length(u)
-    else                                           # vector of vectors carries its own mesh length, utils.jl:339-348
-        N, n = length(u0), length(first(u0))
-        mesh = collect(range(t0; stop = t1, length = N))
-        y = reduce(vcat, (collect(Float64, ui) for ui in u0))      # node-major like recursive_flatten
+            h[], t0, t1, dt, y))
+        n = length(y)
+    else
+        n = size(y, 1)
         check(ccall((:mirk_set_mesh_guess, libmirkb200[]), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}),
-            h[], N, mesh, y))
+            h[], length(mesh), mesh, y))
     end
-    cache = MIRKB200Cache(prob, alg, h[], n, nlsolve_kwargs, optimize_kwargs, verbose)
+    # like the reference's cache, prob.u0 of the stored problem is a plain state vector (mirk.jl:71-77)
+    prob_stored = prob.u0 isa AbstractVector{<:Number} ? prob : SciMLBase.remake(prob; u0 = y[:, 1])
+    cache = MIRKB200Cache(prob_stored, alg, h[], n, nlsolve_kwargs, optimize_kwargs, _verbosity(verbose))
     finalizer(c -> ccall((:mirk_destroy, libmirkb200[]), Cint, (Ptr{Cvoid},), c.handle), cache)
     return cache
 end
+
+SciMLBase.__init(prob::BVProblem, alg::AbstractMIRKB200; kwargs...) =
+    __init_b200(prob, alg, tableau_code(alg), alg.device; kwargs...)
 
 function SciMLBase.solve!(cache::MIRKB200Cache)
     res = Ref{MirkResult}()
@@ -150,7 +205,8 @@ function SciMLBase.solve!(cache::MIRKB200Cache)
     mesh = Vector{Float64}(undef, N)
     y = Matrix{Float64}(undef, n, N)               # column i = node i: node-major in memory
     check(ccall((:mirk_get_solution, libmirkb200[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), cache.handle, mesh, y))
-    resid = Vector{Float64}(undef, n + (N - 1) * n)
+    L = Int(problem_info(device_function(cache.prob)).n_bc)
+    resid = Vector{Float64}(undef, L + (N - 1) * n)
     check(ccall((:mirk_get_residual, libmirkb200[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), cache.handle, resid))
     u = [y[:, i] for i in 1:N]
     sol = SciMLBase.build_solution(cache.prob, cache.alg, mesh, u; interp = MIRKB200Interpolation(cache),
@@ -174,11 +230,11 @@ end
 SciMLBase.interp_summary(::MIRKB200Interpolation) = "MIRK continuous extension evaluated by libmirkb200"
 
 # ---- ensembles -----------------------------------------------------------------------------------
-"`solve(EnsembleProblem(prob; prob_func), MIRK4B200(), EnsembleB200(); trajectories, dt)`"
+"`solve(EnsembleProblem(prob; prob_func), MIRK4(), EnsembleB200(); trajectories, dt)`"
 struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
-    node_cap::Int
+    node_cap::Int       # 0: the library default (on-chip state up to its limit, HBM slab beyond)
 end
-EnsembleB200() = EnsembleB200(128)
+EnsembleB200() = EnsembleB200(0)
 
 struct MirkEnsembleDesc
     problem_id::Int32
@@ -196,25 +252,67 @@ struct MirkEnsembleDesc
     dt::Float64
 end
 
-function SciMLBase.__solve(ens::SciMLBase.AbstractEnsembleProblem, alg::AbstractMIRKB200, ealg::EnsembleB200;
-        trajectories, dt, abstol = 1e-6, adaptive = true, controller = DefectControl(), kwargs...)
-    base = ens.prob
-    f = base.f.f::BVPDeviceFunction
-    probs = [ens.prob_func(base, i) for i in 1:trajectories]          # harvested on the host, 2-arg prob_func
-    params = reduce(hcat, (collect(Float64, q.p) for q in probs))      # np × ntraj = [ntraj][np] row-major
-    u0 = collect(Float64, base.u0)
-    desc = MirkEnsembleDesc(problem_id(f), alg_order(alg), abstol, adaptive, controller.defect_threshold,
-        alg.max_num_subintervals, 1000, 0, alg.device, ealg.node_cap, base.tspan[1], base.tspan[2], dt)
-    ret = Vector{Int32}(undef, trajectories)
-    nm = similar(ret); its = similar(ret)
-    yfirst = Matrix{Float64}(undef, length(u0), trajectories)
-    check(ccall((:mirk_ensemble_solve, libmirkb200[]), Cint,
-        (Ref{MirkEnsembleDesc}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
-        desc, trajectories, params, u0, 0, ret, nm, its, yfirst))
-    converged = all(==(0), ret)
-    return (; retcodes = RETCODES[ret .+ 1], n_mesh = nm, newton_iters = its, u_first = yfirst, converged)
+# generic functions the CUDA extension adds device-array methods to
+function set_guess! end
+function solution! end
+
+# packed inputs of a sweep: (params np x ntraj, u0).  Host arrays here; the CUDA extension adds the CuArray methods
+stage_params(p::AbstractMatrix) = Matrix{Float64}(p)
+set_inputs!(h, params::Matrix{Float64}, u0::Vector{Float64}) =
+    check(ccall((:mirk_ensemble_set_inputs, libmirkb200[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32),
+        h, params, u0, 0))
+
+function ensemble_order(alg, order)
+    order in (4, 6) || throw(ArgumentError("the batched ensemble kernel is instantiated for MIRK4 and MIRK6"))
+    return order
 end
 
-export BVPDeviceFunction, MIRK2B200, MIRK3B200, MIRK4B200, MIRK5B200, MIRK6B200, MIRK6IB200, EnsembleB200, register_plugin
+function __solve_ensemble_b200(ens, alg, order, device, ealg::EnsembleB200; trajectories, dt, abstol = 1e-6,
+        adaptive = true, controller = DefectControl(), packed_params = nothing, kwargs...)
+    base = ens.prob
+    f = device_function(base)
+    f === nothing && throw(ArgumentError("the B200 backend needs prob.f to wrap a BVPDeviceFunction"))
+    # prob_func is harvested on the host (2-argument form of this SciMLBase major, ensemble_tests.jl:20,37);
+    # `packed_params` (np x trajectories, host Matrix or CuArray) is the fast path that skips 262 144 remake calls
+    probs = packed_params === nothing ? [ens.prob_func(base, i) for i in 1:trajectories] : nothing
+    params = packed_params === nothing ? reduce(hcat, (collect(Float64, q.p) for q in probs)) : packed_params
+    u0 = collect(Float64, base.u0)
+    desc = MirkEnsembleDesc(problem_id(f), ensemble_order(alg, order), abstol, adaptive, controller.defect_threshold,
+        alg.max_num_subintervals, 1000, 0, device, ealg.node_cap, base.tspan[1], base.tspan[2], dt)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mirk_ensemble_create, libmirkb200[]), Cint, (Ref{MirkEnsembleDesc}, Int64, Ref{Ptr{Cvoid}}), desc, trajectories, h))
+    try
+        set_inputs!(h[], stage_params(params), u0)
+        check(ccall((:mirk_ensemble_run, libmirkb200[]), Cint, (Ptr{Cvoid}, Ptr{Cfloat}), h[], C_NULL))
+        ret = Vector{Int32}(undef, trajectories)
+        resid = Vector{Float64}(undef, trajectories)
+        check(ccall((:mirk_ensemble_get_results, libmirkb200[]), Cint,
+            (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h[], ret, C_NULL, C_NULL, C_NULL, resid, C_NULL, C_NULL))
+        # one SciMLBase solution per trajectory (sol.t, sol.u, sol.retcode), wrapped like the stock ensemble driver does
+        n = length(u0)
+        cap = Ref{Int32}(0)
+        check(ccall((:mirk_ensemble_node_cap, libmirkb200[]), Cint, (Ptr{Cvoid}, Ref{Int32}), h[], cap))
+        mesh = Vector{Float64}(undef, cap[]); y = Matrix{Float64}(undef, n, cap[])
+        sols = map(1:trajectories) do i
+            N = Ref{Int32}(0)
+            check(ccall((:mirk_ensemble_get_trajectory, libmirkb200[]), Cint,
+                (Ptr{Cvoid}, Int64, Ref{Int32}, Ptr{Float64}, Ptr{Float64}), h[], i - 1, N, mesh, y))
+            prob_i = probs === nothing ? base : probs[i]
+            SciMLBase.build_solution(prob_i, alg, mesh[1:N[]], [y[:, k] for k in 1:N[]]; retcode = RETCODES[ret[i] + 1],
+                resid = [resid[i]])
+        end
+        return SciMLBase.EnsembleSolution(sols, 0.0, all(==(0), ret))
+    finally
+        ccall((:mirk_ensemble_destroy, libmirkb200[]), Cint, (Ptr{Cvoid},), h[])
+    end
+end
+
+SciMLBase.__solve(ens::SciMLBase.AbstractEnsembleProblem, alg::AbstractMIRKB200, ealg::EnsembleB200; kwargs...) =
+    __solve_ensemble_b200(ens, alg, tableau_code(alg), alg.device, ealg; kwargs...)
+
+export BVPDeviceFunction, EnsembleB200, register_plugin
+# MIRK2 … MIRK6I are deliberately NOT exported (they would clash with BoundaryValueDiffEqMIRK's): import them
+# explicitly, `using BoundaryValueDiffEqMIRKB200: MIRK4, MIRK6`, or use the reference's own through the extension.
 
 end # module

@@ -31,7 +31,7 @@ void orc_default_options(orc_options *o) {
     o->max_num_subintervals = 3000; /* MIRK/algorithms.jl:55-61 */
     o->maxiters = 1000;
     o->reinterp_inplace = 0; /* see DESIGN.md "Q3": 1 reproduces the reference's in-place hazard */
-    o->max_outer = 60;
+    o->max_outer = 1000; /* safety net only: the reference loop has no cap (mirk.jl:296-322) */
 }
 
 /* alg_order (MIRK/alg_utils.jl:1-11): MIRK6I is a 6th-order method selected by its own code */

@@ -18,11 +18,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    for maker, nint in (("c2_chain8", 4001), ("c5_chain16", 1203), ("c2_chain8", 20 * world + 3)):
+    # both exchange flavours: remote stores into peer memory (CUDA IPC over NVLink, graph-replayed) and NCCL
+    for exchange, maker, nint in (("p2p", "c2_chain8", 4001), ("nccl", "c2_chain8", 4001), ("p2p", "c5_chain16", 1203),
+                                  ("nccl", "c5_chain16", 1203), ("p2p", "c2_chain8", 20 * world + 3)):
         c = getattr(configs, maker)(nint)
         alg = M.MIRK6() if c.order == 6 else M.MIRK4()
         prob = M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh)
-        cache, (lo, hi) = partition.init_partitioned(prob, alg, device=local)
+        cache, (lo, hi) = partition.init_partitioned(prob, alg, device=local, exchange=exchange)
         r_loc, nrm0 = cache.residual()
         ret, it, nrm = cache.newton_solve()
         full = partition.gather_solution(cache, c.N)
@@ -32,17 +34,29 @@ def main():
             rret, rit, rnrm = ref.newton_solve()
             _, u = ref.solution()
             err = np.max(np.abs(full - u)) / np.max(np.abs(u))
-            print(f"{maker} N={c.N} world={world}: iters {it} vs {rit}, |F| {nrm:.3e} vs {rnrm:.3e}, rel err {err:.2e}", flush=True)
+            print(f"{maker} N={c.N} world={world} exchange={exchange}: iters {it} vs {rit}, |F| {nrm:.3e} vs {rnrm:.3e}, rel err {err:.2e}", flush=True)
             assert (ret, it) == (rret, rit) and ret == 0
             assert abs(nrm0 - ref_nrm0) <= 1e-12 * max(1.0, ref_nrm0)
             assert err < 1e-10
             ref.close()
         # timing of the collective Newton step (device events, max over ranks)
+        cache.bench_newton_steps(4)  # warm: the p2p flavour replays CUDA graphs from the third run on
         st, ms, ph, launches = cache.bench_newton_steps(5)
+        assert st == 0
+        # the graph-replayed steps leave the same iterate as one direct Newton step from the guess would
+        full_b = partition.gather_solution(cache, c.N)
+        if rank == 0:
+            ref = M.init(prob, alg, adaptive=False, device=local)
+            ref.newton_step()
+            _, u1 = ref.solution()
+            ref.close()
+            errb = np.max(np.abs(full_b - u1)) / np.max(np.abs(u1))
+            assert errb < 1e-10, errb
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(f"  partitioned Newton step: {t.item() / 5:.3f} ms (phases us: {[round(1e3 * p / 5, 1) for p in ph[:7]]})", flush=True)
+        dist.barrier()  # nobody frees its exchange buffer while a peer may still push into it
         cache.close()
     dist.barrier()
     if rank == 0:

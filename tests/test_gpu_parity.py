@@ -311,6 +311,34 @@ def test_large_block_problems_match_golden(M, key, maker, nint):
     cache.close()
 
 
+@pytest.mark.parametrize("key,maker", [("c4_full", "c4_bratu64"), ("c5_slice", "c5_chain16")])
+def test_full_size_large_block_configs_match_golden(M, key, maker):
+    """BASELINE config C4 at its full size (n = 128, N = 4000, MIRK4) and one GPU's slice of C5 (n = 32, 250 000
+    nodes = 2 000 000 / 8, MIRK6): |F|_inf before and after the oracle's Newton steps and the iterate itself
+    (tests/golden/make_golden_large.py; minutes of CPU, so the oracle's result is a committed fixture)."""
+    import json
+    import os
+    from boundaryvaluediffeq_jl_b200 import configs
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "newton_golden_large.json")))[key]
+    c = getattr(configs, maker)(gold["nint"])
+    cache = M.init(M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh), M.MIRK6() if c.order == 6 else M.MIRK4(),
+                   adaptive=False)
+    _, nrm0 = cache.residual()
+    assert abs(nrm0 - gold["norm_first"]) <= 1e-12 * gold["norm_first"] + 1e-18
+    nrm = None
+    for _ in range(gold["steps"]):
+        st, nrm = cache.newton_step()
+        assert st == 0
+    # the last norms are at rounding level (1e-12): compare magnitudes, and the iterate to 1e-10 relative
+    assert nrm < 1e-9
+    _, u = cache.solution()
+    scale = gold["sum_abs"] / u.size
+    assert abs(u.sum() - gold["sum"]) < 1e-10 * gold["sum_abs"]
+    for name, idx in (("y_mid", c.N // 2), ("y_q1", c.N // 4), ("y_last", c.N - 2)):
+        assert np.max(np.abs(u[idx] - np.array(gold[name]))) < 1e-10 * max(1.0, scale, np.max(np.abs(gold[name])))
+    cache.close()
+
+
 USER_FUNCTOR = r"""
 // u'' + lam * exp(u) = 0, u(0) = u(1) = 0 (1-D Bratu) as a user-supplied device functor
 struct UserBratu {

@@ -174,3 +174,59 @@ def test_dmma_fragment_merge_n32_four_warps_matches_sequential_elimination():
     assert (qa == qb).all()
     assert np.abs(Wa[:, 32:] - Wb[:, 32:]).max() < 1e-11
     assert np.abs(ra - rb).max() < 1e-11 and np.abs(ia - ib).max() < 1e-13
+
+
+# ---- struct layouts across the C ABI: header (gcc) vs ctypes mirror vs the Julia glue's struct definitions ------
+def _c_layout(tmp_path):
+    exe = os.path.join(str(tmp_path), "c_abi_layout")
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_layout.c"),
+                    "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    return {k: int(v) for k, v in (ln.split() for ln in out.strip().splitlines())}
+
+
+_JL_TYPES = {"Int32": (4, 4), "Float64": (8, 8), "Ptr{Float64}": (8, 8), "Ptr{Cvoid}": (8, 8), "Int64": (8, 8)}
+
+
+def _julia_layout(struct_name):
+    """(size, {field: offset}) of an immutable Julia struct of C-compatible fields, by the C layout rules Julia's
+    `ccall` follows for isbits structs (natural alignment, NTuple{N,T} = T[N])."""
+    src = open(os.path.join(ROOT, "julia", "BoundaryValueDiffEqMIRKB200", "src", "BoundaryValueDiffEqMIRKB200.jl")).read()
+    m = re.search(r"^struct %s\n(.*?)^end" % struct_name, src, flags=re.M | re.S)
+    assert m, f"struct {struct_name} not found in the Julia glue"
+    off, offs, maxal = 0, {}, 1
+    for ln in m.group(1).strip().splitlines():
+        ln = ln.split("#")[0].strip()
+        if not ln:
+            continue
+        name, typ = [x.strip() for x in ln.split("::")]
+        nt = re.match(r"NTuple\{(\d+),\s*(\w+)\}", typ)
+        if nt:
+            sz, al = _JL_TYPES[nt.group(2)]
+            sz *= int(nt.group(1))
+        else:
+            sz, al = _JL_TYPES[typ]
+        off = (off + al - 1) // al * al
+        offs[name] = off
+        off += sz
+        maxal = max(maxal, al)
+    return (off + maxal - 1) // maxal * maxal, offs
+
+
+def test_struct_layouts_agree_between_header_ctypes_and_julia(tmp_path):
+    import mirk_b200  # noqa: F401
+    from boundaryvaluediffeq_jl_b200 import _lib as B
+    c = _c_layout(tmp_path)
+    pairs = [("mirk_desc", B.Desc, "MirkDesc"), ("mirk_problem_info", B.ProblemInfo, "MirkProblemInfo"),
+             ("mirk_result", B.Result, "MirkResult"), ("mirk_ensemble_desc", B.EnsembleDesc, "MirkEnsembleDesc")]
+    import ctypes as C
+    for cname, ct, jl in pairs:
+        fields = {k.split(".", 1)[1]: v for k, v in c.items() if k.startswith(cname + ".")}
+        assert fields, cname
+        assert C.sizeof(ct) == c["sizeof." + cname], cname
+        assert [f for f, _ in ct._fields_] == list(fields), (cname, "field order")
+        for f, _ in ct._fields_:
+            assert getattr(ct, f).offset == fields[f], (cname, f)
+        jsize, joffs = _julia_layout(jl)
+        assert jsize == c["sizeof." + cname], (jl, jsize)
+        assert joffs == fields, (jl, joffs, fields)
