@@ -184,7 +184,7 @@ def work_model(n, N, order):
     are overhead traffic, not algorithmic bytes."""
     ni, nn = N - 1, n * n
     s, g = (5, 6) if order == 6 else (3, 2)
-    cf = 6 * n + (n // 2) * 20       # RHS flop count of the pendulum chain (sin ~ 20 flops)
+    cf = 6 * n + (n // 2) * 20       # RHS flop count of the pendulum chain / Bratu lines (sin, exp ~ 20 flops)
     Ff = ni * (s * cf + 2 * n * (s * (s + 1) // 2) + (2 * s + 1) * n)
     FJ = ni * (s * 4 * n + 2 * g * n ** 3)
     FS = (14.0 / 3.0) * n ** 3 * ni
@@ -481,14 +481,16 @@ def measure_ensemble(args, scaling="strong", with_cpu=True):
 
 
 # ---- BASELINE config C5: n = 32, 2 000 000 nodes, mesh-partitioned ------------------------------------------
-def measure_c5(args):
+def measure_c5(args, which="c5"):
+    """C5 (n = 32, 2 000 000 nodes, mesh-partitioned over the ranks) or, with which = "c4", BASELINE config C4
+    (n = 128, N = 4000, MIRK4; one GPU)."""
     import numpy as np  # noqa: F401
 
     import mirk_b200 as M
     from boundaryvaluediffeq_jl_b200 import configs, partition
 
     rank, world, local, barrier, allmax = _dist_setup()
-    c = configs.c5_chain16(args.c5_nint)
+    c = configs.c5_chain16(args.c5_nint) if which == "c5" else configs.c4_bratu64(args.c4_nint)
     cache, (lo, hi) = _make_cache(M, partition, c, world, local, args)
     steps = max(1, min(args.steps, 5))
     st, _, _, _ = cache.bench_newton_steps(2)
@@ -508,7 +510,7 @@ def measure_c5(args):
             "algorithmic_gb_per_step": B_ * 1e-9, "achieved_gbs_all_gpus": B_ / (per * 1e-3) * 1e-9,
             "exchange": getattr(cache, "exchange", None),
             "phases_ms_rank0": dict(zip(PHASES, [p / steps for p in ph[:7]])), "gpu_launches": int(launches),
-            "workload": f"C5: {c.desc}; mesh partitioned into {world} segment(s)"}
+            "workload": f"{c.key}: {c.desc}; mesh partitioned into {world} segment(s)"}
 
 
 def _guarded(fn, *a, **kw):
@@ -528,12 +530,13 @@ def main():
     ap.add_argument("--nint", type=int, default=C2_NINT, help="mesh intervals per GPU (default: C2's 19 999)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--exchange", default=None, choices=["p2p", "nccl"], help="interface exchange of the partitioned mode")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5part"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5part", "c4"],
                     help="c2: the headline Newton-step line (default, with the extras); c3 / c5part: that workload alone")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C5 extras of the default run")
     ap.add_argument("--trajectories", type=int, default=262144)
     ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--c5-nint", type=int, default=1999999)
+    ap.add_argument("--c4-nint", type=int, default=3999)
     ap.add_argument("--extra-timeout", type=float, default=300.0)
     ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
     args = ap.parse_args()
@@ -545,8 +548,8 @@ def main():
         out = measure_ensemble(args, args.ensemble_scaling)
         if rank == 0:
             print(json.dumps(out), flush=True)
-    elif args.workload == "c5part":
-        out = measure_c5(args)
+    elif args.workload in ("c5part", "c4"):
+        out = measure_c5(args, "c5" if args.workload == "c5part" else "c4")
         if rank == 0:
             print(json.dumps(out), flush=True)
     else:
@@ -565,6 +568,8 @@ def main():
                 dog.daemon = True
                 dog.start()
                 extra = {"c3_strong": _guarded(measure_ensemble, args, "strong", True), "c5part": _guarded(measure_c5, args)}
+                if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+                    extra["c4"] = _guarded(measure_c5, args, "c4")
                 dog.cancel()
             if rank == 0:
                 line["extra"] = extra

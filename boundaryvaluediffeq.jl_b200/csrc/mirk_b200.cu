@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "abd.cuh"
+#include "abd_block.cuh"
 #include "abd_pair.cuh"
 #include "abd_warp.cuh"
 #include "ensemble.cuh"
@@ -282,8 +283,13 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     }
     // upper levels: an explicit field keeps one launch per level; the warp-path default is radix 2 with up to
     // kSegLevels levels per launch (depth log2 instead of 3 merges per radix-4 level, a third of the launches)
+    // large blocks (abd_block.cuh, one CTA per group, ~0.15 ms per merge): level 0 sized to ONE balanced wave of CTAs,
+    // radix 2 above it — the depth in merges is what the step costs
+    static const bool use_block = !(getenv("MIRK_ABD_BLOCK") && atoi(getenv("MIRK_ABD_BLOCK")) == 0);
+    const bool block_path = use_block && block_reduce_supported(n);
+    if ((chunk & 0xff) < 2 && block_path) c0 = std::min(32, std::max(4, (N - 1 + S->sm_count - 1) / S->sm_count));
     const bool multi = warp_path0 && ((chunk >> 8) & 0xff) < 2;
-    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : (warp_path0 ? 2 : c0);
+    const int c1 = ((chunk >> 8) & 0xff) >= 2 ? ((chunk >> 8) & 0xff) : ((warp_path0 || block_path) ? 2 : c0);
     const int tail_thr = ((chunk >> 16) & 0xffff) ? ((chunk >> 16) & 0xffff) : 8;
     const bool warp_path = warp_reduce_supported(n);
     if (P.valid && P.N == N && P.chunk == chunk && P.pinned == pinned) return MIRK_OK;
@@ -383,8 +389,10 @@ static int build_plan_for(mirk_solver_s* S, Plan& P, int N, std::vector<int> pin
     CK(cudaStreamSynchronize(S->st));  // hint goes out of scope
 
     // scratch for the generic reduction when the working matrix does not fit in shared memory
-    if (reduce_smem_bytes(n) > kSmemLimit && P.nlev > 0) {
-        const size_t need = (size_t)P.G[0] * (2 * n) * (3 * n + 1);
+    if ((reduce_smem_bytes(n) > kSmemLimit || block_reduce_supported(n)) && P.nlev > 0) {
+        int gmax = 0;
+        for (int l = 0; l < P.nlev; l++) gmax = std::max(gmax, P.G[l]);
+        const size_t need = (size_t)gmax * (2 * n) * (3 * n + 1);
         if (need > S->scratch_cap) {
             dfree(S->scratch);
             CK(dalloc(&S->scratch, need));
@@ -577,6 +585,9 @@ static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int 
         } else if (pair_reduce_supported(n)) {
             launch_pair_reduce(S->st, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
                                P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, (int*)(S->words + 2));
+        } else if (block_reduce_supported(n) && !(getenv("MIRK_ABD_BLOCK") && atoi(getenv("MIRK_ABD_BLOCK")) == 0)) {
+            CK(launch_block_reduce(S->st, n, P.G[l], P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1], P.relR[l + 1],
+                                   P.relr[l + 1], P.d_nodes[l], P.d_gs[l], C.TL, C.TR, C.rt, S->scratch, (int*)(S->words + 2)));
         } else {
             const int smem = smem_ok ? reduce_smem_bytes(n) : reduce_small_smem_bytes(n);
             k_reduce_generic<<<P.G[l], 256, smem, S->st>>>(n, P.relL[l], P.relR[l], P.relr[l], P.relL[l + 1],
