@@ -177,7 +177,8 @@ struct mirk_solver_s {
            *y_best = nullptr, *Kd = nullptr, *Ki = nullptr, *resid = nullptr, *errors = nullptr,
            *est = nullptr, *Lb = nullptr, *Rb = nullptr, *TL = nullptr, *TR = nullptr, *rt = nullptr,
            *delta = nullptr, *p = nullptr, *Bc = nullptr, *scratch = nullptr, *Mfinal = nullptr,
-           *tbuf = nullptr, *obuf = nullptr;
+           *tbuf = nullptr, *obuf = nullptr, *jscratch = nullptr;
+    size_t jscratch_cap = 0;
     int *bc_nodes = nullptr, *m_dev = nullptr, *iold = nullptr, *sel_out = nullptr;
     size_t scratch_cap = 0, Mfinal_cap = 0, tbuf_cap = 0;
     // host-visible words: [0] residual norm bits, [1] defect bits, [2] status
@@ -516,9 +517,19 @@ static int eval_jacobian(mirk_solver_s* S) {
 
 // F(y) and J(y) in one pass over the mesh: the Newton loop's per-iteration evaluation
 static int eval_resjac(mirk_solver_s* S) {
+    {   // scratch of the stage-wise dense Jacobian path (large n only; 0 otherwise)
+        const size_t need = S->ops->resjac_scratch_doubles(S->N);
+        if (need > S->jscratch_cap) {
+            CK(cudaStreamSynchronize(S->st));
+            dfree(S->jscratch);
+            CK(dalloc(&S->jscratch, need));
+            S->jscratch_cap = need;
+            S->graph_epoch++;
+        }
+    }
     CKS(run_graphed(S, kGraphResjac, [&]() -> int {
         CK(cudaMemsetAsync(S->words, 0, sizeof(unsigned long long), S->st));
-        S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb);
+        S->ops->resjac(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->resid + S->La, S->words, S->Lb, S->Rb, S->jscratch);
         S->launches++;
         CKS(eval_bc(S, 1, true));
         return launch_check("resjac");
@@ -1040,6 +1051,7 @@ int mirk_destroy(mirk_handle S) {
     cudaSetDevice(S->desc.device);
     if (S->st) cudaStreamSynchronize(S->st);
     free_buffers(S);
+    dfree(S->jscratch);
     dfree(S->p); dfree(S->Bc); dfree(S->scratch); dfree(S->Mfinal); dfree(S->tbuf); dfree(S->obuf);
     dfree(S->bc_nodes); dfree(S->m_dev); dfree(S->sel_out); dfree(S->words);
     dfree(S->plan.d_int); dfree(S->plan.d_rel);

@@ -8,6 +8,7 @@
 
 #include "kernels.cuh"
 #include "problems.cuh"
+#include "stagejac.cuh"
 
 namespace mirk {
 
@@ -22,7 +23,9 @@ struct ProblemOps {
     void (*jac_blocks)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
                        double* Lb, double* Rb);
     void (*resjac)(cudaStream_t, int N, const double* mesh, const double* y, const double* p, double* Kd,
-                   double* phi_out, unsigned long long* norm_bits, double* Lb, double* Rb);
+                   double* phi_out, unsigned long long* norm_bits, double* Lb, double* Rb, double* scratch);
+    // doubles of scratch resjac wants for a mesh of N nodes (0: none) — the stage-wise dense path of large n
+    size_t (*resjac_scratch_doubles)(int N);
     void (*defect)(cudaStream_t, int N, const double* mesh, const double* y, const double* p,
                    const double* Kd, double* Ki, double* errors, double* est,
                    unsigned long long* defect_bits);
@@ -59,8 +62,41 @@ template <class P, int ORDER> struct OpsImpl {
         const long long tot = (long long)(N - 1) * 2 * P::n;
         k_jac_blocks<P, ORDER><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(N, mesh, y, p, Lb, Rb);
     }
+    // large state dimension: stage Jacobians + dense DMMA chain-rule products (stagejac.cuh); MIRK_RESJAC=tape keeps
+    // the per-column taped sweep for A/B runs
+    static constexpr bool kDense = (P::n == 64 || P::n == 128) && (ORDER == 4 || ORDER == 6);
+    static constexpr size_t kDenseBatchDoubles = (size_t)1 << 28;  // 2 GiB of scratch at most: longer meshes run in batches
+    static bool dense_enabled() {
+        static const bool off = getenv("MIRK_RESJAC") && (!strcmp(getenv("MIRK_RESJAC"), "tape") || !strcmp(getenv("MIRK_RESJAC"), "dual"));
+        return kDense && !off;
+    }
+    static size_t resjac_scratch_doubles(int N) {
+        if constexpr (kDense) {
+            if (!dense_enabled()) return 0;
+            const size_t per = stagejac_doubles_per_interval<P, ORDER>(), want = per * (size_t)(N - 1);
+            return want < kDenseBatchDoubles ? want : (kDenseBatchDoubles / per) * per;
+        } else {
+            return 0;
+        }
+    }
     static void resjac(cudaStream_t st, int N, const double* mesh, const double* y, const double* p, double* Kd,
-                       double* phi_out, unsigned long long* nb, double* Lb, double* Rb) {
+                       double* phi_out, unsigned long long* nb, double* Lb, double* Rb, double* scratch) {
+        if constexpr (kDense) {
+            if (dense_enabled() && scratch) {
+                residual(st, N, mesh, y, p, Kd, phi_out, nb);  // stages, Phi, |Phi|_inf
+                const size_t per = stagejac_doubles_per_interval<P, ORDER>();
+                const int batch = (int)(resjac_scratch_doubles(N) / per);
+                static const cudaError_t attr = cudaFuncSetAttribute(k_chain_gemm<P::n, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                     (int)(sizeof(double) * ChainGemm<P::n, ORDER>::smem_doubles));
+                (void)attr;
+                for (int i0 = 0; i0 < N - 1; i0 += batch) {
+                    const int cnt = (N - 1 - i0) < batch ? (N - 1 - i0) : batch;
+                    k_stage_jac<P, ORDER><<<cnt, P::n, 0, st>>>(i0, N, mesh, y, p, Kd, scratch);
+                    k_chain_gemm<P::n, ORDER><<<cnt, 256, sizeof(double) * ChainGemm<P::n, ORDER>::smem_doubles, st>>>(i0, N, mesh, scratch, Lb, Rb);
+                }
+                return;
+            }
+        }
         // default: taped values + tangent replay (k_resjac_tape); MIRK_RESJAC=dual selects the plain dual
         // sweep per column, MIRK_TAPE_IPW the intervals per warp (tuning / A-B measurements)
         static const bool use_dual = getenv("MIRK_RESJAC") && !strcmp(getenv("MIRK_RESJAC"), "dual");
@@ -104,7 +140,7 @@ template <class P, int ORDER> struct OpsImpl {
     static ProblemOps make(const char* name) {
         using TB = Tableau<ORDER>;
         return ProblemOps{name, ORDER, P::n, P::np, P::n_bc, P::n_bca, P::problem_type, P::max_bc_pts,
-                          TB::s, TB::s_star, &residual, &bc, &jac_blocks, &resjac, &defect, &interp_setup,
+                          TB::s, TB::s_star, &residual, &bc, &jac_blocks, &resjac, &resjac_scratch_doubles, &defect, &interp_setup,
                           &bc_nodes_host};
     }
 };

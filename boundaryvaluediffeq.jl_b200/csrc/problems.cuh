@@ -24,6 +24,10 @@ namespace mirk {
 namespace problems {
 
 #define MIRK_PF template <class T> __host__ __device__ __forceinline__ static void
+// the same with argument types left open: `du` only needs `du[k] = value`, `u` only `u[k]` — raw pointers, or the
+// proxies of stagejac.cuh (seeds generated on the fly, tangents stored straight into the Jacobian).  Functors written
+// this way must treat du as WRITE-ONLY.
+#define MIRK_PFX template <class T, class DU = T*, class U = const T*> __host__ __device__ __forceinline__ static void
 #define MIRK_PT __host__ __device__ __forceinline__ static int
 
 constexpr double kPi = 3.14159265358979323846;
@@ -175,7 +179,7 @@ template <int NP> struct Chain {
 //    u = [u_1..u_M, v_1..v_M], p = [lambda]
 template <int M> struct BratuMOL {
     static constexpr int n = 2 * M, np = 1, n_bc = 2 * M, n_bca = M, problem_type = 1, max_bc_pts = 2;
-    MIRK_PF f(T* du, const T* u, const double* p, double) {
+    MIRK_PFX f(DU du, U u, const double* p, double) {
         using namespace fn;
         constexpr double dz = 1.0 / (M + 1), idz2 = 1.0 / (dz * dz);
 #pragma unroll 4

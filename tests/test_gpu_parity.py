@@ -55,6 +55,7 @@ CASES = [
     ("lotka", 6, [7.5, 4.0, 8.5, 5.0], (0.0, 10.0), 50), ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 30),
     ("layer", 6, [0.1], (-1.0, 1.0), 64), ("chain8", 6, None, (0.0, 0.5), 100), ("chain8", 4, None, (0.0, 0.5), 37),
     ("chain16", 6, None, (0.0, 0.5), 41), ("bratu64", 4, [1.0], (0.0, 1.0), 19),
+    ("bratu64", 6, [1.0], (0.0, 1.0), 11),   # MIRK6 through the stage-wise dense Jacobian (three chained DMMA products)
     # the rest of the MIRK family: MIRK2, MIRK3, MIRK5
     ("pendulum", 2, [9.81], PENDULUM_T, 32), ("pendulum", 3, [9.81], PENDULUM_T, 32), ("pendulum", 5, [9.81], PENDULUM_T, 32),
     ("swirling", 5, [0.01], (0.0, 1.0), 31), ("torus", 3, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 20),
