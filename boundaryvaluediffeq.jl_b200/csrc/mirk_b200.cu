@@ -680,6 +680,14 @@ static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
         return launch_check("abd_tail_partitioned");
     }
     if (C.exchange) return part_exchange_and_close(S);
+    static const bool use_block = !(getenv("MIRK_ABD_BLOCK") && atoi(getenv("MIRK_ABD_BLOCK")) == 0);
+    if (use_block && block_reduce_supported(n) && P.Q == 2 && S->L == n) {
+        // two kept nodes, n boundary rows: the blocked Gauss-Jordan of abd_block.cuh on the 2n x 2n closing system
+        CK(launch_block_final(S->st, n, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, C.m_dev,
+                              C.bc_nodes, C.Bc, C.resid, C.tail_off, S->Mfinal, C.delta, (int*)(S->words + 2)));
+        S->launches++;
+        return launch_check("abd_final_block");
+    }
     const int threads = D * (D + 1) >= 4096 ? 1024 : 256;
     k_final_solve<<<1, threads, final_smem_bytes(D, m_in_smem), S->st>>>(
         n, P.Q, P.d_nodes[P.nlev], P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->L, S->La, C.m_dev,
