@@ -29,7 +29,7 @@ class Desc(C.Structure):
                 ("adaptive", C.c_int32), ("defect_threshold", C.c_double),
                 ("max_num_subintervals", C.c_int32), ("maxiters", C.c_int32),
                 ("reinterp_inplace", C.c_int32), ("chunk", C.c_int32), ("device", C.c_int32),
-                ("n_params", C.c_int32), ("params", dp)]
+                ("n_params", C.c_int32), ("params", dp), ("nlsolve", C.c_int32)]
 
 
 class ProblemInfo(C.Structure):
@@ -49,7 +49,7 @@ class EnsembleDesc(C.Structure):
                 ("adaptive", C.c_int32), ("defect_threshold", C.c_double),
                 ("max_num_subintervals", C.c_int32), ("maxiters", C.c_int32),
                 ("reinterp_inplace", C.c_int32), ("device", C.c_int32), ("node_cap", C.c_int32),
-                ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double)]
+                ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double), ("nlsolve", C.c_int32)]
 
 
 Handle = C.c_void_p
@@ -77,6 +77,7 @@ SYMBOLS = {
     "mirk_linear_solve": (C.c_int, [Handle, dp]),
     "mirk_newton_step": (C.c_int, [Handle, dp]),
     "mirk_newton_solve": (C.c_int, [Handle, ip, dp]),
+    "mirk_nlsolve_stats": (C.c_int, [Handle, ip, ip]),
     "mirk_defect": (C.c_int, [Handle, dp, dp]),
     "mirk_refine_mesh": (C.c_int, [Handle, ip]),
     "mirk_solve": (C.c_int, [Handle, C.POINTER(Result)]),

@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib as B
 
-__all__ = ["BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
+__all__ = ["NewtonRaphson", "BackTracking", "TrustRegion", "BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
            "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b",
            "EnsembleProblem", "EnsembleSolution", "EnsembleB200", "compile_device_function",
            "successful_retcode"]
@@ -168,6 +168,38 @@ class BVPJacobianAlgorithm:
 
 
 @dataclass(frozen=True)
+class BackTracking:
+    """LineSearch.BackTracking() — the line search of the polyalgorithm's second solver"""
+
+
+@dataclass(frozen=True)
+class NewtonRaphson:
+    """NonlinearSolve.NewtonRaphson(; linesearch): `nlsolve = NewtonRaphson()` / `NewtonRaphson(linesearch = BackTracking())`"""
+    linesearch: object = None
+
+
+@dataclass(frozen=True)
+class TrustRegion:
+    """NonlinearSolve.TrustRegion() (Simple radius update, dogleg step)"""
+
+
+def _nlsolve_code(nlsolve) -> int:
+    """alg.nlsolve -> the C ABI's solver code.  None is the reference default: the polyalgorithm NewtonRaphson ->
+    NewtonRaphson + BackTracking -> TrustRegion (CORE/src/default_internal_solve.jl:31-45)."""
+    if nlsolve is None:
+        return 0
+    if isinstance(nlsolve, TrustRegion):
+        return 3
+    if isinstance(nlsolve, NewtonRaphson):
+        if nlsolve.linesearch is None:
+            return 1
+        if isinstance(nlsolve.linesearch, BackTracking):
+            return 2
+    raise NotImplementedError("nlsolve must be None (the default polyalgorithm), NewtonRaphson(), "
+                              "NewtonRaphson(linesearch=BackTracking()) or TrustRegion(): other solvers cannot run on the device")
+
+
+@dataclass(frozen=True)
 class _AbstractMIRK:
     """MIRK/src/algorithms.jl:55-61"""
     nlsolve: object = None
@@ -178,9 +210,9 @@ class _AbstractMIRK:
     order = 0
 
     def __post_init__(self):
-        if self.nlsolve is not None or self.optimize is not None:
-            raise NotImplementedError("a user-supplied nlsolve/optimize is not supported by the B200 backend "
-                                      "(NewtonRaphson on device only)")
+        if self.optimize is not None:
+            raise NotImplementedError("`optimize` solvers are not supported by the B200 backend")
+        _nlsolve_code(self.nlsolve)
 
 
 @dataclass(frozen=True)
@@ -280,7 +312,7 @@ class MIRKCache:
         desc = B.Desc(prob.f.problem_id, alg.order, float(self.nlsolve_kwargs["abstol"]), int(bool(adaptive)),
                       float(controller.defect_threshold), int(alg.max_num_subintervals),
                       int(self.nlsolve_kwargs.get("maxiters", 1000)), int(reinterp_inplace), int(chunk), int(device),
-                      len(p), _d(p) if len(p) else None)
+                      len(p), _d(p) if len(p) else None, _nlsolve_code(alg.nlsolve))
         self._h = B.Handle()
         B.check(B.lib().mirk_create(C.byref(desc), C.byref(self._h)))
         t0, t1 = prob.tspan
@@ -361,6 +393,12 @@ class MIRKCache:
         it, nrm = C.c_int32(0), C.c_double(0)
         ret = B.check(B.lib().mirk_newton_solve(self._h, C.byref(it), C.byref(nrm)))
         return ret, it.value, nrm.value
+
+    def nlsolve_stats(self):
+        """(steps, retcodes) of NewtonRaphson / + BackTracking / TrustRegion in the last nonlinear solve (-1: did not run)"""
+        st, rc = np.zeros(3, dtype=np.int32), np.zeros(3, dtype=np.int32)
+        B.check(B.lib().mirk_nlsolve_stats(self._h, _i(st), _i(rc)))
+        return list(map(int, st)), list(map(int, rc))
 
     def defect(self):
         N = self.n_mesh

@@ -22,6 +22,9 @@ namespace mirk {
 
 // SciMLBase.ReturnCode values (same numbers as MIRK_RET_* in include/mirk_b200.h)
 constexpr int MIRK_RET_SUCCESS_ = 0, MIRK_RET_FAILURE_ = 1, MIRK_RET_MAXITERS_ = 2, MIRK_RET_UNSTABLE_ = 3;
+// internal: plain NewtonRaphson did not succeed and the default polyalgorithm is requested — the host re-runs that
+// trajectory through the single-problem driver (mirk_solve), which has the line-search / trust-region fallbacks
+constexpr int MIRK_ENS_NEEDS_POLY = -101;
 
 struct EnsArgs {
     long long ntraj;
@@ -34,7 +37,12 @@ struct EnsArgs {
     int u0_per_traj;
     double abstol, defect_threshold;
     int adaptive, max_sub, maxiters, reinterp_inplace, max_outer;
+    int nlsolve;           // 0: default polyalgorithm (kernels run its first solver, failures go to the host), 1: NewtonRaphson only
+    unsigned long long* poly_count;  // trajectories handed to the host, and their list
+    long long* poly_list;
     double* work;
+    // optional indirection (overflow re-runs of the warp kernel): slab slot t holds global trajectory idx[t]
+    const long long* idx;
     // per-trajectory results
     int* retcode;
     int* n_mesh;
@@ -441,6 +449,12 @@ template <class P, int ORDER> struct EnsSolver {
                 for (int k = 0; k < n; k++) Y(i, k) = YB(i, k);
             nrm = residual_sweep(rbc);
         }
+        if (ret != MIRK_RET_SUCCESS_ && a.nlsolve == 0) {
+            // the reference would now restart this Newton solve with BackTracking, then TrustRegion
+            a.retcode[tid] = MIRK_ENS_NEEDS_POLY;
+            a.poly_list[atomicAdd(a.poly_count, 1ull)] = tid;
+            return;
+        }
         resid_norm = nrm;
         newton_total += it;
         error_norm = 2.0 * abstol;
@@ -625,10 +639,11 @@ k_ensemble_solve(EnsArgs a) {
     using ES = EnsSolver<P, ORDER>;
     using LY = EnsLayout<P, ORDER>;
     constexpr int n = P::n;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= a.ntraj) return;
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.ntraj) return;
+    const long long tid = a.idx ? a.idx[slot] : slot;  // global trajectory: parameters in, outcomes out
     ES S;
-    S.B = a.work + tid;
+    S.B = a.work + slot;
     S.st = (size_t)a.stride;
     S.NC = a.NC;
     S.N = a.N0;
@@ -669,12 +684,23 @@ static __global__ void k_ensemble_extract(long long stride, int NC, int n, int o
     for (int k = 0; k < n; k++) out_y[(size_t)i * n + k] = B[((size_t)(oY + k) * NC + i) * (size_t)stride];
 }
 
-// y at node 0 of every trajectory (what SciML ensemble reductions typically read): out[ntraj][n]
+// y at node 0 of every trajectory (what SciML ensemble reductions typically read): out[ntraj][n];
+// idx (optional): slab slot t holds global trajectory idx[t]
 static __global__ void k_ensemble_first(long long ntraj, long long stride, int NC, int n, int oY, const double* __restrict__ work,
-                                 double* __restrict__ out) {
+                                 const long long* __restrict__ idx, double* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntraj) return;
-    for (int k = 0; k < n; k++) out[t * n + k] = work[((size_t)(oY + k) * NC) * (size_t)stride + t];
+    const long long g = idx ? idx[t] : t;
+    for (int k = 0; k < n; k++) out[g * n + k] = work[((size_t)(oY + k) * NC) * (size_t)stride + t];
+}
+
+// trajectories that outgrew a capacity that is final: ReturnCode.Failure, like max_num_subintervals does
+static __global__ void k_ensemble_mark_failed(long long cnt, const long long* __restrict__ idx, int* __restrict__ retcode,
+                                       int* __restrict__ n_mesh) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    retcode[idx[t]] = MIRK_RET_FAILURE_;
+    n_mesh[idx[t]] = 0;
 }
 
 }  // namespace mirk

@@ -25,6 +25,92 @@ __global__ void k_axpy_neg(size_t len, double* __restrict__ y, const double* __r
     if (i < len) y[i] -= d[i];
 }
 
+// ---- small vector kernels of the line-search / trust-region fallbacks of the Newton polyalgorithm (failure paths
+// only: simple mappings, deterministic reductions so that accept / reject decisions repeat from run to run) --------
+__global__ void k_axpby(size_t len, double* __restrict__ out, double a, const double* __restrict__ x, double b,
+                        const double* __restrict__ y) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) out[i] = a * x[i] + b * y[i];
+}
+// out[0] = a . b, out[1] = min(a), out[2] = max(a): one block, fixed summation order
+__global__ void __launch_bounds__(1024) k_dot_minmax(size_t len, const double* __restrict__ a, const double* __restrict__ b,
+                                                     double* __restrict__ out) {
+    __shared__ double sd[1024], smn[1024], smx[1024];
+    double acc = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (size_t i = threadIdx.x; i < len; i += blockDim.x) {
+        const double v = a[i];
+        acc += v * b[i];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    sd[threadIdx.x] = acc; smn[threadIdx.x] = mn; smx[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sd[threadIdx.x] += sd[threadIdx.x + o];
+            smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + o]);
+            smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sd[0]; out[1] = smn[0]; out[2] = smx[0]; }
+}
+// |delta|_2^2 and |y|_2^2 of a Newton step into out[0], out[1] (zeroed by the caller): feeds the stalled-step rule of
+// the termination test (only compared against thresholds many orders away, so the atomic summation order is harmless)
+__global__ void __launch_bounds__(256) k_step_norms(size_t len, const double* __restrict__ delta, const double* __restrict__ y,
+                                                    double* __restrict__ out) {
+    double a = 0.0, b = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        a += delta[i] * delta[i];
+        b += y[i] * y[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+// residual-row index of boundary row q: Standard [bc; Phi], TwoPoint [bc_a; Phi; bc_b]
+__device__ __forceinline__ size_t bc_row(int q, int La, int N, int n) {
+    return q < La ? (size_t)q : (size_t)La + (size_t)(N - 1) * n + (q - La);
+}
+// out = J v on the block structure (Jacobian blocks of the last evaluation): one thread per residual row
+__global__ void k_jvec(int n, int N, int L, int La, const double* __restrict__ Lb, const double* __restrict__ Rb,
+                       const int* __restrict__ m_ptr, const int* __restrict__ bc_nodes, const double* __restrict__ Bc,
+                       const double* __restrict__ v, double* __restrict__ out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nphi = (size_t)(N - 1) * n;
+    if (e < nphi) {
+        const size_t i = e / n;
+        const int r = (int)(e % n);
+        const double *lr = Lb + (i * n + r) * n, *rr = Rb + (i * n + r) * n, *vi = v + i * n;
+        double acc = 0.0;
+        for (int j = 0; j < n; j++) acc += lr[j] * vi[j] + rr[j] * vi[n + j];
+        out[La + e] = acc;
+    } else if (e < nphi + L) {
+        const int q = (int)(e - nphi), m = *m_ptr;
+        double acc = 0.0;
+        for (int k = 0; k < m; k++)
+            for (int j = 0; j < n; j++) acc += Bc[((size_t)k * L + q) * n + j] * v[(size_t)bc_nodes[k] * n + j];
+        out[bc_row(q, La, N, n)] = acc;
+    }
+}
+// out = J^T w: one thread per unknown (node i, component j)
+__global__ void k_jtvec(int n, int N, int L, int La, const double* __restrict__ Lb, const double* __restrict__ Rb,
+                        const int* __restrict__ m_ptr, const int* __restrict__ bc_nodes, const double* __restrict__ Bc,
+                        const double* __restrict__ w, double* __restrict__ out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)N * n) return;
+    const size_t i = e / n;
+    const int j = (int)(e % n), m = *m_ptr;
+    double acc = 0.0;
+    if (i < (size_t)N - 1)
+        for (int r = 0; r < n; r++) acc += Lb[(i * n + r) * n + j] * w[La + i * n + r];
+    if (i > 0)
+        for (int r = 0; r < n; r++) acc += Rb[((i - 1) * n + r) * n + j] * w[La + (i - 1) * n + r];
+    for (int k = 0; k < m; k++)
+        if ((size_t)bc_nodes[k] == i)
+            for (int q = 0; q < L; q++) acc += Bc[((size_t)k * L + q) * n + j] * w[bc_row(q, La, N, n)];
+    out[e] = acc;
+}
+
 __global__ void k_fill_nodes(int N, int n, const double* __restrict__ u0, double* __restrict__ y) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (size_t)N * n) y[i] = u0[i % n];

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@
 #include "abd_pair.cuh"
 #include "abd_warp.cuh"
 #include "ensemble.cuh"
+#include "ensemble_warp.cuh"
 #include "generic_kernels.cuh"
 #include "mirk_b200.h"
 #include "ops.cuh"
@@ -179,6 +181,11 @@ struct mirk_solver_s {
            *delta = nullptr, *p = nullptr, *Bc = nullptr, *scratch = nullptr, *Mfinal = nullptr,
            *tbuf = nullptr, *obuf = nullptr, *jscratch = nullptr;
     size_t jscratch_cap = 0;
+    // Newton polyalgorithm (line-search / trust-region fallbacks): work vectors allocated on first use, scalars
+    double *nl_y0 = nullptr, *nl_yb = nullptr, *nl_up = nullptr, *nl_du = nullptr, *nl_g = nullptr, *nl_fu = nullptr,
+           *nl_Jg = nullptr, *nl_sc = nullptr;
+    size_t nl_cap = 0;
+    double* h_sc = nullptr;  // pinned: scalar results of the reductions
     int *bc_nodes = nullptr, *m_dev = nullptr, *iold = nullptr, *sel_out = nullptr;
     size_t scratch_cap = 0, Mfinal_cap = 0, tbuf_cap = 0;
     // host-visible words: [0] residual norm bits, [1] defect bits, [2] status
@@ -205,6 +212,7 @@ struct mirk_solver_s {
            *if_delta = nullptr, *if_Bc = nullptr, *if_resid = nullptr;
     int *if_bc_nodes = nullptr, *if_m = nullptr;
     bool jac_valid = false, resid_valid = false;
+    int nl_steps[3] = {-1, -1, -1}, nl_rets[3] = {-1, -1, -1};  // per sub-solver of the last nonlinear solve (-1: did not run)
     // lazy zeroing of the stage arrays after a guess upload: Kd is fully rewritten by the first residual pass (only a
     // reader that runs before any residual needs the zeros), Ki only has to be cleared if something wrote it
     bool kd_stale = true, ki_dirty = true;
@@ -769,15 +777,92 @@ static int read_words(mirk_solver_s* S) {
     return MIRK_OK;
 }
 
-// NewtonRaphson with |F|_inf <= abstol termination and best-iterate bookkeeping; same control flow
-// as oracle/mirk_oracle.c orc_newton (from-memory restatement of NonlinearSolve).
-static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* ret_out) {
-    const size_t ybytes = (size_t)S->N * S->n * sizeof(double);
-    const double abstol = S->desc.abstol;
-    const int maxiters = S->desc.maxiters;
-    int ret = MIRK_RET_MAXITERS, it = 0;
-    double best = INFINITY;
+// ---- the nonlinear solve: the reference's default NonlinearSolvePolyAlgorithm(NewtonRaphson, NewtonRaphson +
+// BackTracking, TrustRegion) (CORE/default_internal_solve.jl:31-45; sub-solvers and their termination restated from
+// memory exactly as in oracle/mirk_oracle.c orc_nlsolve — same control flow line for line, parity unpinned against a
+// Julia run).  NewtonRaphson is the hot path (graph-replayed fused kernels); the two fallbacks only run when it
+// fails and use small generic kernels (J v, J^T w, dot products) with scalar read-backs.
+
+// AbsNormSafeBest termination (NonlinearSolveBase): Success / Unstable / Stalled, -1 = continue
+struct NlTerm {
+    double abstol, reltol, best = INFINITY, trace[100];
+    int nsteps = 0, stall_counter = 0;
     bool have_best = false;
+    explicit NlTerm(double abstol_) : abstol(abstol_), reltol(pow(2.220446049250313e-16, 0.8)) {}
+    // du2 = |u - u_prev|_2, u2 = |u|_2; *improved tells the caller to save the iterate as the best one
+    int check(double objective, double du2, double u2, bool* improved) {
+        *improved = false;
+        if (!std::isfinite(objective)) return MIRK_RET_UNSTABLE;
+        if (objective < best) { best = objective; have_best = true; *improved = true; }
+        if (objective <= abstol) return MIRK_RET_SUCCESS;
+        nsteps++;
+        trace[(nsteps - 1) % 100] = objective;
+        if (objective <= 3.0 * abstol && nsteps >= 100) {
+            double mn = INFINITY, mx = -INFINITY;
+            for (int i = 0; i < 100; i++) { mn = std::min(mn, trace[i]); mx = std::max(mx, trace[i]); }
+            if (mn < 1.3 * mx) return MIRK_RET_STALLED;
+        }
+        if (du2 <= abstol && du2 <= reltol * u2) stall_counter++; else stall_counter = 0;
+        if (stall_counter >= 32) return MIRK_RET_STALLED;
+        return -1;
+    }
+};
+
+static int ensure_nl_buffers(mirk_solver_s* S) {
+    const size_t nu = (size_t)S->Ncap * S->n, nr = nu + (size_t)S->n;
+    if (!S->h_sc) CK(cudaMallocHost((void**)&S->h_sc, 8 * sizeof(double)));
+    if (!S->nl_sc) CK(dalloc(&S->nl_sc, 8));
+    if (S->nl_cap >= nu) return MIRK_OK;
+    dfree(S->nl_y0); dfree(S->nl_yb); dfree(S->nl_up); dfree(S->nl_du); dfree(S->nl_g); dfree(S->nl_fu); dfree(S->nl_Jg);
+    CK(dalloc(&S->nl_y0, nu)); CK(dalloc(&S->nl_yb, nu)); CK(dalloc(&S->nl_up, nu)); CK(dalloc(&S->nl_du, nu));
+    CK(dalloc(&S->nl_g, nu)); CK(dalloc(&S->nl_fu, nr)); CK(dalloc(&S->nl_Jg, nr));
+    S->nl_cap = nu;
+    return MIRK_OK;
+}
+// |delta|_2^2 and |y|_2^2 of the step just taken (stalled-step rule of the termination test): launched behind the
+// update, read back together with the norm words — no extra host synchronisation
+static int launch_step_norms(mirk_solver_s* S) {
+    if (!S->nl_sc) CK(dalloc(&S->nl_sc, 8));
+    if (!S->h_sc) CK(cudaMallocHost((void**)&S->h_sc, 8 * sizeof(double)));
+    const size_t len = (size_t)S->N * S->n;
+    CK(cudaMemsetAsync(S->nl_sc, 0, 2 * sizeof(double), S->st));
+    k_step_norms<<<std::max(1, std::min(S->sm_count, (int)((len + 255) / 256))), 256, 0, S->st>>>(len, S->delta, S->y, S->nl_sc);
+    S->launches++;
+    CK(cudaMemcpyAsync(S->h_sc, S->nl_sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    return launch_check("step_norms");
+}
+static int dev_dot(mirk_solver_s* S, const double* a, const double* b, size_t len, double* dot, double* mn = nullptr,
+                   double* mx = nullptr) {
+    k_dot_minmax<<<1, 1024, 0, S->st>>>(len, a, b, S->nl_sc + 4);
+    S->launches++;
+    CK(cudaMemcpyAsync(S->h_sc + 4, S->nl_sc + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    *dot = S->h_sc[4];
+    if (mn) *mn = S->h_sc[5];
+    if (mx) *mx = S->h_sc[6];
+    return launch_check("dot");
+}
+static void dev_axpby(mirk_solver_s* S, double* out, double a, const double* x, double b, const double* y, size_t len) {
+    k_axpby<<<(unsigned)((len + 255) / 256), 256, 0, S->st>>>(len, out, a, x, b, y);
+    S->launches++;
+}
+static void dev_jvec(mirk_solver_s* S, const double* v, double* out) {
+    const size_t rows = (size_t)(S->N - 1) * S->n + S->L;
+    k_jvec<<<(unsigned)((rows + 127) / 128), 128, 0, S->st>>>(S->n, S->N, S->L, S->La, S->Lb, S->Rb, S->m_dev, S->bc_nodes, S->Bc, v, out);
+    S->launches++;
+}
+static void dev_jtvec(mirk_solver_s* S, const double* w, double* out) {
+    const size_t len = (size_t)S->N * S->n;
+    k_jtvec<<<(unsigned)((len + 127) / 128), 128, 0, S->st>>>(S->n, S->N, S->L, S->La, S->Lb, S->Rb, S->m_dev, S->bc_nodes, S->Bc, w, out);
+    S->launches++;
+}
+
+// NewtonRaphson (sub-solver 1): the graph-replayed hot path
+static int newton_raphson(mirk_solver_s* S, int* iters_out, double* nrm_out, int* ret_out) {
+    const size_t ybytes = (size_t)S->N * S->n * sizeof(double);
+    const int maxiters = S->desc.maxiters;
+    NlTerm term(S->desc.abstol);
+    int ret = MIRK_RET_MAXITERS, it = 0;
     if (maxiters > 0) CKS(eval_resjac(S)); else CKS(eval_residual(S));
     CKS(read_words(S));
     double nrm = bits_to_double(S->h_words[0]);
@@ -785,27 +870,246 @@ static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* 
         CKS(linear_solve(S, true));
         CKS(apply_update(S));
         it++;
+        if (!S->part) CKS(launch_step_norms(S));  // (a partitioned handle would need a cross-rank sum: rule not applied there)
         CKS(eval_resjac(S));  // F and J at the new iterate; J is unused only on the converged last pass
         CKS(read_words(S));
-        if (S->h_words[2] != 0ull) {  // singular block met by the elimination
+        if (S->h_words[2] != 0ull) {  // singular block met by the elimination (or a peer timed out)
             ret = MIRK_RET_FAILURE;
             nrm = bits_to_double(S->h_words[0]);
             break;
         }
         nrm = bits_to_double(S->h_words[0]);
-        if (!std::isfinite(nrm)) { ret = MIRK_RET_UNSTABLE; break; }
-        if (nrm < best) {
-            best = nrm;
-            have_best = true;
-            CK(cudaMemcpyAsync(S->y_best, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
-        }
-        if (nrm <= abstol) { ret = MIRK_RET_SUCCESS; break; }
+        const double du2 = S->part ? INFINITY : sqrt(S->h_sc[0]), u2 = S->part ? 0.0 : sqrt(S->h_sc[1]);
+        bool improved = false;
+        const int tc = term.check(nrm, du2, u2, &improved);
+        if (improved) CK(cudaMemcpyAsync(S->y_best, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        if (tc >= 0) { ret = tc; break; }
     }
-    if (ret != MIRK_RET_SUCCESS && it > 0 && have_best && ret != MIRK_RET_FAILURE) {
+    if (ret != MIRK_RET_SUCCESS && it > 0 && term.have_best && ret != MIRK_RET_FAILURE) {
         CK(cudaMemcpyAsync(S->y, S->y_best, ybytes, cudaMemcpyDeviceToDevice, S->st));
         CKS(eval_residual(S));
         CKS(read_words(S));
         nrm = bits_to_double(S->h_words[0]);
+    }
+    *iters_out = it;
+    *nrm_out = nrm;
+    *ret_out = ret;
+    return MIRK_OK;
+}
+
+// F(y) into S->resid and |F|_inf (one host sync)
+static int residual_norm(mirk_solver_s* S, double* nrm) {
+    CKS(eval_residual(S));
+    CKS(read_words(S));
+    *nrm = bits_to_double(S->h_words[0]);
+    return MIRK_OK;
+}
+// phi(alpha) = |F(y_prev + alpha du)|_2^2 / 2, leaving the trial point in S->y and F in S->resid
+static int phi_at(mirk_solver_s* S, double alpha, double* phi) {
+    const size_t nu = (size_t)S->N * S->n, nr = nu - S->n + S->L;
+    dev_axpby(S, S->y, 1.0, S->nl_up, alpha, S->nl_du, nu);
+    S->jac_valid = false;
+    CKS(eval_residual(S));
+    double d = 0;
+    CKS(dev_dot(S, S->resid, S->resid, nr, &d));
+    *phi = 0.5 * d;
+    return MIRK_OK;
+}
+// LineSearches.BackTracking (order 3); returns alpha (NAN on failure) — oracle: nl_backtracking
+static int backtracking(mirk_solver_s* S, double phi_0, double dphi_0, double* alpha_out) {
+    const double c_1 = 1e-4, rho_hi = 0.5, rho_lo = 0.1;
+    auto nan_min = [](double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : std::min(a, b); };
+    auto nan_max = [](double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : std::max(a, b); };
+    double a1 = 1.0, a2 = 1.0, phx0 = phi_0, phx1 = 0;
+    CKS(phi_at(S, a1, &phx1));
+    int iterfinite = 0;
+    while (!std::isfinite(phx1) && iterfinite < 52) { iterfinite++; a1 = a2; a2 = a1 / 2.0; CKS(phi_at(S, a2, &phx1)); }
+    int iteration = 0;
+    *alpha_out = NAN;
+    while (phx1 > phi_0 + c_1 * a2 * dphi_0) {
+        iteration++;
+        if (iteration > 1000) return MIRK_OK;
+        double atmp;
+        if (iteration == 1) {
+            atmp = -(dphi_0 * a2 * a2) / (2.0 * (phx1 - phi_0 - dphi_0 * a2));
+        } else {
+            const double div = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+            const double a = (a1 * a1 * (phx1 - phi_0 - dphi_0 * a2) - a2 * a2 * (phx0 - phi_0 - dphi_0 * a1)) * div;
+            const double b = (-a1 * a1 * a1 * (phx1 - phi_0 - dphi_0 * a2) + a2 * a2 * a2 * (phx0 - phi_0 - dphi_0 * a1)) * div;
+            if (fabs(a) <= 2.220446049250313e-16) atmp = dphi_0 / (2.0 * b);
+            else { double d = b * b - 3.0 * a * dphi_0; if (d < 0.0) d = 0.0; atmp = (-b + sqrt(d)) / (3.0 * a); }
+        }
+        a1 = a2;
+        atmp = nan_min(atmp, a2 * rho_hi);
+        a2 = nan_max(atmp, a2 * rho_lo);
+        phx0 = phx1;
+        CKS(phi_at(S, a2, &phx1));
+        if (std::isnan(a2)) return MIRK_OK;
+    }
+    *alpha_out = a2;
+    return MIRK_OK;
+}
+
+// sub-solvers 2 (NewtonRaphson + BackTracking) and 3 (TrustRegion) from the iterate in S->y — oracle: nl_run
+static int nl_fallback(mirk_solver_s* S, int alg, int* iters_out, double* nrm_out, int* ret_out) {
+    CKS(ensure_nl_buffers(S));
+    const size_t nu = (size_t)S->N * S->n, nr = nu - S->n + S->L, ybytes = nu * sizeof(double), rbytes = nr * sizeof(double);
+    const int maxiters = S->desc.maxiters;
+    NlTerm term(S->desc.abstol);
+    int ret = MIRK_RET_MAXITERS, it = 0;
+    double nrm = 0;
+    CKS(residual_norm(S, &nrm));
+    double Delta = 0.0, Delta_max = 0.0;
+    int shrink_counter = 0;
+    bool have_jac = false;
+    if (alg == 3) {
+        double yy = 0, umin = 0, umax = 0, ff = 0;
+        CKS(dev_dot(S, S->y, S->y, nu, &yy, &umin, &umax));
+        CKS(dev_dot(S, S->resid, S->resid, nr, &ff));
+        Delta_max = std::max(sqrt(ff), umax - umin);
+        Delta = Delta_max / 11.0;
+    }
+    while (it < maxiters) {
+        CK(cudaMemcpyAsync(S->nl_up, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        if (alg != 3 || !have_jac) { CKS(eval_resjac(S)); have_jac = true; }  // (also re-evaluates F(y): same values)
+        CKS(linear_solve(S, false));
+        CKS(read_words(S));
+        if (S->h_words[2] != 0ull) { ret = MIRK_RET_FAILURE; break; }
+        dev_axpby(S, S->nl_du, -1.0, S->delta, 0.0, S->delta, nu);  // Newton direction
+        double du2 = 0, u2 = 0;
+        if (alg == 2) {
+            dev_jvec(S, S->nl_du, S->nl_Jg);
+            double ff = 0, dphi_0 = 0, alpha = NAN;
+            CKS(dev_dot(S, S->resid, S->resid, nr, &ff));
+            CKS(dev_dot(S, S->resid, S->nl_Jg, nr, &dphi_0));
+            CKS(backtracking(S, 0.5 * ff, dphi_0, &alpha));
+            if (std::isnan(alpha)) {  // InternalLineSearchFailed: the sub-solver ends where it stood
+                CK(cudaMemcpyAsync(S->y, S->nl_up, ybytes, cudaMemcpyDeviceToDevice, S->st));
+                ret = MIRK_RET_FAILURE;
+                break;
+            }
+            // S->y = y_prev + alpha du and S->resid = F(S->y) are what the accepted trial left behind
+            double dd = 0;
+            CKS(dev_dot(S, S->nl_du, S->nl_du, nu, &dd));
+            du2 = alpha * sqrt(dd);
+        } else {
+            CK(cudaMemcpyAsync(S->nl_fu, S->resid, rbytes, cudaMemcpyDeviceToDevice, S->st));  // F(y) survives the trial
+            double nN2 = 0;
+            CKS(dev_dot(S, S->nl_du, S->nl_du, nu, &nN2));
+            if (!(sqrt(nN2) <= Delta)) {
+                dev_jtvec(S, S->nl_fu, S->nl_g);
+                dev_axpby(S, S->nl_g, -1.0, S->nl_g, 0.0, S->nl_g, nu);  // steepest descent direction
+                double gg = 0, JgJg = 0;
+                CKS(dev_dot(S, S->nl_g, S->nl_g, nu, &gg));
+                dev_jvec(S, S->nl_g, S->nl_Jg);
+                CKS(dev_dot(S, S->nl_Jg, S->nl_Jg, nr, &JgJg));
+                const double lg = sqrt(gg), dc = lg * lg * lg / JgJg;
+                if (dc >= Delta) {
+                    dev_axpby(S, S->nl_du, Delta / lg, S->nl_g, 0.0, S->nl_g, nu);
+                } else {
+                    dev_axpby(S, S->nl_g, dc / lg, S->nl_g, 0.0, S->nl_g, nu);       // Cauchy point
+                    dev_axpby(S, S->nl_du, 1.0, S->nl_du, -1.0, S->nl_g, nu);        // du <- Newton - Cauchy
+                    double aa = 0, bb = 0;
+                    CKS(dev_dot(S, S->nl_du, S->nl_du, nu, &aa));
+                    CKS(dev_dot(S, S->nl_du, S->nl_g, nu, &bb));
+                    const double cc = dc * dc - Delta * Delta;
+                    const double tau = (-bb + sqrt(std::max(0.0, bb * bb - aa * cc))) / aa;
+                    dev_axpby(S, S->nl_du, 1.0, S->nl_g, tau, S->nl_du, nu);
+                }
+            }
+            dev_axpby(S, S->y, 1.0, S->nl_up, 1.0, S->nl_du, nu);  // trial point
+            S->jac_valid = false;
+            double ntrial = 0;
+            CKS(residual_norm(S, &ntrial));
+            dev_jvec(S, S->nl_du, S->nl_Jg);
+            dev_jtvec(S, S->nl_fu, S->nl_g);
+            double f0 = 0, f1 = 0, dg = 0, JJ = 0, dd = 0;
+            CKS(dev_dot(S, S->nl_fu, S->nl_fu, nr, &f0));
+            CKS(dev_dot(S, S->resid, S->resid, nr, &f1));
+            CKS(dev_dot(S, S->nl_du, S->nl_g, nu, &dg));
+            CKS(dev_dot(S, S->nl_Jg, S->nl_Jg, nr, &JJ));
+            CKS(dev_dot(S, S->nl_du, S->nl_du, nu, &dd));
+            const double rho = 0.5 * (f0 - f1) / (-(dg + 0.5 * JJ));
+            const bool accept = rho > 1e-4;
+            if (rho < 0.25) { Delta *= 0.25; shrink_counter++; }
+            else { shrink_counter = 0; if (rho > 0.75) Delta = std::min(2.0 * Delta, Delta_max); }
+            if (accept) {
+                have_jac = false;
+                du2 = sqrt(dd);
+            } else {
+                // rejected: stay, keep the Jacobian blocks; stages and F must again belong to y
+                CK(cudaMemcpyAsync(S->y, S->nl_up, ybytes, cudaMemcpyDeviceToDevice, S->st));
+                double dummy = 0;
+                CKS(residual_norm(S, &dummy));
+                du2 = 0.0;
+            }
+            if (shrink_counter > 32) { it++; ret = MIRK_RET_FAILURE; break; }  // ShrinkThresholdExceeded
+        }
+        it++;
+        CKS(read_words(S));
+        nrm = bits_to_double(S->h_words[0]);
+        double yy = 0;
+        CKS(dev_dot(S, S->y, S->y, nu, &yy));
+        u2 = sqrt(yy);
+        bool improved = false;
+        const int tc = term.check(nrm, du2, u2, &improved);
+        if (improved) CK(cudaMemcpyAsync(S->y_best, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        if (tc >= 0) { ret = tc; break; }
+    }
+    if (ret != MIRK_RET_SUCCESS && it > 0 && term.have_best) {
+        CK(cudaMemcpyAsync(S->y, S->y_best, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        CKS(residual_norm(S, &nrm));
+    }
+    S->jac_valid = false;
+    *iters_out = it;
+    *nrm_out = nrm;
+    *ret_out = ret;
+    return MIRK_OK;
+}
+
+// desc.nlsolve: 0 the default polyalgorithm, 1 NewtonRaphson, 2 NewtonRaphson + BackTracking, 3 TrustRegion.
+// iters counts the steps of every sub-solver that ran (oracle: orc_nlsolve).
+static int newton_solve(mirk_solver_s* S, int* iters_out, double* nrm_out, int* ret_out) {
+    const int which = S->part ? 1 : S->desc.nlsolve;  // (mesh-partitioned handles: NewtonRaphson only)
+    int it = 0, ret = MIRK_RET_FAILURE;
+    double nrm = 0;
+    for (int k = 0; k < 3; k++) S->nl_steps[k] = S->nl_rets[k] = -1;
+    if (which == 1) {
+        CKS(newton_raphson(S, &it, &nrm, &ret));
+        S->nl_steps[0] = it; S->nl_rets[0] = ret;
+    } else if (which == 2 || which == 3) {
+        CKS(nl_fallback(S, which, &it, &nrm, &ret));
+        S->nl_steps[which - 1] = it; S->nl_rets[which - 1] = ret;
+    } else {
+        const size_t ybytes = (size_t)S->N * S->n * sizeof(double);
+        CKS(ensure_nl_buffers(S));
+        CK(cudaMemcpyAsync(S->nl_y0, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+        int total = 0, best_ret = MIRK_RET_FAILURE;
+        double best = INFINITY;
+        bool done = false;
+        for (int alg = 1; alg <= 3 && !done; alg++) {
+            int k = 0, r = 0;
+            double nr_ = 0;
+            if (alg > 1) {
+                CK(cudaMemcpyAsync(S->y, S->nl_y0, ybytes, cudaMemcpyDeviceToDevice, S->st));
+                S->jac_valid = S->resid_valid = false;
+            }
+            if (alg == 1) CKS(newton_raphson(S, &k, &nr_, &r)); else CKS(nl_fallback(S, alg, &k, &nr_, &r));
+            S->nl_steps[alg - 1] = k; S->nl_rets[alg - 1] = r;
+            total += k;
+            if (r == MIRK_RET_SUCCESS) { ret = r; nrm = nr_; done = true; break; }
+            if (alg == 1 || !(nr_ >= best)) {
+                best = nr_;
+                best_ret = r;
+                CK(cudaMemcpyAsync(S->nl_yb, S->y, ybytes, cudaMemcpyDeviceToDevice, S->st));
+            }
+        }
+        if (!done) {  // all failed: the sub-solver that got closest provides the iterate and the return code
+            CK(cudaMemcpyAsync(S->y, S->nl_yb, ybytes, cudaMemcpyDeviceToDevice, S->st));
+            CKS(residual_norm(S, &nrm));
+            ret = best_ret;
+        }
+        it = total;
     }
     S->last_resid_norm = nrm;
     *iters_out = it;
@@ -1060,6 +1364,9 @@ int mirk_destroy(mirk_handle S) {
     if (S->st) cudaStreamSynchronize(S->st);
     free_buffers(S);
     dfree(S->jscratch);
+    dfree(S->nl_y0); dfree(S->nl_yb); dfree(S->nl_up); dfree(S->nl_du); dfree(S->nl_g); dfree(S->nl_fu); dfree(S->nl_Jg);
+    dfree(S->nl_sc);
+    if (S->h_sc) cudaFreeHost(S->h_sc);
     dfree(S->p); dfree(S->Bc); dfree(S->scratch); dfree(S->Mfinal); dfree(S->tbuf); dfree(S->obuf);
     dfree(S->bc_nodes); dfree(S->m_dev); dfree(S->sel_out); dfree(S->words);
     dfree(S->plan.d_int); dfree(S->plan.d_rel);
@@ -1103,6 +1410,7 @@ int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     S->desc = *desc;
     S->desc.params = nullptr;
     if (S->desc.maxiters < 0) S->desc.maxiters = 0;
+    if (S->desc.nlsolve < 0 || S->desc.nlsolve > 3) { delete S; return fail(MIRK_ERR_ARG, "nlsolve must be 0 (default polyalgorithm), 1, 2 or 3"); }
     S->ops = ops;
     S->n = ops->n; S->L = ops->n_bc; S->s = ops->s; S->si = ops->s_star - ops->s;
     S->La = ops->problem_type == 1 ? ops->n_bca : ops->n_bc;
@@ -1305,6 +1613,15 @@ int mirk_newton_solve(mirk_handle S, int32_t* iters, double* resid_norm) {
     if (iters) *iters = it;
     if (resid_norm) *resid_norm = nrm;
     return ret;
+}
+
+int mirk_nlsolve_stats(mirk_handle S, int32_t* steps3, int32_t* retcodes3) {
+    if (!S) return fail(MIRK_ERR_ARG, "NULL handle");
+    for (int k = 0; k < 3; k++) {
+        if (steps3) steps3[k] = S->nl_steps[k];
+        if (retcodes3) retcodes3[k] = S->nl_rets[k];
+    }
+    return MIRK_OK;
 }
 
 int mirk_defect(mirk_handle S, double* errors, double* defect_norm) {
@@ -1602,6 +1919,20 @@ struct mirk_ensemble_s {
     int *retcode = nullptr, *n_mesh = nullptr, *newton_iters = nullptr, *outer_iters = nullptr;
     int u0_per_traj = 0;
     bool have_inputs = false, ran = false;
+    // warp-per-trajectory mode (on-chip state, n <= 2): NCs = on-chip node capacity, NC = the final capacity a
+    // trajectory may reach (overflowing ones are re-run through the HBM-slab kernel)
+    bool warp_mode = false;
+    int NCs = 0;
+    unsigned long long* counters = nullptr;  // [0] work counter, [1] overflow count
+    long long* overflow_list = nullptr;
+    double *out_mesh = nullptr, *out_y = nullptr;
+    std::vector<long long> h_overflow;        // overflowed trajectories of the last run, sorted (slab slot = position)
+    // trajectories whose plain Newton solve failed under the default polyalgorithm: re-run on `single` (mirk_solve)
+    unsigned long long* poly_count = nullptr;
+    long long* poly_list = nullptr;
+    mirk_handle single = nullptr;
+    std::map<long long, std::pair<std::vector<double>, std::vector<double>>> poly_sol;  // traj -> (mesh, y)
+    size_t work_cap = 0;                      // doubles allocated in `work`
 };
 
 static const EnsembleOps* find_ensemble_ops(int id, int order) {
@@ -1615,6 +1946,9 @@ int mirk_ensemble_destroy(mirk_ensemble_handle E) {
     if (!E) return MIRK_OK;
     cudaSetDevice(E->desc.device);
     if (E->st) cudaStreamSynchronize(E->st);
+    dfree(E->counters); dfree(E->overflow_list); dfree(E->out_mesh); dfree(E->out_y);
+    dfree(E->poly_count); dfree(E->poly_list);
+    if (E->single) mirk_destroy(E->single);
     dfree(E->work); dfree(E->params); dfree(E->u0); dfree(E->mesh0); dfree(E->resid_norm); dfree(E->defect_norm);
     dfree(E->y_first); dfree(E->tmesh); dfree(E->ty); dfree(E->retcode); dfree(E->n_mesh); dfree(E->newton_iters);
     dfree(E->outer_iters);
@@ -1642,7 +1976,14 @@ int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ens
     CK(cudaSetDevice(desc->device));
     const int nint = (int)ceil((desc->t1 - desc->t0) / desc->dt);  // cld(t1 - t0, dt), CORE/utils.jl:362
     const int N0 = nint + 1;
-    int NC = desc->node_cap > 0 ? desc->node_cap : 128;
+    // warp-per-trajectory kernel (state in shared memory) where it is instantiated; MIRK_ENS_KERNEL=thread keeps the
+    // thread-per-trajectory HBM-slab kernel for A/B runs
+    static const bool force_thread = getenv("MIRK_ENS_KERNEL") && !strcmp(getenv("MIRK_ENS_KERNEL"), "thread");
+    const bool warp_mode = ops->run_warp != nullptr && !force_thread;
+    // capacity in nodes a trajectory may reach: node_cap when given, else what max_num_subintervals allows (warp mode:
+    // only trajectories that outgrow the on-chip capacity ever touch an HBM slab) / 128 (thread mode: every trajectory
+    // owns a slab of that many nodes)
+    int NC = desc->node_cap > 0 ? desc->node_cap : (warp_mode ? desc->max_num_subintervals + 1 : 128);
     if (NC < N0) NC = N0;
     mirk_ensemble_s* E = new mirk_ensemble_s();
     E->desc = *desc;
@@ -1651,6 +1992,14 @@ int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ens
     E->stride = (ntraj + 31) / 32 * 32;
     E->NC = NC;
     E->N0 = N0;
+    E->warp_mode = warp_mode;
+    if (warp_mode) {
+        static const int smem_nodes = getenv("MIRK_ENS_SMEM_NODES") ? atoi(getenv("MIRK_ENS_SMEM_NODES")) : 64;  // measured best on C3 (16 warps per SM); larger meshes overflow to HBM slabs
+        int ncs = std::max(smem_nodes, N0);
+        while (ncs > N0 && ops->warp_smem_bytes(ncs) > (size_t)220 * 1024) ncs--;
+        if (ops->warp_smem_bytes(ncs) > (size_t)220 * 1024) E->warp_mode = false;  // initial mesh alone does not fit on chip
+        E->NCs = std::min(ncs, NC);
+    }
 #define CKE(call)                                                                       \
     do {                                                                                \
         cudaError_t e2 = (call);                                                        \
@@ -1660,7 +2009,17 @@ int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ens
         }                                                                               \
     } while (0)
     CKE(cudaStreamCreateWithFlags(&E->st, cudaStreamNonBlocking));
-    CKE(dalloc(&E->work, (size_t)ops->slots_per_node * NC * (size_t)E->stride));
+    if (!E->warp_mode) {
+        E->work_cap = (size_t)ops->slots_per_node * NC * (size_t)E->stride;
+        CKE(dalloc(&E->work, E->work_cap));
+    } else {
+        CKE(dalloc(&E->counters, 2));
+        CKE(dalloc(&E->overflow_list, (size_t)ntraj));
+        CKE(dalloc(&E->out_mesh, (size_t)ntraj * E->NCs));
+        CKE(dalloc(&E->out_y, (size_t)ntraj * E->NCs * ops->n));
+    }
+    CKE(dalloc(&E->poly_count, 1));
+    CKE(dalloc(&E->poly_list, (size_t)ntraj));
     CKE(dalloc(&E->params, (size_t)ntraj * std::max(ops->np, 1)));
     CKE(dalloc(&E->u0, (size_t)ntraj * ops->n));
     CKE(dalloc(&E->mesh0, (size_t)N0));
@@ -1719,16 +2078,70 @@ int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
     a.adaptive = E->desc.adaptive; a.max_sub = E->desc.max_num_subintervals;
     a.maxiters = E->desc.maxiters < 0 ? 0 : E->desc.maxiters; a.reinterp_inplace = E->desc.reinterp_inplace;
     a.max_outer = kMaxOuter;
+    a.nlsolve = E->desc.nlsolve == 1 ? 1 : 0;
+    a.poly_count = E->poly_count;
+    a.poly_list = E->poly_list;
+    CK(cudaMemsetAsync(E->poly_count, 0, sizeof(unsigned long long), E->st));
+    E->poly_sol.clear();
     a.work = E->work;
     a.retcode = E->retcode; a.n_mesh = E->n_mesh; a.newton_iters = E->newton_iters; a.outer_iters = E->outer_iters;
     a.resid_norm = E->resid_norm; a.defect_norm = E->defect_norm;
+    a.idx = nullptr;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, E->st));
-    E->ops->run(E->st, a);
-    k_ensemble_first<<<(unsigned)((E->ntraj + 255) / 256), 256, 0, E->st>>>(E->ntraj, E->stride, E->NC, E->ops->n,
-                                                                          E->ops->oY, E->work, E->y_first);
+    if (!E->warp_mode) {
+        E->ops->run(E->st, a);
+        k_ensemble_first<<<(unsigned)((E->ntraj + 255) / 256), 256, 0, E->st>>>(E->ntraj, E->stride, E->NC, E->ops->n,
+                                                                              E->ops->oY, E->work, nullptr, E->y_first);
+    } else {
+        EnsWarpArgs w;
+        w.a = a;
+        w.NCs = E->NCs;
+        w.counter = E->counters;
+        w.overflow_count = E->counters + 1;
+        w.overflow_list = E->overflow_list;
+        w.out_mesh = E->out_mesh;
+        w.out_y = E->out_y;
+        w.y_first = E->y_first;
+        CK(cudaMemsetAsync(E->counters, 0, 2 * sizeof(unsigned long long), E->st));
+        CK(E->ops->run_warp(E->st, w));
+        // trajectories whose mesh outgrew the on-chip capacity: re-run them (only them) on HBM slabs of NC nodes
+        unsigned long long novf = 0;
+        CK(cudaMemcpyAsync(&novf, E->counters + 1, sizeof(novf), cudaMemcpyDeviceToHost, E->st));
+        CK(cudaStreamSynchronize(E->st));
+        E->h_overflow.clear();
+        if (novf > 0) {
+            E->h_overflow.resize(novf);
+            CK(cudaMemcpy(E->h_overflow.data(), E->overflow_list, novf * sizeof(long long), cudaMemcpyDeviceToHost));
+            std::sort(E->h_overflow.begin(), E->h_overflow.end());
+            if (E->NC <= E->NCs) {
+                // the on-chip capacity IS the final capacity (node_cap): outgrowing it is a Failure, as in thread mode
+                k_ensemble_mark_failed<<<(unsigned)((novf + 255) / 256), 256, 0, E->st>>>((long long)novf, E->overflow_list, E->retcode,
+                                                                                       E->n_mesh);
+            } else {
+                const size_t stride2 = (novf + 31) / 32 * 32, need = (size_t)E->ops->slots_per_node * E->NC * stride2;
+                if (need * sizeof(double) > ((size_t)96 << 30))
+                    return fail(MIRK_ERR_UNSUPPORTED, "too many trajectories outgrew the on-chip mesh capacity for one HBM slab; "
+                                                      "lower max_num_subintervals or pass node_cap");
+                if (need > E->work_cap) {
+                    dfree(E->work);
+                    CK(dalloc(&E->work, need));
+                    E->work_cap = need;
+                }
+                CK(cudaMemcpyAsync(E->overflow_list, E->h_overflow.data(), novf * sizeof(long long), cudaMemcpyHostToDevice, E->st));
+                EnsArgs b = a;
+                b.ntraj = (long long)novf;
+                b.stride = (long long)stride2;
+                b.work = E->work;
+                b.idx = E->overflow_list;
+                E->ops->run(E->st, b);
+                k_ensemble_first<<<(unsigned)((novf + 255) / 256), 256, 0, E->st>>>((long long)novf, (long long)stride2, E->NC, E->ops->n,
+                                                                                  E->ops->oY, E->work, E->overflow_list, E->y_first);
+            }
+        }
+    }
     CK(cudaEventRecord(e1, E->st));
     CKS(launch_check("ensemble"));
     CK(cudaStreamSynchronize(E->st));
@@ -1736,6 +2149,48 @@ int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    // trajectories whose plain Newton solve failed: the complete adaptive solve again through the single-problem
+    // driver, whose nonlinear solver is the reference's full polyalgorithm (rare; sequential on one handle)
+    unsigned long long npoly = 0;
+    CK(cudaMemcpy(&npoly, E->poly_count, sizeof(npoly), cudaMemcpyDeviceToHost));
+    if (npoly > 0) {
+        std::vector<long long> lst(npoly);
+        CK(cudaMemcpy(lst.data(), E->poly_list, npoly * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int np = std::max(E->ops->np, 1), n = E->ops->n;
+        std::vector<double> hp(np), hu(n);
+        for (long long traj : lst) {
+            CK(cudaMemcpy(hp.data(), E->params + (size_t)traj * np, sizeof(double) * np, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hu.data(), E->u0 + (E->u0_per_traj ? (size_t)traj * n : 0), sizeof(double) * n, cudaMemcpyDeviceToHost));
+            if (!E->single) {
+                mirk_desc d;
+                memset(&d, 0, sizeof(d));
+                d.problem_id = E->desc.problem_id; d.order = E->desc.order; d.abstol = E->desc.abstol;
+                d.adaptive = E->desc.adaptive; d.defect_threshold = E->desc.defect_threshold;
+                d.max_num_subintervals = E->desc.max_num_subintervals; d.maxiters = E->desc.maxiters;
+                d.reinterp_inplace = E->desc.reinterp_inplace; d.device = E->desc.device;
+                d.n_params = E->ops->np; d.params = hp.data(); d.nlsolve = 0;
+                CKS(mirk_create(&d, &E->single));
+            } else {
+                CKS(mirk_set_params(E->single, hp.data(), E->ops->np));
+            }
+            CKS(mirk_set_uniform_guess(E->single, E->desc.t0, E->desc.t1, E->desc.dt, hu.data()));
+            mirk_result R;
+            CKS(mirk_solve(E->single, &R));
+            auto& slot = E->poly_sol[traj];
+            slot.first.resize(R.n_mesh);
+            slot.second.resize((size_t)R.n_mesh * n);
+            CKS(mirk_get_solution(E->single, slot.first.data(), slot.second.data()));
+            CK(cudaSetDevice(E->desc.device));
+            const int rc = R.retcode, nm = R.n_mesh, ni = R.newton_iters, no = R.outer_iters;
+            CK(cudaMemcpy(E->retcode + traj, &rc, sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->n_mesh + traj, &nm, sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->newton_iters + traj, &ni, sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->outer_iters + traj, &no, sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->resid_norm + traj, &R.resid_norm, sizeof(double), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->defect_norm + traj, &R.defect_norm, sizeof(double), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(E->y_first + (size_t)traj * n, slot.second.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+        }
+    }
     if (device_ms) *device_ms = ms;
     E->ran = true;
     return MIRK_OK;
@@ -1769,16 +2224,42 @@ int mirk_ensemble_get_trajectory(mirk_ensemble_handle E, int64_t traj, int32_t* 
     if (!E->ran) return fail(MIRK_ERR_STATE, "ensemble has not been run");
     if (traj < 0 || traj >= E->ntraj) return fail(MIRK_ERR_ARG, "trajectory index out of range");
     CK(cudaSetDevice(E->desc.device));
+    {
+        const auto ps = E->poly_sol.find((long long)traj);
+        if (ps != E->poly_sol.end()) {  // solved by the single-problem driver (polyalgorithm fallback)
+            const int Np = (int)ps->second.first.size();
+            *n_mesh = Np;
+            if (mesh) memcpy(mesh, ps->second.first.data(), sizeof(double) * Np);
+            if (y) memcpy(y, ps->second.second.data(), sizeof(double) * (size_t)Np * E->ops->n);
+            return MIRK_OK;
+        }
+    }
     int N = 0;
     CK(cudaMemcpyAsync(&N, E->n_mesh + traj, sizeof(int), cudaMemcpyDeviceToHost, E->st));
     CK(cudaStreamSynchronize(E->st));
     *n_mesh = N;
     if (mesh || y) {
-        k_ensemble_extract<<<(N + 127) / 128, 128, 0, E->st>>>(E->stride, E->NC, E->ops->n, E->ops->oMESH, E->ops->oY,
-                                                               E->work, traj, N, E->tmesh, E->ty);
-        CKS(launch_check("ensemble_extract"));
-        if (mesh) CK(cudaMemcpyAsync(mesh, E->tmesh, sizeof(double) * N, cudaMemcpyDeviceToHost, E->st));
-        if (y) CK(cudaMemcpyAsync(y, E->ty, sizeof(double) * (size_t)N * E->ops->n, cudaMemcpyDeviceToHost, E->st));
+        const double *src_mesh = E->tmesh, *src_y = E->ty;
+        if (E->warp_mode) {
+            const auto it = std::lower_bound(E->h_overflow.begin(), E->h_overflow.end(), (long long)traj);
+            const bool overflowed = it != E->h_overflow.end() && *it == traj && E->NC > E->NCs;
+            if (overflowed) {  // lives in the HBM slab of the re-run, slot = position in the sorted overflow list
+                const long long slot = it - E->h_overflow.begin();
+                const long long stride2 = ((long long)E->h_overflow.size() + 31) / 32 * 32;
+                k_ensemble_extract<<<(N + 127) / 128, 128, 0, E->st>>>(stride2, E->NC, E->ops->n, E->ops->oMESH, E->ops->oY,
+                                                                       E->work, slot, N, E->tmesh, E->ty);
+                CKS(launch_check("ensemble_extract"));
+            } else {
+                src_mesh = E->out_mesh + (size_t)traj * E->NCs;
+                src_y = E->out_y + (size_t)traj * E->NCs * E->ops->n;
+            }
+        } else {
+            k_ensemble_extract<<<(N + 127) / 128, 128, 0, E->st>>>(E->stride, E->NC, E->ops->n, E->ops->oMESH, E->ops->oY,
+                                                                   E->work, traj, N, E->tmesh, E->ty);
+            CKS(launch_check("ensemble_extract"));
+        }
+        if (mesh) CK(cudaMemcpyAsync(mesh, src_mesh, sizeof(double) * N, cudaMemcpyDeviceToHost, E->st));
+        if (y) CK(cudaMemcpyAsync(y, src_y, sizeof(double) * (size_t)N * E->ops->n, cudaMemcpyDeviceToHost, E->st));
         CK(cudaStreamSynchronize(E->st));
     }
     return MIRK_OK;

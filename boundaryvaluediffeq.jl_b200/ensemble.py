@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib as B
-from .api import BVProblem, EnsembleProblem, EnsembleSolution, _AbstractMIRK, _arr, _d, _i
+from .api import BVProblem, EnsembleProblem, EnsembleSolution, _AbstractMIRK, _arr, _d, _i, _nlsolve_code
 
 
 def partition(ntraj: int, world: int) -> list:
@@ -80,10 +80,13 @@ class EnsembleHandle:
         self.ntraj = int(ntraj)
         desc = B.EnsembleDesc(prob.f.problem_id, alg.order, float(abstol), int(bool(adaptive)), float(defect_threshold),
                               int(alg.max_num_subintervals), int(maxiters), int(reinterp_inplace), int(device),
-                              int(node_cap), float(prob.tspan[0]), float(prob.tspan[1]), float(dt))
+                              int(node_cap), float(prob.tspan[0]), float(prob.tspan[1]), float(dt),
+                              1 if _nlsolve_code(alg.nlsolve) == 1 else 0)
         self._h = B.Handle()
         B.check(B.lib().mirk_ensemble_create(C.byref(desc), self.ntraj, C.byref(self._h)))
-        self.node_cap = max(int(node_cap) if node_cap else 128, int(np.ceil((prob.tspan[1] - prob.tspan[0]) / dt)) + 1)
+        cap = C.c_int32(0)
+        B.check(B.lib().mirk_ensemble_node_cap(self._h, C.byref(cap)))
+        self.node_cap = int(cap.value)   # most nodes a trajectory's final mesh can have
 
     def set_inputs(self, params: np.ndarray, u0: np.ndarray, per_traj: bool = False):
         params = _arr(params).reshape(self.ntraj, -1)

@@ -58,6 +58,10 @@ typedef struct {
     int32_t device;                /* CUDA device ordinal                                       */
     int32_t n_params;              /* length of params                                          */
     const double* params;          /* prob.p (host)                                             */
+    int32_t nlsolve;               /* alg.nlsolve: 0 = nothing given -> the reference's default polyalgorithm
+                                      NewtonRaphson -> NewtonRaphson + BackTracking -> TrustRegion, each restarting
+                                      from the original iterate (CORE/default_internal_solve.jl:31-45); 1, 2, 3 = that
+                                      single solver */
 } mirk_desc;
 
 typedef struct {
@@ -117,8 +121,13 @@ int mirk_jacobian_blocks(mirk_handle h, double* Lb, double* Rb, int32_t* bc_node
 int mirk_linear_solve(mirk_handle h, double* delta);
 /* one NewtonRaphson iteration: J d = F, y -= d, F(y) ; returns the new |F|_inf */
 int mirk_newton_step(mirk_handle h, double* resid_norm);
-/* __internal_solve(nlprob, NewtonRaphson; abstol, maxiters) (CORE/default_internal_solve.jl:107-110) */
+/* __internal_solve(nlprob, alg; abstol, maxiters) with alg per desc.nlsolve (CORE/default_internal_solve.jl:31-45,
+ * 107-110); returns Success / Failure / MaxIters / Unstable / Stalled, iters = steps of every sub-solver that ran */
 int mirk_newton_solve(mirk_handle h, int32_t* iters, double* resid_norm);
+/* steps and return code of each sub-solver (NewtonRaphson, + BackTracking, TrustRegion) in the last nonlinear solve;
+ * -1 where a sub-solver did not run.  (A sub-solver that DIVERGES amplifies rounding differences, so its step count
+ * is not reproducible across linear solvers; the converging one's is.) */
+int mirk_nlsolve_stats(mirk_handle h, int32_t* steps3, int32_t* retcodes3);
 /* error_estimate!(cache, DefectControl, ...) (MIRK/adaptivity.jl:370-415); errors is (N-1)×n, may be NULL */
 int mirk_defect(mirk_handle h, double* errors, double* defect_norm);
 /* mesh_selector! + interp_eval! + __expand_cache! (MIRK/adaptivity.jl:23-75, mirk.jl:364-372);
@@ -178,9 +187,13 @@ typedef struct {
     int32_t adaptive;
     double defect_threshold;
     int32_t max_num_subintervals, maxiters, reinterp_inplace, device;
-    int32_t node_cap;       /* per-trajectory mesh capacity in nodes (0: 128); a mesh that would outgrow it
-                               ends that trajectory with MIRK_RET_FAILURE, like max_num_subintervals does */
+    int32_t node_cap;       /* per-trajectory mesh capacity in nodes; 0: max_num_subintervals + 1 (state lives on chip
+                               up to the kernel's shared-memory capacity, beyond it on an HBM slab).  A mesh that would
+                               outgrow node_cap ends that trajectory with MIRK_RET_FAILURE, like max_num_subintervals */
     double t0, t1, dt;      /* tspan and dt: uniform initial mesh of cld(t1 - t0, dt) intervals */
+    int32_t nlsolve;        /* 0: the default polyalgorithm (the batched kernels run NewtonRaphson; a trajectory whose
+                               Newton solve fails is re-run by the single-problem driver with the BackTracking and
+                               TrustRegion fallbacks); 1: NewtonRaphson only */
 } mirk_ensemble_desc;
 int mirk_ensemble_create(const mirk_ensemble_desc* desc, int64_t ntraj, mirk_ensemble_handle* out);
 int mirk_ensemble_destroy(mirk_ensemble_handle h);

@@ -101,6 +101,7 @@ struct MirkDesc
     device::Int32
     n_params::Int32
     params::Ptr{Float64}
+    nlsolve::Int32
 end
 
 struct MirkResult
@@ -163,18 +164,32 @@ function _guess(u0, p, t0, t1, dt)
     end
 end
 
+# alg.nlsolve -> the C ABI's solver code.  `nothing` is the reference default (polyalgorithm NewtonRaphson ->
+# NewtonRaphson + BackTracking -> TrustRegion, CORE/src/default_internal_solve.jl:31-45); the three sub-solvers can be
+# requested on their own; anything else cannot run on the device and is rejected rather than ignored.
+nlsolve_code(::Nothing) = Int32(0)
+function nlsolve_code(alg)
+    name = string(nameof(typeof(alg)))
+    occursin("TrustRegion", name) && return Int32(3)
+    if occursin("GeneralizedFirstOrderAlgorithm", name) || occursin("NewtonRaphson", name)
+        ls = hasproperty(alg, :linesearch) ? getproperty(alg, :linesearch) : nothing
+        (ls === nothing || occursin("NoLineSearch", string(typeof(ls)))) && return Int32(1)
+        occursin("BackTracking", string(typeof(ls))) && return Int32(2)
+    end
+    throw(ArgumentError("nlsolve = $(typeof(alg)) cannot run on the B200 backend (supported: nothing, NewtonRaphson(), NewtonRaphson(linesearch = BackTracking()), TrustRegion())"))
+end
+
 function __init_b200(prob::BVProblem, alg, order::Integer, device::Integer; dt = 0.0, abstol = 1e-6, adaptive = true,
         controller = DefectControl(), nlsolve_kwargs = (; abstol = abstol), optimize_kwargs = (;),
         verbose = DEFAULT_VERBOSE, kwargs...)
     f = device_function(prob)
     f === nothing && throw(ArgumentError("the B200 backend needs prob.f to wrap a BVPDeviceFunction"))
-    (alg.nlsolve === nothing && alg.optimize === nothing) ||
-        throw(ArgumentError("a user-supplied nlsolve / optimize is not supported by the B200 backend (its Newton polyalgorithm runs on the device)"))
+    alg.optimize === nothing || throw(ArgumentError("`optimize` solvers are not supported by the B200 backend"))
     controller isa DefectControl || throw(ArgumentError("the B200 backend implements DefectControl and the global-error controllers through `controller_code`"))
     p = prob.p isa SciMLBase.NullParameters ? Float64[] : collect(Float64, prob.p)
     desc = MirkDesc(problem_id(f), order, get(nlsolve_kwargs, :abstol, abstol), adaptive,
         controller.defect_threshold, alg.max_num_subintervals, get(nlsolve_kwargs, :maxiters, 1000), 0, 0,
-        device, length(p), pointer(p))
+        device, length(p), pointer(p), nlsolve_code(alg.nlsolve))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve p check(ccall((:mirk_create, libmirkb200[]), Cint, (Ref{MirkDesc}, Ref{Ptr{Cvoid}}), desc, h))
     t0, t1 = prob.tspan
@@ -250,6 +265,7 @@ struct MirkEnsembleDesc
     t0::Float64
     t1::Float64
     dt::Float64
+    nlsolve::Int32
 end
 
 # generic functions the CUDA extension adds device-array methods to
@@ -278,7 +294,8 @@ function __solve_ensemble_b200(ens, alg, order, device, ealg::EnsembleB200; traj
     params = packed_params === nothing ? reduce(hcat, (collect(Float64, q.p) for q in probs)) : packed_params
     u0 = collect(Float64, base.u0)
     desc = MirkEnsembleDesc(problem_id(f), ensemble_order(alg, order), abstol, adaptive, controller.defect_threshold,
-        alg.max_num_subintervals, 1000, 0, device, ealg.node_cap, base.tspan[1], base.tspan[2], dt)
+        alg.max_num_subintervals, 1000, 0, device, ealg.node_cap, base.tspan[1], base.tspan[2], dt,
+        nlsolve_code(alg.nlsolve) == 1 ? Int32(1) : Int32(0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:mirk_ensemble_create, libmirkb200[]), Cint, (Ref{MirkEnsembleDesc}, Int64, Ref{Ptr{Cvoid}}), desc, trajectories, h))
     try

@@ -31,6 +31,7 @@ void orc_default_options(orc_options *o) {
     o->max_num_subintervals = 3000; /* MIRK/algorithms.jl:55-61 */
     o->maxiters = 1000;
     o->reinterp_inplace = 0; /* see DESIGN.md "Q3": 1 reproduces the reference's in-place hazard */
+    o->nlsolve = 0; /* the reference default: NewtonRaphson -> NewtonRaphson + BackTracking -> TrustRegion */
     o->max_outer = 1000; /* safety net only: the reference loop has no cap (mirk.jl:296-322) */
 }
 
@@ -663,57 +664,307 @@ static double norm_inf(const double *x, size_t len) {
     return m;
 }
 
-int orc_newton(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
-               double *y, double *Kd, double *Ki, double abstol, int maxiters, double *resid_norm,
-               int *iters) {
-    const int n = P->n, L = P->n_bc;
-    const size_t nu = (size_t)N * n, nr = (size_t)L + (size_t)(N - 1) * n;
-    double *fu = (double *)malloc(sizeof(double) * nr);
-    double *Lb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n * n);
-    double *Rb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n * n);
-    double *B = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * L * n);
-    double *delta = (double *)malloc(sizeof(double) * nu);
-    double *ybest = (double *)malloc(sizeof(double) * nu);
-    double *rhs_bc = (double *)malloc(sizeof(double) * L);
-    int nodes[ORC_MAX_BC_PTS];
-    int ret = ORC_MAXITERS, it = 0;
-    double best = INFINITY;
-    memcpy(ybest, y, sizeof(double) * nu);
+/* ---- the reference's DEFAULT nonlinear solver: NonlinearSolvePolyAlgorithm(NewtonRaphson, NewtonRaphson +
+ * BackTracking, TrustRegion), CORE/src/default_internal_solve.jl:31-45, each sub-solver restarting from the original
+ * u0.  The sub-solvers live in third-party packages that are not under /root/reference (NonlinearSolveFirstOrder,
+ * NonlinearSolveBase, LineSearch / LineSearches): what follows restates their published algorithms FROM MEMORY —
+ * parity unpinned until julia/parity/dump_reference.jl has been run on a Julia box.
+ *   termination  AbsNormSafeBest on |F|_inf (NonlinearSolveBase termination_conditions): Success when the objective
+ *                <= abstol; Unstable when it is not finite; the best iterate is tracked and returned; Stalled when,
+ *                after patience_steps = 100 steps with the objective within 3 abstol, the window's min and max are
+ *                within a factor 1.3, or after max_stalled_steps = 32 consecutive steps with |u - u_prev|_2 <= abstol
+ *                and <= reltol |u|_2 (reltol = eps^(4/5));
+ *   NewtonRaphson            J d = F, u <- u - d
+ *   + BackTracking           LineSearches.BackTracking(order 3, c_1 = 1e-4, rho_hi = 0.5, rho_lo = 0.1, 1000 iterations)
+ *                            on phi(alpha) = |F(u + alpha du)|_2^2 / 2 with phi'(0) = F . (J du); a failed search ends
+ *                            the sub-solver (InternalLineSearchFailed)
+ *   TrustRegion              Simple radius update: Delta_max = max(|F|_2, max(u) - min(u)), Delta_0 = Delta_max / 11,
+ *                            dogleg step (Newton / Cauchy / their blend), rho = actual / predicted reduction, accept when
+ *                            rho > 1e-4, shrink by 1/4 when rho < 1/4, expand by 2 when rho > 3/4, give up after 32
+ *                            consecutive shrinks (ShrinkThresholdExceeded)
+ *   polyalgorithm            first success wins; if all fail, the sub-solver with the smallest final |F|_inf provides
+ *                            the iterate and the return code. */
 
-    orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
-    double nrm = norm_inf(fu, nr);
-    for (; it < maxiters;) {
-        orc_jac_blocks(P, T, p, N, mesh, y, Lb, Rb);
-        const int m = orc_bc_jac(P, T, p, N, mesh, y, Kd, Ki, nodes, B);
-        const double *rphi;
-        if (P->problem_type == 0) {
-            memcpy(rhs_bc, fu, sizeof(double) * L);
-            rphi = fu + L;
-        } else {
-            const int La = P->n_bca;
-            memcpy(rhs_bc, fu, sizeof(double) * La);
-            memcpy(rhs_bc + La, fu + La + (size_t)(N - 1) * n, sizeof(double) * (L - La));
-            rphi = fu + La;
-        }
-        if (orc_abd_solve(n, N, L, Lb, Rb, m, nodes, B, rhs_bc, rphi, delta)) { ret = ORC_FAILURE; break; }
-        for (size_t i = 0; i < nu; i++) y[i] -= delta[i];
-        it++;
-        orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
-        nrm = norm_inf(fu, nr);
-        if (!isfinite(nrm)) { ret = ORC_UNSTABLE; break; }
-        if (nrm < best) { best = nrm; memcpy(ybest, y, sizeof(double) * nu); }
-        if (nrm <= abstol) { ret = ORC_SUCCESS; break; }
+typedef struct {
+    const orc_problem *P; const orc_tableau *T; const double *p; int N; const double *mesh;
+    int n, L, La; size_t nu, nr;
+    double *Kd, *Ki;
+    double *Lb, *Rb, *B; int nodes[ORC_MAX_BC_PTS]; int m;   /* Jacobian at the current iterate */
+} nl_ctx;
+
+/* rows of the residual vector: Standard [bc(L); Phi], TwoPoint [bc_a(La); Phi; bc_b] */
+static size_t nl_bc_row(const nl_ctx *c, int q) { return q < c->La ? (size_t)q : (size_t)c->La + (size_t)(c->N - 1) * c->n + (q - c->La); }
+
+static void nl_jacobian(nl_ctx *c, const double *y) {
+    orc_jac_blocks(c->P, c->T, c->p, c->N, c->mesh, y, c->Lb, c->Rb);
+    c->m = orc_bc_jac(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, c->nodes, c->B);
+}
+/* out = J v  (out has nr entries, v has nu) */
+static void nl_jvec(const nl_ctx *c, const double *v, double *out) {
+    const int n = c->n, L = c->L;
+    for (int q = 0; q < L; q++) {
+        double acc = 0.0;
+        for (int k = 0; k < c->m; k++)
+            for (int j = 0; j < n; j++) acc += c->B[((size_t)k * L + q) * n + j] * v[(size_t)c->nodes[k] * n + j];
+        out[nl_bc_row(c, q)] = acc;
     }
-    if (ret != ORC_SUCCESS && it > 0 && isfinite(best)) {
+    for (int i = 0; i < c->N - 1; i++)
+        for (int r = 0; r < n; r++) {
+            double acc = 0.0;
+            for (int j = 0; j < n; j++)
+                acc += c->Lb[((size_t)i * n + r) * n + j] * v[(size_t)i * n + j] + c->Rb[((size_t)i * n + r) * n + j] * v[(size_t)(i + 1) * n + j];
+            out[(size_t)c->La + (size_t)i * n + r] = acc;
+        }
+}
+/* out = J^T w  (w has nr entries, out has nu) */
+static void nl_jtvec(const nl_ctx *c, const double *w, double *out) {
+    const int n = c->n, L = c->L;
+    for (size_t e = 0; e < c->nu; e++) out[e] = 0.0;
+    for (int q = 0; q < L; q++)
+        for (int k = 0; k < c->m; k++)
+            for (int j = 0; j < n; j++) out[(size_t)c->nodes[k] * n + j] += c->B[((size_t)k * L + q) * n + j] * w[nl_bc_row(c, q)];
+    for (int i = 0; i < c->N - 1; i++)
+        for (int r = 0; r < n; r++) {
+            const double wr = w[(size_t)c->La + (size_t)i * n + r];
+            for (int j = 0; j < n; j++) {
+                out[(size_t)i * n + j] += c->Lb[((size_t)i * n + r) * n + j] * wr;
+                out[(size_t)(i + 1) * n + j] += c->Rb[((size_t)i * n + r) * n + j] * wr;
+            }
+        }
+}
+/* delta = J \ fu with the Jacobian stored in c */
+static int nl_linsolve(const nl_ctx *c, const double *fu, double *delta, double *rhs_bc) {
+    const int L = c->L, La = c->La;
+    for (int q = 0; q < L; q++) rhs_bc[q] = fu[nl_bc_row(c, q)];
+    return orc_abd_solve(c->n, c->N, L, c->Lb, c->Rb, c->m, c->nodes, c->B, rhs_bc, fu + La, delta);
+}
+static double nl_dot(const double *a, const double *b, size_t len) {
+    double s = 0.0;
+    for (size_t i = 0; i < len; i++) s += a[i] * b[i];
+    return s;
+}
+
+/* AbsNormSafeBest termination state */
+typedef struct {
+    double abstol, reltol, best, initial, trace[100];
+    int nsteps, stall_counter;
+    double *ubest; int have_best;
+} nl_term;
+static void nl_term_init(nl_term *t, double abstol, double *ubest) {
+    memset(t, 0, sizeof(*t));
+    t->abstol = abstol; t->reltol = pow(2.220446049250313e-16, 0.8); t->best = INFINITY; t->ubest = ubest;
+}
+/* returns -1 to continue, else the return code that ends the sub-solver */
+static int nl_term_check(nl_term *t, double objective, const double *u, const double *uprev, size_t nu) {
+    if (!isfinite(objective)) return ORC_UNSTABLE;
+    if (objective < t->best) { t->best = objective; memcpy(t->ubest, u, sizeof(double) * nu); t->have_best = 1; }
+    if (objective <= t->abstol) return ORC_SUCCESS;
+    t->nsteps++;
+    if (t->nsteps == 1) t->initial = objective;
+    t->trace[(t->nsteps - 1) % 100] = objective;
+    if (objective <= 3.0 * t->abstol && t->nsteps >= 100) {
+        const int cnt = t->nsteps < 100 ? t->nsteps : 100;
+        double mn = INFINITY, mx = -INFINITY;
+        for (int i = 0; i < cnt; i++) { if (t->trace[i] < mn) mn = t->trace[i]; if (t->trace[i] > mx) mx = t->trace[i]; }
+        if (mn < 1.3 * mx) return ORC_STALLED;
+    }
+    double du2 = 0.0, u2 = 0.0;
+    for (size_t i = 0; i < nu; i++) { const double d = u[i] - uprev[i]; du2 += d * d; u2 += u[i] * u[i]; }
+    du2 = sqrt(du2); u2 = sqrt(u2);
+    if (du2 <= t->abstol && du2 <= t->reltol * u2) t->stall_counter++; else t->stall_counter = 0;
+    if (t->stall_counter >= 32) return ORC_STALLED;
+    return -1;
+}
+
+/* LineSearches.BackTracking (order 3).  phi(alpha) evaluates F(y + alpha du) into fu_trial.  Returns alpha, or NAN. */
+typedef struct { nl_ctx *c; const double *y; const double *du; double *ytrial; double *fu_trial; } nl_phi_ctx;
+static double nl_phi(nl_phi_ctx *k, double alpha) {
+    for (size_t i = 0; i < k->c->nu; i++) k->ytrial[i] = k->y[i] + alpha * k->du[i];
+    orc_loss(k->c->P, k->c->T, k->c->p, k->c->N, k->c->mesh, k->ytrial, k->c->Kd, k->c->Ki, k->fu_trial);
+    return 0.5 * nl_dot(k->fu_trial, k->fu_trial, k->c->nr);
+}
+static double nan_min(double a, double b) { return (isnan(a) || isnan(b)) ? NAN : (a < b ? a : b); }
+static double nan_max(double a, double b) { return (isnan(a) || isnan(b)) ? NAN : (a > b ? a : b); }
+static double nl_backtracking(nl_phi_ctx *k, double phi_0, double dphi_0) {
+    const double c_1 = 1e-4, rho_hi = 0.5, rho_lo = 0.1;
+    double a1 = 1.0, a2 = 1.0, phx0 = phi_0, phx1 = nl_phi(k, a1);
+    int iterfinite = 0;
+    while (!isfinite(phx1) && iterfinite < 52) { iterfinite++; a1 = a2; a2 = a1 / 2.0; phx1 = nl_phi(k, a2); }
+    int iteration = 0;
+    while (phx1 > phi_0 + c_1 * a2 * dphi_0) {
+        iteration++;
+        if (iteration > 1000) return NAN;
+        double atmp;
+        if (iteration == 1) {
+            atmp = -(dphi_0 * a2 * a2) / (2.0 * (phx1 - phi_0 - dphi_0 * a2));
+        } else {
+            const double div = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+            const double a = (a1 * a1 * (phx1 - phi_0 - dphi_0 * a2) - a2 * a2 * (phx0 - phi_0 - dphi_0 * a1)) * div;
+            const double b = (-a1 * a1 * a1 * (phx1 - phi_0 - dphi_0 * a2) + a2 * a2 * a2 * (phx0 - phi_0 - dphi_0 * a1)) * div;
+            if (fabs(a) <= 2.220446049250313e-16) atmp = dphi_0 / (2.0 * b);
+            else { double d = b * b - 3.0 * a * dphi_0; if (d < 0.0) d = 0.0; atmp = (-b + sqrt(d)) / (3.0 * a); }
+        }
+        a1 = a2;
+        atmp = nan_min(atmp, a2 * rho_hi);
+        a2 = nan_max(atmp, a2 * rho_lo);
+        phx0 = phx1;
+        phx1 = nl_phi(k, a2);
+        if (isnan(a2)) return NAN;
+    }
+    return a2;
+}
+
+/* one sub-solver from the iterate in y; alg 1 NewtonRaphson, 2 + BackTracking, 3 TrustRegion */
+static int nl_run(nl_ctx *c, int alg, double *y, double abstol, int maxiters, double *resid_norm, int *iters) {
+    const size_t nu = c->nu, nr = c->nr;
+    double *fu = (double *)malloc(sizeof(double) * nr), *fu2 = (double *)malloc(sizeof(double) * nr);
+    double *du = (double *)malloc(sizeof(double) * nu), *uprev = (double *)malloc(sizeof(double) * nu);
+    double *ytr = (double *)malloc(sizeof(double) * nu), *ubest = (double *)malloc(sizeof(double) * nu);
+    double *g = (double *)malloc(sizeof(double) * nu), *Jg = (double *)malloc(sizeof(double) * nr);
+    double *rhs_bc = (double *)malloc(sizeof(double) * c->L);
+    nl_term term;
+    nl_term_init(&term, abstol, ubest);
+    int ret = ORC_MAXITERS, it = 0;
+    orc_loss(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, fu);
+    double nrm = norm_inf(fu, nr);
+    /* trust region state */
+    double Delta = 0.0, Delta_max = 0.0;
+    int shrink_counter = 0, have_jac = 0;
+    if (alg == 3) {
+        double umax = -INFINITY, umin = INFINITY;
+        for (size_t i = 0; i < nu; i++) { if (y[i] > umax) umax = y[i]; if (y[i] < umin) umin = y[i]; }
+        const double f2 = sqrt(nl_dot(fu, fu, nr));
+        Delta_max = f2 > umax - umin ? f2 : umax - umin;
+        Delta = Delta_max / 11.0;
+    }
+    for (; it < maxiters;) {
+        memcpy(uprev, y, sizeof(double) * nu);
+        if (alg != 3 || !have_jac) { nl_jacobian(c, y); have_jac = 1; }
+        if (nl_linsolve(c, fu, du, rhs_bc)) { ret = ORC_FAILURE; break; }
+        for (size_t i = 0; i < nu; i++) du[i] = -du[i];   /* Newton direction */
+        if (alg == 1) {
+            for (size_t i = 0; i < nu; i++) y[i] += du[i];
+            orc_loss(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, fu);
+        } else if (alg == 2) {
+            nl_jvec(c, du, Jg);
+            const double phi_0 = 0.5 * nl_dot(fu, fu, nr), dphi_0 = nl_dot(fu, Jg, nr);
+            nl_phi_ctx k = {c, uprev, du, ytr, fu2};
+            const double alpha = nl_backtracking(&k, phi_0, dphi_0);
+            if (isnan(alpha)) { ret = ORC_FAILURE; break; }   /* InternalLineSearchFailed */
+            for (size_t i = 0; i < nu; i++) y[i] = uprev[i] + alpha * du[i];
+            orc_loss(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, fu);
+        } else {
+            /* dogleg step within Delta */
+            const double nN = sqrt(nl_dot(du, du, nu));
+            if (!(nN <= Delta)) {
+                nl_jtvec(c, fu, g);
+                for (size_t i = 0; i < nu; i++) g[i] = -g[i];   /* steepest descent direction */
+                const double lg = sqrt(nl_dot(g, g, nu));
+                nl_jvec(c, g, Jg);
+                const double dc = lg * lg * lg / nl_dot(Jg, Jg, nr);
+                if (dc >= Delta) {
+                    for (size_t i = 0; i < nu; i++) du[i] = (Delta / lg) * g[i];
+                } else {
+                    for (size_t i = 0; i < nu; i++) g[i] *= dc / lg;           /* Cauchy point */
+                    double aa = 0.0, bb = 0.0;
+                    for (size_t i = 0; i < nu; i++) { const double df = du[i] - g[i]; aa += df * df; bb += df * g[i]; }
+                    const double cc = dc * dc - Delta * Delta;
+                    double disc = bb * bb - aa * cc;
+                    if (disc < 0.0) disc = 0.0;
+                    const double tau = (-bb + sqrt(disc)) / aa;
+                    for (size_t i = 0; i < nu; i++) du[i] = g[i] + tau * (du[i] - g[i]);
+                }
+            }
+            for (size_t i = 0; i < nu; i++) ytr[i] = uprev[i] + du[i];
+            orc_loss(c->P, c->T, c->p, c->N, c->mesh, ytr, c->Kd, c->Ki, fu2);
+            nl_jvec(c, du, Jg);
+            nl_jtvec(c, fu, g);
+            const double num = 0.5 * (nl_dot(fu, fu, nr) - nl_dot(fu2, fu2, nr));
+            const double den = nl_dot(du, g, nu) + 0.5 * nl_dot(Jg, Jg, nr);
+            const double rho = num / (-den);
+            const int accept = rho > 1e-4;
+            if (rho < 0.25) { Delta *= 0.25; shrink_counter++; }
+            else { shrink_counter = 0; if (rho > 0.75) { Delta *= 2.0; if (Delta > Delta_max) Delta = Delta_max; } }
+            if (accept) {
+                memcpy(y, ytr, sizeof(double) * nu);
+                memcpy(fu, fu2, sizeof(double) * nr);
+                have_jac = 0;
+            } else {
+                /* rejected: stay, keep the Jacobian; the stages must again belong to y */
+                orc_loss(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, fu);
+            }
+            if (shrink_counter > 32) { it++; ret = ORC_FAILURE; break; }   /* ShrinkThresholdExceeded */
+        }
+        it++;
+        nrm = norm_inf(fu, nr);
+        const int tc = nl_term_check(&term, nrm, y, uprev, nu);
+        if (tc >= 0) { ret = tc; break; }
+    }
+    if (ret != ORC_SUCCESS && it > 0 && term.have_best) {
         /* SafeBest: hand back the best iterate seen and stages consistent with it */
-        memcpy(y, ybest, sizeof(double) * nu);
-        orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
+        memcpy(y, ubest, sizeof(double) * nu);
+        orc_loss(c->P, c->T, c->p, c->N, c->mesh, y, c->Kd, c->Ki, fu);
         nrm = norm_inf(fu, nr);
     }
     *resid_norm = nrm;
     *iters = it;
-    free(fu); free(Lb); free(Rb); free(B); free(delta); free(ybest); free(rhs_bc);
+    free(fu); free(fu2); free(du); free(uprev); free(ytr); free(ubest); free(g); free(Jg); free(rhs_bc);
     return ret;
+}
+
+/* nlsolve: 0 the default polyalgorithm, 1 NewtonRaphson, 2 NewtonRaphson + BackTracking, 3 TrustRegion.
+ * *iters counts the steps of every sub-solver that ran. */
+int orc_nlsolve(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+                double *y, double *Kd, double *Ki, double abstol, int maxiters, int nlsolve, double *resid_norm,
+                int *iters) {
+    nl_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.P = P; c.T = T; c.p = p; c.N = N; c.mesh = mesh; c.n = P->n; c.L = P->n_bc;
+    c.La = P->problem_type == 1 ? P->n_bca : P->n_bc;
+    c.nu = (size_t)N * c.n; c.nr = (size_t)c.L + (size_t)(N - 1) * c.n;
+    c.Kd = Kd; c.Ki = Ki;
+    c.Lb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * c.n * c.n);
+    c.Rb = (double *)malloc(sizeof(double) * (size_t)(N - 1) * c.n * c.n);
+    c.B = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * c.L * c.n);
+    int ret, total = 0;
+    if (nlsolve != 0) {
+        ret = nl_run(&c, nlsolve, y, abstol, maxiters, resid_norm, &total);
+    } else {
+        double *y0 = (double *)malloc(sizeof(double) * c.nu), *ybest = (double *)malloc(sizeof(double) * c.nu);
+        memcpy(y0, y, sizeof(double) * c.nu);
+        double best = INFINITY;
+        int best_ret = ORC_FAILURE;
+        ret = ORC_FAILURE;
+        for (int alg = 1; alg <= 3; alg++) {
+            int it = 0;
+            double nrm = 0.0;
+            memcpy(y, y0, sizeof(double) * c.nu);
+            const int r = nl_run(&c, alg, y, abstol, maxiters, &nrm, &it);
+            total += it;
+            if (r == ORC_SUCCESS) { ret = r; *resid_norm = nrm; best = -1.0; break; }
+            if (alg == 1 || !(nrm >= best)) { best = nrm; best_ret = r; memcpy(ybest, y, sizeof(double) * c.nu); }
+        }
+        if (ret != ORC_SUCCESS) {
+            /* all failed: the sub-solver that got closest provides the iterate and the return code */
+            memcpy(y, ybest, sizeof(double) * c.nu);
+            double *fu = (double *)malloc(sizeof(double) * c.nr);
+            orc_loss(P, T, p, N, mesh, y, Kd, Ki, fu);
+            *resid_norm = norm_inf(fu, c.nr);
+            free(fu);
+            ret = best_ret;
+        }
+        free(y0); free(ybest);
+    }
+    *iters = total;
+    free(c.Lb); free(c.Rb); free(c.B);
+    return ret;
+}
+
+/* the plain NewtonRaphson sub-solver alone (kept under its round-1 name) */
+int orc_newton(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+               double *y, double *Kd, double *Ki, double abstol, int maxiters, double *resid_norm,
+               int *iters) {
+    return orc_nlsolve(P, T, p, N, mesh, y, Kd, Ki, abstol, maxiters, 1, resid_norm, iters);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -891,7 +1142,7 @@ int orc_solve(const orc_problem *P, int order, const double *p, int N0, const do
     double error_norm = 2.0 * opt->abstol, resid_norm = 0.0;
     do {
         int iters = 0;
-        const int nret = orc_newton(P, &T, p, N, mesh, y, Kd, Ki, opt->abstol, opt->maxiters,
+        const int nret = orc_nlsolve(P, &T, p, N, mesh, y, Kd, Ki, opt->abstol, opt->maxiters, opt->nlsolve,
                                     &resid_norm, &iters);
         out->newton_iters += iters;
         error_norm = 2.0 * opt->abstol;

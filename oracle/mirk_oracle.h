@@ -71,6 +71,8 @@ typedef struct {
     int maxiters;              /* 1000   NonlinearSolve default                 */
     int reinterp_inplace;      /* 1 = reproduce quirk Q3 (MIRK/mirk.jl:368-370); default 0 */
     int max_outer;             /* safety cap on adaptive outer iterations       */
+    int nlsolve;               /* 0 default polyalgorithm (CORE/default_internal_solve.jl:31-45); 1 NewtonRaphson,
+                                  2 NewtonRaphson + BackTracking, 3 TrustRegion */
 } orc_options;
 
 typedef struct {
@@ -116,6 +118,9 @@ int orc_abd_solve(int n, int N, int L, const double *Lb, const double *Rb, int m
 int orc_newton(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
                double *y, double *Kd, double *Ki, double abstol, int maxiters, double *resid_norm,
                int *iters);
+int orc_nlsolve(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+                double *y, double *Kd, double *Ki, double abstol, int maxiters, int nlsolve, double *resid_norm,
+                int *iters);
 double orc_defect(const orc_problem *P, const orc_tableau *T, const double *p, int N,
                   const double *mesh, const double *y, const double *Kd, double *Ki, double *errors);
 int orc_mesh_select(int order, int n, int N, const double *mesh, const double *errors, double abstol,

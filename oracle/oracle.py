@@ -44,7 +44,7 @@ class Tableau(C.Structure):
 class Options(C.Structure):
     _fields_ = [("abstol", C.c_double), ("adaptive", C.c_int), ("defect_threshold", C.c_double),
                 ("max_num_subintervals", C.c_int), ("maxiters", C.c_int),
-                ("reinterp_inplace", C.c_int), ("max_outer", C.c_int)]
+                ("reinterp_inplace", C.c_int), ("max_outer", C.c_int), ("nlsolve", C.c_int)]
 
 
 class Result(C.Structure):
@@ -87,6 +87,7 @@ def lib():
         L.orc_bc_jac.argtypes = [PP, TP, dp, C.c_int, dp, dp, dp, dp, ip, dp]
         L.orc_abd_solve.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, ip, dp, dp, dp, dp]
         L.orc_newton.argtypes = [PP, TP, dp, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int, dp, ip]
+        L.orc_nlsolve.argtypes = [PP, TP, dp, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, dp, ip]
         L.orc_defect.argtypes = [PP, TP, dp, C.c_int, dp, dp, dp, dp, dp]
         L.orc_defect.restype = C.c_double
         L.orc_mesh_select.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_int, ip, dp]
@@ -267,6 +268,13 @@ class Workspace:
         nrm, it = C.c_double(0), C.c_int(0)
         ret = lib().orc_newton(*self._a(), _d(self.Kd), _d(self.Ki), abstol, maxiters,
                                C.byref(nrm), C.byref(it))
+        return ret, it.value, nrm.value
+
+    def nlsolve(self, alg=0, abstol=1e-6, maxiters=1000):
+        """alg 0: the reference's default polyalgorithm (NewtonRaphson -> + BackTracking -> TrustRegion), 1 / 2 / 3: one of them"""
+        nrm, it = C.c_double(0), C.c_int(0)
+        ret = lib().orc_nlsolve(*self._a(), _d(self.Kd), _d(self.Ki), abstol, maxiters, int(alg),
+                                C.byref(nrm), C.byref(it))
         return ret, it.value, nrm.value
 
     def defect(self):

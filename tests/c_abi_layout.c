@@ -15,7 +15,7 @@ int main(void) {
     OFF(mirk_desc, problem_id); OFF(mirk_desc, order); OFF(mirk_desc, abstol); OFF(mirk_desc, adaptive);
     OFF(mirk_desc, defect_threshold); OFF(mirk_desc, max_num_subintervals); OFF(mirk_desc, maxiters);
     OFF(mirk_desc, reinterp_inplace); OFF(mirk_desc, chunk); OFF(mirk_desc, device); OFF(mirk_desc, n_params);
-    OFF(mirk_desc, params);
+    OFF(mirk_desc, params); OFF(mirk_desc, nlsolve);
     SZ(mirk_problem_info);
     OFF(mirk_problem_info, n); OFF(mirk_problem_info, n_params); OFF(mirk_problem_info, problem_type);
     OFF(mirk_problem_info, n_bc); OFF(mirk_problem_info, n_bca); OFF(mirk_problem_info, max_bc_pts);
@@ -28,6 +28,6 @@ int main(void) {
     OFF(mirk_ensemble_desc, adaptive); OFF(mirk_ensemble_desc, defect_threshold);
     OFF(mirk_ensemble_desc, max_num_subintervals); OFF(mirk_ensemble_desc, maxiters);
     OFF(mirk_ensemble_desc, reinterp_inplace); OFF(mirk_ensemble_desc, device); OFF(mirk_ensemble_desc, node_cap);
-    OFF(mirk_ensemble_desc, t0); OFF(mirk_ensemble_desc, t1); OFF(mirk_ensemble_desc, dt);
+    OFF(mirk_ensemble_desc, t0); OFF(mirk_ensemble_desc, t1); OFF(mirk_ensemble_desc, dt); OFF(mirk_ensemble_desc, nlsolve);
     return 0;
 }

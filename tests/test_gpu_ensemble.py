@@ -141,3 +141,21 @@ def test_one_shot_c_abi_entry_point(M, oracle):
     bad = B.EnsembleDesc(desc.problem_id, 4, 1e-6, 1, 0.1, 3000, 1000, 0, 0, 0, 0.0, 1.0, 0.0)
     with pytest.raises(ValueError, match="dt must be positive"):
         B.check(B.lib().mirk_ensemble_solve(C.byref(bad), nt, d(params), d(u0), 0, i(ret), i(nm), i(its), d(yf)))
+
+
+@pytest.mark.parametrize("name,order,p,u0,tspan,dt", [
+    ("lotka", 4, [7.5, 4.0, 8.5, 5.0], [5.0, 5.0], (0.0, 10.0), 0.1),                           # warp kernel (n = 2)
+    ("torus", 4, [1.2, 1.0, 0.0, 0.0, 3.0, 5.0], [3.0, 0.0, 10.0, -20.0], (0.0, 1.0), 0.05),     # thread kernel (n = 4)
+])
+def test_trajectories_that_need_the_polyalgorithm_are_rerun_by_the_single_driver(M, oracle, name, order, p, u0, tspan, dt):
+    """Plain Newton fails on these: under the default polyalgorithm the batched kernel hands such a trajectory to the
+    single-problem driver (line-search / trust-region fallbacks), so the ensemble gives what the oracle's ensemble
+    (every trajectory through the full polyalgorithm) gives."""
+    ref = oracle.solve_dt(oracle.builtin(name), order, p, u0, tspan, dt)
+    params = np.tile(np.asarray(p, dtype=float), (2, 1))
+    ens = M.EnsembleProblem(M.BVProblem(name, u0, tspan, p=p), params=params)
+    sol = M.solve(ens, M.MIRK4(), trajectories=2, dt=dt, keep_solutions=True)
+    assert list(sol.retcodes) == [ref.retcode] * 2
+    assert list(sol.n_mesh) == [ref.N] * 2
+    # (total step counts include the diverging sub-solvers, whose counts are not reproducible across linear solvers)
+    assert np.max(np.abs(sol.u[1] - ref.u)) < 1e-7 * max(1.0, np.max(np.abs(ref.u)))

@@ -458,3 +458,63 @@ def test_handles_are_reentrant_across_host_threads(M, oracle):
         assert sol is not None and sol.retcode == ref.retcode == 0
         assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
         assert _rel(sol.u, ref.u) < 1e-10
+
+
+# ---- the reference's default nonlinear solver: NewtonRaphson -> NewtonRaphson + BackTracking -> TrustRegion ----------
+NL_CASES = [
+    # name, order, p, tspan, nint, constant guess — chosen so that the first solver(s) fail (oracle: orc_nlsolve)
+    ("lotka", 4, [7.5, 4.0, 8.5, 5.0], (0.0, 10.0), 100, [5.0, 5.0]),          # NR fails, BackTracking stalls, TrustRegion converges
+    ("torus", 4, [1.2, 1.0, 0.0, 0.0, 3.0, 5.0], (0.0, 1.0), 20, [3.0, 0.0, 10.0, -20.0]),  # NR unstable, BackTracking converges
+    ("pendulum", 4, [9.81], PENDULUM_T, 32, PENDULUM_U0),                          # NR converges: the fallbacks never run
+    ("swirling", 4, [0.01], (0.0, 1.0), 100, [0.0] * 6),
+]
+
+
+@pytest.mark.parametrize("nl", [0, 1, 2, 3])
+@pytest.mark.parametrize("name,order,p,tspan,nint,u0", NL_CASES)
+def test_nonlinear_solvers_match_oracle(M, oracle, name, order, p, tspan, nint, u0, nl):
+    """Every sub-solver of the default polyalgorithm on its own (nlsolve = NewtonRaphson(), NewtonRaphson(linesearch =
+    BackTracking()), TrustRegion()) and the polyalgorithm itself against the oracle's restatement: same return code
+    (incl. Stalled / Unstable), same step count, same final iterate."""
+    O = oracle
+    mesh = O.mesh_uniform(tspan[0], tspan[1], nint)
+    y = np.tile(np.asarray(u0, dtype=float), (nint + 1, 1))
+    ws = O.Workspace(O.builtin(name), order, p, mesh, y)
+    ret_ref, it_ref, nrm_ref = ws.nlsolve(nl, maxiters=200)
+    nlsolve = {0: None, 1: M.NewtonRaphson(), 2: M.NewtonRaphson(linesearch=M.BackTracking()), 3: M.TrustRegion()}[nl]
+    alg = (M.MIRK4 if order == 4 else M.MIRK6)(nlsolve=nlsolve)
+    cache = M.init(M.BVProblem(name, y, tspan, p=p, mesh=mesh), alg, adaptive=False, nlsolve_kwargs={"maxiters": 200})
+    ret, it, nrm = cache.newton_solve()
+    steps, rets = cache.nlsolve_stats()
+    # what every sub-solver does on its own in the oracle.  A sub-solver that CONVERGES reproduces exactly (return code
+    # and step count); one that diverges amplifies the rounding differences between two linear solvers, so only its
+    # failing is compared, not where along the blow-up it stopped
+    alone = {k: O.Workspace(O.builtin(name), order, p, mesh, y).nlsolve(k, maxiters=200) for k in ((1, 2, 3) if nl == 0 else (nl,))}
+    for k, (r_k, it_k, _) in alone.items():
+        if rets[k - 1] < 0:
+            continue   # the polyalgorithm stopped before this one
+        assert (rets[k - 1] == 0) == (r_k == 0), (k, rets, alone)
+        if r_k == 0:
+            assert steps[k - 1] == it_k
+    assert (ret == 0) == (ret_ref == 0)
+    if nl == 0:
+        first_ok = next((k for k in (1, 2, 3) if alone[k][0] == 0), None)
+        assert [k for k in (1, 2, 3) if rets[k - 1] >= 0] == ([1, 2, 3] if first_ok is None else list(range(1, first_ok + 1)))
+    if ret == 0:
+        _, u = cache.solution()
+        assert _rel(u, ws.y) < 1e-8   # (long line-search / trust-region paths accumulate rounding differences)
+        assert nrm <= 1e-6
+    cache.close()
+
+
+def test_polyalgorithm_inside_the_adaptive_solve(M, oracle):
+    """A full adaptive solve whose first Newton solve needs the trust-region fallback: mesh history, step counts and
+    solution against the oracle."""
+    O = oracle
+    p, u0, tspan = [7.5, 4.0, 8.5, 5.0], [5.0, 5.0], (0.0, 10.0)
+    ref = O.solve_dt(O.builtin("lotka"), 4, p, u0, tspan, 0.1)
+    sol = M.solve(M.BVProblem("lotka", u0, tspan, p=p), M.MIRK4(), dt=0.1)
+    assert sol.retcode == ref.retcode
+    # (the first outer iteration's count contains the two diverging sub-solvers, whose step counts are not reproducible)
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"][1:] == ref.hist_newton[1:]
+    assert _rel(sol.u, ref.u) < 1e-7

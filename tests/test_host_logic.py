@@ -52,6 +52,10 @@ def test_registry_and_host_helpers():
         assert np.array_equal(M.mesh_uniform(t0, t1, nint), O.mesh_uniform(t0, t1, nint))
     with pytest.raises(NotImplementedError):
         M.MIRK4(nlsolve="NewtonRaphson")
+    # the sub-solvers of the reference's default polyalgorithm can be requested on their own
+    assert M.MIRK4(nlsolve=M.NewtonRaphson()).nlsolve.linesearch is None
+    M.MIRK4(nlsolve=M.NewtonRaphson(linesearch=M.BackTracking()))
+    M.MIRK6(nlsolve=M.TrustRegion())
 
 
 def test_partition_covers_every_trajectory_once():
