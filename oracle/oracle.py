@@ -258,6 +258,59 @@ class Workspace:
                 J[La + (N - 1) * n:, nd * n:(nd + 1) * n] += B[k][La:]
         return J
 
+    def dense_jacobian_reference_pattern(self):
+        """The Jacobian the REFERENCE's default (sparse, coloured ForwardDiff) path assembles — quirk Q1 of SURVEY §8(c).
+
+        The reference differentiates with a KNOWN sparsity pattern that is too narrow for n > 2
+        (lib/BoundaryValueDiffEqMIRK/src/sparse_jacobians.jl:16-36: Standard problems band (1, 2n-1) over the collocation
+        rows, two-point problems band (n+1, n+1) over all rows) and the greedy natural-order column colouring of a
+        band of total width w = l + u + 1 is colour(c) = c mod w.  Coloured forward mode computes B = J_true * S (one
+        column per colour) and decompression writes J[r, c] = B[r, colour(c)] for every (r, c) INSIDE the pattern: a true
+        entry outside the band is not merely dropped, it is added to the in-band column of its colour in that row.
+        For n <= 2 the pattern covers every true entry and this equals dense_jacobian().  (Restated from the published
+        behaviour of SparseMatrixColorings / DifferentiationInterface, which are not under /root/reference: unpinned.)"""
+        n, N, L = self.n, self.N, self.P.n_bc
+        Jt = self.dense_jacobian()
+        Jr = np.zeros_like(Jt)
+        ncols = N * n
+        if self.P.problem_type == 1:
+            r0, r1, lo, up = 0, Jt.shape[0], n + 1, n + 1          # the whole matrix is one banded prototype
+        else:
+            r0, r1, lo, up = L, Jt.shape[0], 1, 2 * n - 1          # collocation rows only; the boundary rows are dense "fill"
+            Jr[:L] = Jt[:L]
+        w = lo + up + 1
+        colour = np.arange(ncols) % w
+        for R in range(r0, r1):
+            r = R - r0
+            B = np.bincount(colour, weights=Jt[R], minlength=w)    # compressed row: sum of the true entries per colour
+            c0, c1 = max(0, r - lo), min(ncols - 1, r + up)
+            cols = np.arange(c0, c1 + 1)
+            Jr[R, cols] = B[colour[cols]]
+        return Jr
+
+    def newton_reference_pattern(self, abstol=1e-6, maxiters=1000, exact=False):
+        """NewtonRaphson with dense solves of the reference-pattern Jacobian (exact=True: of the exact one, same code
+        path) — for Newton-count comparisons at small N; O((nN)^3) per step."""
+        it, ret = 0, MAXITERS
+        nrm = float(np.max(np.abs(self.loss())))
+        while it < maxiters:
+            J = self.dense_jacobian() if exact else self.dense_jacobian_reference_pattern()
+            try:
+                d = np.linalg.solve(J, self.loss())
+            except np.linalg.LinAlgError:
+                ret = FAILURE
+                break
+            self.y -= d.reshape(self.y.shape)
+            it += 1
+            nrm = float(np.max(np.abs(self.loss())))
+            if not np.isfinite(nrm):
+                ret = UNSTABLE
+                break
+            if nrm <= abstol:
+                ret = SUCCESS
+                break
+        return ret, it, nrm
+
     def eval_sol(self, t, deriv=0, bc_shortcut=False):
         out = np.zeros(self.n)
         lib().orc_eval_sol(C.byref(self.P), C.byref(self.T), self.N, _d(self.mesh), _d(self.y),

@@ -486,3 +486,50 @@ def test_mirk6i_convergence_order_and_interpolation(oracle, name, p):
     s = O.solve_dt(P, O.MIRK6I, p, [5.0, -3.5], (0.0, 5.0), 0.1)
     for t in (0.37, 2.51, 4.99):
         assert np.abs(s(t) - _exact_lin(t)).max() < 1e-6
+
+
+def test_reference_pattern_jacobian_mode_quirk_Q1(oracle):
+    """the Jacobian the reference's default sparse path assembles (pattern too narrow for n > 2, out-of-band
+    entries aliased onto the in-band column of their colour).  n = 2: identical to the exact Jacobian.  n = 16: differs
+    only in O(h) entries, exactly in the columns the aliasing rule predicts, and the Newton count on C2's problem is the
+    same as with the exact Jacobian."""
+    import math
+    O = oracle
+    mesh = O.mesh_uniform(0.0, math.pi / 2, 32)
+    ws = O.Workspace(O.builtin("pendulum"), 4, [9.81], mesh, np.tile([math.pi / 2, math.pi / 2], (33, 1)))
+    assert np.array_equal(ws.dense_jacobian(), ws.dense_jacobian_reference_pattern())
+    # chain8 (two-point, n = 16): band (n + 1, n + 1), period 2n + 3 = 35
+    n, nint = 16, 12
+    rng = np.random.default_rng(3)
+    p = np.concatenate([[9.81, 4.0], rng.uniform(-1, 1, 16)])
+    mesh = O.mesh_uniform(0.0, 0.5, nint)
+    y = 0.3 * rng.standard_normal((nint + 1, n))
+    ws = O.Workspace(O.builtin("chain8"), 6, p, mesh, y)
+    Jt, Jr = ws.dense_jacobian(), ws.dense_jacobian_reference_pattern()
+    R, Cc = np.nonzero(Jt != Jr)
+    assert len(R) > 0
+    for r, c in zip(R, Cc):
+        inside = -(n + 1) <= c - r <= n + 1
+        if inside:   # an aliased value landed here: it is a true entry 35 columns away
+            src = [c2 for c2 in (c - 35, c + 35) if 0 <= c2 < Jt.shape[1] and Jt[r, c2] != 0.0]
+            assert src and Jr[r, c] == pytest.approx(Jt[r, c] + sum(Jt[r, c2] for c2 in src))
+        else:        # a true entry outside the band: dropped from its own place
+            assert Jr[r, c] == 0.0 and Jt[r, c] != 0.0
+    a = O.Workspace(O.builtin("chain8"), 6, p, mesh, np.zeros((nint + 1, n)))
+    b = O.Workspace(O.builtin("chain8"), 6, p, mesh, np.zeros((nint + 1, n)))
+    ra, rb = a.newton_reference_pattern(exact=True, maxiters=50), b.newton_reference_pattern(maxiters=50)
+    assert ra[0] == rb[0] == 0 and ra[1] == rb[1]
+
+
+def test_polyalgorithm_order_and_stalled(oracle):
+    """The default nonlinear solver tries NewtonRaphson, NewtonRaphson + BackTracking, TrustRegion in that order from the
+    same start; the first success wins and the step count is the sum over the solvers that ran."""
+    O = oracle
+    mesh = O.mesh_uniform(0.0, 10.0, 100)
+    y = np.tile([5.0, 5.0], (101, 1))
+    runs = {}
+    for alg in (0, 1, 2, 3):
+        ws = O.Workspace(O.builtin("lotka"), 4, [7.5, 4.0, 8.5, 5.0], mesh, y)
+        runs[alg] = ws.nlsolve(alg, maxiters=200)
+    assert runs[1][0] != 0 and runs[2][0] == O.STALLED and runs[3][0] == 0
+    assert runs[0][0] == 0 and runs[0][1] == runs[1][1] + runs[2][1] + runs[3][1]
