@@ -333,10 +333,11 @@ __device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsign
 }
 
 // pack this segment's collapsed relation (+ the boundary blocks and rows it owns) and push it to every rank
-__global__ void __launch_bounds__(1024)
-k_part_push(int n, int L, int La, const double* __restrict__ relL, const double* __restrict__ relR,
-            const double* __restrict__ relr, const double* __restrict__ Bc, const double* __restrict__ resid,
-            size_t tail_off, XchgPeers peers, XchgLayout lay, int rank, const unsigned long long* __restrict__ epoch_ptr) {
+// (body: one whole block, any size)
+__device__ __forceinline__ void part_push_body(int n, int L, int La, const double* __restrict__ relL, const double* __restrict__ relR,
+                                               const double* __restrict__ relr, const double* __restrict__ Bc,
+                                               const double* __restrict__ resid, size_t tail_off, const XchgPeers& peers,
+                                               const XchgLayout& lay, int rank, const unsigned long long* __restrict__ epoch_ptr) {
     const int nn = n * n, tid = threadIdx.x, T = blockDim.x;
     const unsigned long long e = *epoch_ptr + 1ull;
     const size_t slot = ((size_t)(e & 1ull) * lay.G + rank) * lay.P;
@@ -358,11 +359,18 @@ k_part_push(int n, int L, int La, const double* __restrict__ relL, const double*
     if (tid < lay.G)
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[tid] + lay.off_pflag()) + (e & 1ull) * lay.G + rank, e);
 }
-// wait for every rank's relation of this epoch, then unpack into the interface system (as k_part_unpack)
 __global__ void __launch_bounds__(1024)
-k_part_wait_unpack(int n, int L, int La, double* __restrict__ xbuf, XchgLayout lay, double* __restrict__ oL,
-                   double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
-                   double* __restrict__ oresid, unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
+k_part_push(int n, int L, int La, const double* __restrict__ relL, const double* __restrict__ relR,
+            const double* __restrict__ relr, const double* __restrict__ Bc, const double* __restrict__ resid,
+            size_t tail_off, XchgPeers peers, XchgLayout lay, int rank, const unsigned long long* __restrict__ epoch_ptr) {
+    part_push_body(n, L, La, relL, relR, relr, Bc, resid, tail_off, peers, lay, rank, epoch_ptr);
+}
+// wait for every rank's relation of this epoch, then unpack into the interface system (as k_part_unpack)
+// (body: one whole block, any size >= G threads)
+__device__ __forceinline__ void part_wait_unpack_body(int n, int L, int La, double* __restrict__ xbuf, const XchgLayout& lay,
+                                                      double* __restrict__ oL, double* __restrict__ oR, double* __restrict__ orr,
+                                                      double* __restrict__ oBc, double* __restrict__ oresid,
+                                                      unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
     const int nn = n * n, tid = threadIdx.x, T = blockDim.x, G = lay.G;
     const unsigned long long e = *epoch_ptr + 1ull;
     if (tid < G) {
@@ -389,11 +397,38 @@ k_part_wait_unpack(int n, int L, int La, double* __restrict__ xbuf, XchgLayout l
     __syncthreads();
     if (tid == 0) *epoch_ptr = e;
 }
+__global__ void __launch_bounds__(1024)
+k_part_wait_unpack(int n, int L, int La, double* __restrict__ xbuf, XchgLayout lay, double* __restrict__ oL,
+                   double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
+                   double* __restrict__ oresid, unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
+    part_wait_unpack_body(n, L, La, xbuf, lay, oL, oR, orr, oBc, oresid, epoch_ptr, status);
+}
 // all-reduce(max) of words[0..3) (|F|_inf bits, defect bits, status) over the ranks: push, wait, reduce — one warp
+// (bc_* != nullptr: the rows of the boundary conditions this rank owns are folded into words[0] first — the work of
+//  k_bc_norm_masked — so the norm exchange is one launch)
 __global__ void __launch_bounds__(32)
 k_words_allmax(unsigned long long* __restrict__ words, double* __restrict__ xbuf, XchgPeers peers, XchgLayout lay, int rank,
-               unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
+               unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status, const double* __restrict__ bc_resid, int L,
+               int La, size_t tail_off, int own_a, int own_b) {
     const int lane = threadIdx.x, G = lay.G;
+    if (bc_resid) {
+        unsigned long long m = 0ull;
+        for (int q = lane; q < L; q += 32) {
+            const bool is_a = q < La;
+            if ((is_a && own_a) || (!is_a && own_b)) {
+                const double v = is_a ? bc_resid[q] : bc_resid[tail_off + (q - La)];
+                const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+                m = b > m ? b : m;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        if (lane == 0 && m > words[0]) words[0] = m;
+        __syncwarp();
+    }
     const unsigned long long e = *epoch_ptr + 1ull, par = e & 1ull;
     unsigned long long w0 = 0ull, w1 = 0ull, w2 = 0ull;
     if (lane < G) {

@@ -477,12 +477,14 @@ constexpr int kTailWarps = 8;
 
 // (A cooperative multi-CTA variant with one warp per SM and grid barriers between levels was measured
 // slower: ~20 grid syncs cost more than the shared-memory contention they avoid — profiles/r01_notes.md.)
+// shared-memory buffers of a tail / segment block (one set per kernel)
+template <int n> struct TailSmem {
+    double pbuf[kTailWarps][reduce_smem_doubles<n, false>()];
+    double dbuf[kTailWarps][2][16];
+};
+
 template <int n>
-__global__ void __launch_bounds__(kTailWarps * 32, 1)
-k_tail_warp(const TailArgs a) {
-    extern __shared__ double tail_smem[];
-    __shared__ __align__(16) double pbuf[kTailWarps][reduce_smem_doubles<n, false>()];
-    __shared__ __align__(16) double dbuf[kTailWarps][2][16];
+__device__ __forceinline__ void tail_body(const TailArgs& a, TailSmem<n>& sm, double* tail_smem) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (int l = 0; l < a.nlev && (a.mode & 1); l++) {
         const int per = a.multi ? ((kTailWarps >> l) > 0 ? (kTailWarps >> l) : 1) : a.G[l];
@@ -490,7 +492,7 @@ k_tail_warp(const TailArgs a) {
         const int ge = gb + per < a.G[l] ? gb + per : a.G[l];
         for (int g = gb + wib; g < ge; g += kTailWarps) {
             if (!reduce_group<n, false>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l],
-                                        a.gs[l], a.TL, a.TR, a.rt, pbuf[wib], lane))
+                                        a.gs[l], a.TL, a.TR, a.rt, sm.pbuf[wib], lane))
                 if (lane == 0) atomicExch(a.status, 1);
         }
         __syncthreads();
@@ -504,9 +506,71 @@ k_tail_warp(const TailArgs a) {
         const int gb = a.multi ? (int)blockIdx.x * per : 0;
         const int ge = gb + per < a.G[l] ? gb + per : a.G[l];
         for (int g = gb + wib; g < ge; g += kTailWarps)
-            warp_backsub_group<n>(g, a.nodes[l], a.gs[l], a.TL, a.TR, a.rt, a.delta, dbuf[wib][0], dbuf[wib][1], lane);
+            warp_backsub_group<n>(g, a.nodes[l], a.gs[l], a.TL, a.TR, a.rt, a.delta, sm.dbuf[wib][0], sm.dbuf[wib][1], lane);
         __syncthreads();
     }
+}
+
+// (A cooperative multi-CTA variant with one warp per SM and grid barriers between levels was measured
+// slower: ~20 grid syncs cost more than the shared-memory contention they avoid — profiles/r01_notes.md.)
+template <int n>
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
+k_tail_warp(const TailArgs a) {
+    extern __shared__ double tail_smem[];
+    __shared__ __align__(16) TailSmem<n> sm;
+    tail_body<n>(a, sm, tail_smem);
+}
+
+// ---- mesh-partitioned mode, peer-memory exchange (abd.cuh): the interface step of a Newton iteration in TWO
+// kernels instead of seven graph nodes.
+//   k_part_tail_push   the local tail levels of this segment (as k_tail_warp, mode 1) and, from the same block, the
+//                      push of the collapsed relation into every peer's exchange buffer
+//   k_part_interface   wait for all ranks' relations, unpack, reduce + close + back-substitute the interface system
+//                      (k_tail_warp on the interface plan, mode 7), hand this rank's two end-node updates to the local
+//                      system and back-substitute the local tail levels (mode 4)
+struct PartPushArgs {
+    int L, La;
+    const double *relL, *relR, *relr, *Bc, *resid;
+    size_t tail_off;
+    XchgPeers peers;
+    XchgLayout lay;
+    int rank;
+    unsigned long long* epoch;
+};
+struct PartIfaceArgs {
+    int L, La, rank, Nloc;
+    double* xbuf;
+    XchgLayout lay;
+    double *if_L, *if_R, *if_r, *if_Bc, *if_resid, *if_delta, *delta;
+    unsigned long long* epoch;
+    int* status;
+};
+
+template <int n>
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
+k_part_tail_push(const TailArgs a, const PartPushArgs ps) {
+    extern __shared__ double tail_smem[];
+    __shared__ __align__(16) TailSmem<n> sm;
+    if (a.nlev > 0) tail_body<n>(a, sm, tail_smem);
+    __syncthreads();  // the collapsed relation is complete (global writes + block barrier)
+    part_push_body(n, ps.L, ps.La, ps.relL, ps.relR, ps.relr, ps.Bc, ps.resid, ps.tail_off, ps.peers, ps.lay, ps.rank, ps.epoch);
+}
+
+template <int n>
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
+k_part_interface(const PartIfaceArgs w, const TailArgs ai, const TailArgs al) {
+    extern __shared__ double tail_smem[];
+    __shared__ __align__(16) TailSmem<n> sm;
+    part_wait_unpack_body(n, w.L, w.La, w.xbuf, w.lay, w.if_L, w.if_R, w.if_r, w.if_Bc, w.if_resid, w.epoch, w.status);
+    __syncthreads();
+    tail_body<n>(ai, sm, tail_smem);  // interface system: reduce, closing solve, back substitution
+    __syncthreads();
+    if (threadIdx.x < n) {  // this rank's two end nodes
+        w.delta[threadIdx.x] = w.if_delta[(size_t)w.rank * n + threadIdx.x];
+        w.delta[(size_t)(w.Nloc - 1) * n + threadIdx.x] = w.if_delta[(size_t)(w.rank + 1) * n + threadIdx.x];
+    }
+    __syncthreads();
+    if (al.nlev > 0) tail_body<n>(al, sm, tail_smem);  // local tail levels, back substitution only (mode 4)
 }
 
 inline bool warp_reduce_supported(int n) { return n == 2 || n == 4 || n == 6 || n == 8 || n == 16; }
@@ -536,6 +600,29 @@ inline void launch_warp_reduce(cudaStream_t st, int n, int G, const double* inL,
         MIRK_WARP_DISPATCH(n, (k_reduce_warp<NN, 3><<<blocks, 32 * wpb, 0, st>>>(G, inL, inR, inr, outL, outR, outr, nodes, gs,
                                                                            TL, TR, rt, status)));
     }
+}
+inline cudaError_t launch_part_tail_push(cudaStream_t st, int n, const TailArgs& a, const PartPushArgs& ps) {
+    MIRK_WARP_DISPATCH(n, (k_part_tail_push<NN><<<1, kTailWarps * 32, 0, st>>>(a, ps)));
+    return cudaGetLastError();
+}
+template <int NN> inline void launch_part_interface_n(cudaStream_t st, const PartIfaceArgs& w, const TailArgs& ai, const TailArgs& al,
+                                                      int smem_bytes) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_part_interface<NN>) == cudaSuccess) {
+            const int room = 227 * 1024 - (int)fa.sharedSizeBytes - 1024;
+            cudaFuncSetAttribute(k_part_interface<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, room < 160 * 1024 ? room : 160 * 1024);
+        }
+        cudaGetLastError();
+        attr_set = true;
+    }
+    k_part_interface<NN><<<1, kTailWarps * 32, smem_bytes, st>>>(w, ai, al);
+}
+inline cudaError_t launch_part_interface(cudaStream_t st, int n, const PartIfaceArgs& w, const TailArgs& ai, const TailArgs& al,
+                                         int smem_bytes) {
+    MIRK_WARP_DISPATCH(n, (launch_part_interface_n<NN>(st, w, ai, al, smem_bytes)));
+    return cudaGetLastError();
 }
 inline cudaError_t launch_warp_tail(cudaStream_t st, int n, const TailArgs& a, int ctas, int smem_bytes) {
     MIRK_WARP_DISPATCH(n, (k_tail_warp<NN><<<ctas, kTailWarps * 32, smem_bytes, st>>>(a)));

@@ -50,6 +50,10 @@ __host__ __device__ __forceinline__ int interval_of(const double* mesh, int N, d
     return j - 1;
 }
 
+// singular BVPs y' = S y / t + f(t, y): the functor says so with `has_singular_term` and provides S u
+template <class P, class = void> struct HasSingular { static constexpr bool value = false; };
+template <class P> struct HasSingular<P, decltype((void)P::has_singular_term)> { static constexpr bool value = P::has_singular_term; };
+
 // ---- one interval: stages and residual (Appendix A.1) -----------------------------------------
 // K is [s][n] of T.  Works for T = double (residual) and T = Dual (one Jacobian column).
 template <class P, int ORDER, class T>
@@ -78,6 +82,17 @@ __device__ __forceinline__ void phi_interval(const T* __restrict__ yi, const T* 
             }
         }
         P::template f<T>(K[r], tmp, p, ti + TB::c(r) * h);
+        if constexpr (HasSingular<P>::value) {
+            // __add_singular_term!: K_r += S tmp / t for t > 0 (CORE/src/utils.jl:932-941)
+            const double tt = ti + TB::c(r) * h;
+            if (tt > 0.0) {
+                T sv[n];
+                P::template singular<T>(sv, tmp, p);
+                const double it = 1.0 / tt;
+#pragma unroll (unroll_for(n))
+                for (int k = 0; k < n; k++) K[r][k] = K[r][k] + it * sv[k];
+            }
+        }
     }
 #pragma unroll (unroll_for(n))
     for (int k = 0; k < n; k++) {

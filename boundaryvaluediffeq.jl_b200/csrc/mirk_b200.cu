@@ -52,7 +52,7 @@ static int fail(int code, const std::string& msg) {
 // ---- registry -----------------------------------------------------------------------------------
 static const char* kBuiltinNames[problems::kNumBuiltin] = {
     "pendulum", "linear2", "linear2_tp", "swirling", "lotka", "torus", "layer", "chain8", "chain16",
-    "bratu64"};
+    "bratu64", "lane_emden"};
 
 struct Plugin {
     std::string name;
@@ -65,7 +65,7 @@ static const int kPluginBase = 1000;
 
 static const ProblemOps* find_ops(int id, int order) {
     using namespace problems;
-    if (id >= 0 && id <= kLayer)
+    if ((id >= 0 && id <= kLayer) || id == kLaneEmden)
         return (order == 4 || order == 6) ? ops_small(id, order) : order == kMIRK6I ? ops_small_6i(id, order) : ops_small_235(id, order);
     if (id == kChain8) return ops_chain8(order);
     if (id == kChain16) return ops_chain16(order);
@@ -483,16 +483,18 @@ static int eval_bc(mirk_solver_s* S, int want_jac, bool into_norm) {
     if (S->ops->problem_type == 0) S->ki_dirty = true;  // interior boundary times fill their interval's Ki
     if (S->part && into_norm) {
         const size_t tail_off = (size_t)S->La + (size_t)(S->N - 1) * S->n;
-        k_bc_norm_masked<<<1, 128, 0, S->st>>>(S->L, S->La, S->resid, tail_off, S->rank == 0, S->rank == S->nranks - 1,
-                                               S->words);
-        S->launches++;
         // |F|_inf, the defect word and the singular-pivot status word travel together, so every rank sees the same
         // values and takes the same exit from the Newton loop (a rank-local failure would otherwise leave the
         // other ranks waiting in the next collective)
         if (S->p2p) {
-            k_words_allmax<<<1, 32, 0, S->st>>>(S->words, S->xbuf, S->peers, S->xlay, S->rank, S->xepoch + 1, (int*)(S->words + 2));
+            // the boundary rows this rank owns are folded in by the same kernel
+            k_words_allmax<<<1, 32, 0, S->st>>>(S->words, S->xbuf, S->peers, S->xlay, S->rank, S->xepoch + 1, (int*)(S->words + 2),
+                                                S->resid, S->L, S->La, tail_off, S->rank == 0, S->rank == S->nranks - 1);
             S->launches++;
         } else {
+            k_bc_norm_masked<<<1, 128, 0, S->st>>>(S->L, S->La, S->resid, tail_off, S->rank == 0, S->rank == S->nranks - 1,
+                                                   S->words);
+            S->launches++;
             CKN(g_nccl.AllReduce(S->words, S->words, 3, ncclUint64, ncclMax, S->comm, S->st));
         }
     }
@@ -681,6 +683,35 @@ static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
             return launch_check("abd_tail");
         }
         a.mode = 1;  // reduce the tail levels, exchange + close the interface system, back-substitute them
+        static const bool fuse_iface = !(getenv("MIRK_PART_FUSED") && atoi(getenv("MIRK_PART_FUSED")) == 0);
+        Plan& IP = S->iplan;
+        if (S->p2p && fuse_iface && IP.tail_begin == 0) {
+            // peer-memory exchange, interface system small enough for the one-block tail: two kernels for the whole
+            // interface step (abd_warp.cuh: k_part_tail_push, k_part_interface)
+            PartPushArgs ps{S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid, C.tail_off,
+                            S->peers, S->xlay, S->rank, S->xepoch};
+            CK(launch_part_tail_push(S->st, n, a, ps));
+            SolveCtx I{&S->iplan, S->if_TL, S->if_TR, S->if_rt, S->if_delta, S->if_Bc, S->if_bc_nodes, S->if_m, S->if_resid,
+                       (size_t)S->La, false};
+            TailArgs ai;
+            fill_tail_levels(ai, IP, I, 0, IP.nlev, (int*)(S->words + 2));
+            ai.mode = 7;
+            ai.Q = IP.Q; ai.kept = IP.d_nodes[IP.nlev];
+            ai.relL = IP.relL[IP.nlev]; ai.relR = IP.relR[IP.nlev]; ai.relr = IP.relr[IP.nlev];
+            ai.L = S->L; ai.La = S->La; ai.m_ptr = I.m_dev; ai.bc_nodes = I.bc_nodes; ai.Bc = I.Bc; ai.resid = I.resid;
+            ai.tail_off = I.tail_off;
+            const int Di = IP.Q * n;
+            const bool mi_smem = final_smem_bytes(Di, true) <= kTailDynLimit;
+            ai.M = mi_smem ? nullptr : S->Mfinal;
+            ai.delta = I.delta;
+            TailArgs al = a;
+            al.mode = 4;
+            PartIfaceArgs w{S->L, S->La, S->rank, S->N, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid,
+                            S->if_delta, S->delta, S->xepoch, (int*)(S->words + 2)};
+            CK(launch_part_interface(S->st, n, w, ai, al, final_smem_bytes(Di, mi_smem)));
+            S->launches += 2;
+            return launch_check("abd_tail_partitioned_fused");
+        }
         if (a.nlev > 0) { CK(launch_warp_tail(S->st, n, a, 1, 0)); S->launches++; }
         CKS(part_exchange_and_close(S));
         a.mode = 4;
@@ -738,7 +769,7 @@ static int abd_backsub(mirk_solver_s* S, const SolveCtx& C) {
 // fused update: the level-0 back substitution of the warp path can apply y -= delta on the fly (every node is
 // either recovered there or the left end of a level-0 group), which saves the separate pass over y and delta
 static bool can_fuse_update(const mirk_solver_s* S) {
-    return warp_reduce_supported(S->n) && !S->part && S->plan.valid && S->plan.tail_begin >= 1 && S->plan.nlev >= 1;
+    return warp_reduce_supported(S->n) && S->plan.valid && S->plan.tail_begin >= 1 && S->plan.nlev >= 1;
 }
 
 static int linear_solve(mirk_solver_s* S, bool with_update = false) {
@@ -1936,7 +1967,7 @@ struct mirk_ensemble_s {
 };
 
 static const EnsembleOps* find_ensemble_ops(int id, int order) {
-    if (id >= 0 && id <= problems::kLayer) return ensemble_ops_small(id, order);
+    if ((id >= 0 && id <= problems::kLayer) || id == problems::kLaneEmden) return ensemble_ops_small(id, order);
     return nullptr;
 }
 

@@ -64,7 +64,7 @@ template <class P, int ORDER> struct OpsImpl {
     }
     // large state dimension: stage Jacobians + dense DMMA chain-rule products (stagejac.cuh); MIRK_RESJAC=tape keeps
     // the per-column taped sweep for A/B runs
-    static constexpr bool kDense = (P::n == 64 || P::n == 128) && (ORDER == 4 || ORDER == 6);
+    static constexpr bool kDense = (P::n == 64 || P::n == 128) && (ORDER == 4 || ORDER == 6) && !HasSingular<P>::value;
     static constexpr size_t kDenseBatchDoubles = (size_t)1 << 28;  // 2 GiB of scratch at most: longer meshes run in batches
     static bool dense_enabled() {
         static const bool off = getenv("MIRK_RESJAC") && (!strcmp(getenv("MIRK_RESJAC"), "tape") || !strcmp(getenv("MIRK_RESJAC"), "dual"));

@@ -7,6 +7,7 @@ const EnsembleOps* ensemble_ops_part_b(int id, int order) {
     case kLinear2TP: ENS2(Linear2TP)
     case kLotka: ENS2(Lotka)
     case kLayer: ENS2(Layer)
+    case kLaneEmden: ENS2(LaneEmden)
     default: return nullptr;
     }
 }

@@ -15,6 +15,7 @@ const ProblemOps* ops_small(int id, int order) {
     case kLotka: OPS2(Lotka, "lotka")
     case kTorus: OPS2(Torus, "torus")
     case kLayer: OPS2(Layer, "layer")
+    case kLaneEmden: OPS2(LaneEmden, "lane_emden")
     default: return nullptr;
     }
 }

@@ -14,6 +14,7 @@ const ProblemOps* ops_small_6i(int id, int order) {
     case kLotka: OPS6I(Lotka, "lotka")
     case kTorus: OPS6I(Torus, "torus")
     case kLayer: OPS6I(Layer, "layer")
+    case kLaneEmden: OPS6I(LaneEmden, "lane_emden")
     default: return nullptr;
     }
 }

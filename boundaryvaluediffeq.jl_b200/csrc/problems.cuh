@@ -7,6 +7,8 @@
 //     template<class T> static void f(T* du, const T* u, const double* p, double t)
 //     static int  bc_times(double* times, const double* p, double t0, double t1)
 //     template<class T> static void bc(T* res, const T* U /* m×n */, const double* p)
+//   optional (singular BVPs, prob.singular_term):  static constexpr bool has_singular_term = true;
+//     template<class T> static void singular(T* out, const T* u, const double* p)     out = S u
 // `T` is double for residuals; for Jacobians it is mirk::Dual (plain forward mode) or the pair mirk::RecVal /
 // mirk::TapeDual of the taped kernel (tape.cuh) — one templated source serves all, like ForwardDiff on the
 // Julia side.  Write elementary functions unqualified after `using namespace mirk::fn;` (sin, cos, exp, log,
@@ -198,9 +200,31 @@ template <int M> struct BratuMOL {
     }
 };
 
+// 10: Lane-Emden equation of index 1 as a SINGULAR BVP  y' = S y / t + f(t, y)  (lib/BoundaryValueDiffEqMIRK/test/Core/
+//     singular_bvp_tests.jl:15-61): y'' + (2/t) y' + y = 0, y(0) = 1, y(1) = sin(1), exact solution sin(t)/t.
+//     `singular` returns S u (here S = [0 0; 0 -2]); the collocation adds it, divided by t, to every DISCRETE stage
+//     with t > 0 (CORE/src/utils.jl:932-941, MIRK/src/collocation.jl:65) — not to the interpolation stages.
+struct LaneEmden {
+    static constexpr int n = 2, np = 0, n_bc = 2, n_bca = 1, problem_type = 1, max_bc_pts = 2;
+    static constexpr bool has_singular_term = true;
+    MIRK_PF f(T* du, const T* u, const double*, double) {
+        du[0] = u[1];
+        du[1] = -u[0];
+    }
+    MIRK_PF singular(T* out, const T* u, const double*) {
+        out[0] = 0.0 * u[0];
+        out[1] = -2.0 * u[1];
+    }
+    MIRK_PT bc_times(double* tm, const double*, double t0, double t1) { return ends_times(tm, t0, t1); }
+    MIRK_PF bc(T* r, const T* U, const double*) {
+        r[0] = U[0] - 1.0;
+        r[1] = U[2] - 0.84147098480789650665;  // sin(1)
+    }
+};
+
 enum BuiltinId {
     kPendulum = 0, kLinear2 = 1, kLinear2TP = 2, kSwirling = 3, kLotka = 4, kTorus = 5, kLayer = 6,
-    kChain8 = 7, kChain16 = 8, kBratu64 = 9, kNumBuiltin = 10
+    kChain8 = 7, kChain16 = 8, kBratu64 = 9, kLaneEmden = 10, kNumBuiltin = 11
 };
 
 }  // namespace problems

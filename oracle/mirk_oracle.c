@@ -312,7 +312,14 @@ void orc_phi(const orc_problem *P, const orc_tableau *T, const double *p, int N,
             /* __maybe_matmul!(tmp, K[:,1:r-1], x[r,1:r-1], h, 1): tmp += h * K_j * x_rj, j ascending */
             for (int j = 0; j < r; j++)
                 for (int k = 0; k < n; k++) tmp[k] = h * K[j * n + k] * T->x[r][j] + tmp[k];
-            P->f(K + r * n, tmp, p, mesh[i] + T->c[r] * h, P->ctx);
+            const double tt = mesh[i] + T->c[r] * h;
+            P->f(K + r * n, tmp, p, tt, P->ctx);
+            if (P->singular_term && tt > 0.0) /* __add_singular_term!: K_r += S tmp / t (CORE/utils.jl:932-941) */
+                for (int k = 0; k < n; k++) {
+                    double acc = 0.0;
+                    for (int j = 0; j < n; j++) acc += P->singular_term[k * n + j] * tmp[j];
+                    K[r * n + k] += acc / tt;
+                }
         }
         double *res = phi + (size_t)i * n;
         for (int k = 0; k < n; k++) res[k] = yi1[k] - yi[k];
@@ -449,6 +456,14 @@ void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p,
             const double tt = mesh[i] + T->c[r] * h;
             P->f(K + r * n, tmp, p, tt, P->ctx);
             P->dfdu(J, tmp, p, tt, P->ctx);
+            if (P->singular_term && tt > 0.0) {
+                for (int k = 0; k < n; k++) {
+                    double acc = 0.0;
+                    for (int j = 0; j < n; j++) acc += P->singular_term[k * n + j] * tmp[j];
+                    K[r * n + k] += acc / tt;
+                }
+                for (int e = 0; e < nn; e++) J[e] += P->singular_term[e] / tt;
+            }
             /* A_r = J_r [(1-v_r) I + h sum_j x_rj A_j] */
             for (int e = 0; e < nn; e++) M[e] = 0.0;
             for (int k = 0; k < n; k++) M[k * n + k] = 1.0 - T->v[r];

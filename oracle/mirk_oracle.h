@@ -54,6 +54,8 @@ typedef struct {
     orc_bc_fn bc;
     orc_bc_jac_fn dbc;
     void *ctx;
+    const double *singular_term; /* prob.singular_term: n×n row-major S of y' = S y / t + f(t, y), or NULL
+                                    (CORE/src/utils.jl:932-941; added to the discrete stages with t > 0 only) */
 } orc_problem;
 
 typedef struct {

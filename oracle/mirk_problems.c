@@ -19,6 +19,7 @@
  *   7 chain8        SURVEY.md §8d C2: 8 torsionally coupled pendula, n=16, two-point
  *   8 chain16       SURVEY.md §8d C5: 16 pendula, n=32
  *   9 bratu64       SURVEY.md §8d C4: 2-D Bratu by method of lines, n=128
+ *  10 lane_emden    lib/BoundaryValueDiffEqMIRK/test/Core/singular_bvp_tests.jl:15-61 (singular_term S = [0 0; 0 -2])
  */
 #include "mirk_oracle.h"
 
@@ -303,10 +304,33 @@ static void bratu_dbc(double *d, const double *U, const double *p, void *c) {
     for (int j = 0; j < M; j++) { d[j * 2 * n + j] = 1.0; d[(M + j) * 2 * n + n + j] = 1.0; }
 }
 
-static const char *NAMES[] = {"pendulum", "linear2", "linear2_tp", "swirling", "lotka",
-                              "torus", "layer", "chain8", "chain16", "bratu64"};
+/* ---- 10: Lane-Emden index 1, y' = S y / t + f, f = [y2, -y1], S = [0 0; 0 -2]; y(0) = 1, y(1) = sin 1 ------------- */
+static void lane_f(double *du, const double *u, const double *p, double t, void *c) {
+    (void)p; (void)t; (void)c;
+    du[0] = u[1];
+    du[1] = -u[0];
+}
+static void lane_df(double *J, const double *u, const double *p, double t, void *c) {
+    (void)u; (void)p; (void)t; (void)c;
+    J[0] = 0.0; J[1] = 1.0; J[2] = -1.0; J[3] = 0.0;
+}
+static void lane_bc(double *r, const double *U, const double *p, void *c) {
+    (void)p; (void)c;
+    r[0] = U[0] - 1.0;
+    r[1] = U[2] - sin(1.0);
+}
+static void lane_dbc(double *d, const double *U, const double *p, void *c) {
+    (void)U; (void)p; (void)c;
+    memset(d, 0, sizeof(double) * 2 * 4);
+    d[0 * 4 + 0] = 1.0;
+    d[1 * 4 + 2] = 1.0;
+}
+static const double LANE_S[4] = {0.0, 0.0, 0.0, -2.0};
 
-const char *orc_builtin_name(int id) { return (id >= 0 && id < 10) ? NAMES[id] : 0; }
+static const char *NAMES[] = {"pendulum", "linear2", "linear2_tp", "swirling", "lotka",
+                              "torus", "layer", "chain8", "chain16", "bratu64", "lane_emden"};
+
+const char *orc_builtin_name(int id) { return (id >= 0 && id < 11) ? NAMES[id] : 0; }
 
 int orc_builtin_problem(int id, orc_problem *P) {
     memset(P, 0, sizeof(*P));
@@ -321,6 +345,10 @@ int orc_builtin_problem(int id, orc_problem *P) {
     case 7: *P = (orc_problem){16, 18, 1, 16, 8, chain8_f, chain8_df, ends_times, chain8_bc, chain8_dbc, 0}; break;
     case 8: *P = (orc_problem){32, 34, 1, 32, 16, chain16_f, chain16_df, ends_times, chain16_bc, chain16_dbc, 0}; break;
     case 9: *P = (orc_problem){128, 1, 1, 128, 64, bratu_f, bratu_df, ends_times, bratu_bc, bratu_dbc, 0}; break;
+    case 10:
+        *P = (orc_problem){2, 0, 1, 2, 1, lane_f, lane_df, ends_times, lane_bc, lane_dbc, 0};
+        P->singular_term = LANE_S;
+        break;
     default: return -1;
     }
     return 0;

@@ -56,6 +56,8 @@ CASES = [
     ("layer", 6, [0.1], (-1.0, 1.0), 64), ("chain8", 6, None, (0.0, 0.5), 100), ("chain8", 4, None, (0.0, 0.5), 37),
     ("chain16", 6, None, (0.0, 0.5), 41), ("bratu64", 4, [1.0], (0.0, 1.0), 19),
     ("bratu64", 6, [1.0], (0.0, 1.0), 11),   # MIRK6 through the stage-wise dense Jacobian (three chained DMMA products)
+    # singular BVP y' = S y / t + f (prob.singular_term; the first interval starts at t = 0 where the term is skipped)
+    ("lane_emden", 4, [], (0.0, 1.0), 25), ("lane_emden", 6, [], (0.0, 1.0), 14), ("lane_emden", 3, [], (0.0, 1.0), 9),
     # the rest of the MIRK family: MIRK2, MIRK3, MIRK5
     ("pendulum", 2, [9.81], PENDULUM_T, 32), ("pendulum", 3, [9.81], PENDULUM_T, 32), ("pendulum", 5, [9.81], PENDULUM_T, 32),
     ("swirling", 5, [0.01], (0.0, 1.0), 31), ("torus", 3, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 20),
@@ -159,6 +161,11 @@ SOLVES = [
     ("pendulum", 3, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {}),
     ("pendulum", 2, [9.81], PENDULUM_U0, PENDULUM_T, 0.05, {"abstol": 1e-4}),
     ("linear2", 5, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),
+    # singular term (lib/BoundaryValueDiffEqMIRK/test/Core/singular_bvp_tests.jl): fixed mesh — the reference's defect
+    # estimate leaves the singular term out (adaptivity.jl:370-415 calls f alone), so an ADAPTIVE solve of a genuinely
+    # singular problem never meets its tolerance near t = 0 and ends in Failure by repeated halving; reproduced below
+    ("lane_emden", 4, [], [1.0, 0.0], (0.0, 1.0), 0.01, {"adaptive": False}),
+    ("lane_emden", 6, [], [1.0, 0.0], (0.0, 1.0), 0.02, {"adaptive": False}),
     ("linear2", 3, LIN_P, [5.0, -3.5], (0.0, 5.0), 0.2, {}),
     ("linear2_tp", 2, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.2, {"abstol": 1e-4}),
     ("swirling", 5, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),
@@ -518,3 +525,13 @@ def test_polyalgorithm_inside_the_adaptive_solve(M, oracle):
     # (the first outer iteration's count contains the two diverging sub-solvers, whose step counts are not reproducible)
     assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"][1:] == ref.hist_newton[1:]
     assert _rel(sol.u, ref.u) < 1e-7
+
+
+def test_adaptive_singular_problem_fails_like_the_reference_would(M, oracle):
+    """The reference's defect estimate evaluates f alone (adaptivity.jl:370-415), without the singular term: on a
+    genuinely singular problem the defect near t = 0 never meets the tolerance and the adaptive loop halves the mesh
+    until max_num_subintervals says Failure.  Same mesh history on both sides."""
+    ref = oracle.solve_dt(oracle.builtin("lane_emden"), 4, [], [1.0, 0.0], (0.0, 1.0), 0.05, max_num_subintervals=200)
+    sol = M.solve(M.BVProblem("lane_emden", [1.0, 0.0], (0.0, 1.0), p=[]), M.MIRK4(max_num_subintervals=200), dt=0.05)
+    assert sol.retcode == ref.retcode == M.ReturnCode.Failure
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton

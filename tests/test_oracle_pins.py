@@ -533,3 +533,33 @@ def test_polyalgorithm_order_and_stalled(oracle):
         runs[alg] = ws.nlsolve(alg, maxiters=200)
     assert runs[1][0] != 0 and runs[2][0] == O.STALLED and runs[3][0] == 0
     assert runs[0][0] == 0 and runs[0][1] == runs[1][1] + runs[2][1] + runs[3][1]
+
+
+def test_singular_term_lane_emden(oracle):
+    """prob.singular_term (CORE/src/utils.jl:932-941): y' = S y / t + f(t, y) with S = [0 0; 0 -2], f = [y2, -y1] is the
+    Lane-Emden equation of index 1, exact solution sin(t)/t (MIRK/test/Core/singular_bvp_tests.jl:15-21).  The term enters
+    the discrete stages with t > 0 only — so the stage at t = 0 of the first interval misses the (finite) limit of S y / t,
+    and the fixed-mesh solution converges to the exact one at SECOND order whatever the tableau (a property of the
+    reference's rule, reproduced).  The analytic Jacobian (df/du + S/t) agrees with central differences."""
+    O = oracle
+    P = O.builtin("lane_emden")
+    errs = []
+    for nint in (50, 100):
+        sol = O.solve_dt(P, 4, [], [1.0, 0.0], (0.0, 1.0), 1.0 / nint, adaptive=0)
+        assert sol.retcode == 0
+        t = sol.t[1:]
+        errs.append(np.max(np.abs(sol.u[1:, 0] - np.sin(t) / t)))
+    assert errs[1] < 1e-5 and 3.5 < errs[0] / errs[1] < 4.5
+    mesh = O.mesh_uniform(0.0, 1.0, 10)
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((11, 2))
+    ws = O.Workspace(P, 4, [], mesh, y)
+    J = ws.dense_jacobian()
+    eps = 1e-6
+    Jfd = np.zeros_like(J)
+    for k in range(y.size):
+        yp, ym = y.copy().ravel(), y.copy().ravel()
+        yp[k] += eps
+        ym[k] -= eps
+        Jfd[:, k] = (O.Workspace(P, 4, [], mesh, yp.reshape(y.shape)).loss() - O.Workspace(P, 4, [], mesh, ym.reshape(y.shape)).loss()) / (2 * eps)
+    assert np.max(np.abs(J - Jfd)) < 1e-6 * max(1.0, np.max(np.abs(J)))
