@@ -29,7 +29,8 @@ class Desc(C.Structure):
                 ("adaptive", C.c_int32), ("defect_threshold", C.c_double),
                 ("max_num_subintervals", C.c_int32), ("maxiters", C.c_int32),
                 ("reinterp_inplace", C.c_int32), ("chunk", C.c_int32), ("device", C.c_int32),
-                ("n_params", C.c_int32), ("params", dp), ("nlsolve", C.c_int32)]
+                ("n_params", C.c_int32), ("params", dp), ("nlsolve", C.c_int32),
+                ("controller", C.c_int32), ("ge_method", C.c_int32), ("DE", C.c_double), ("GE", C.c_double)]
 
 
 class ProblemInfo(C.Structure):

@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib as B
 
-__all__ = ["NewtonRaphson", "BackTracking", "TrustRegion", "BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
+__all__ = ["GlobalErrorControl", "SequentialErrorControl", "HybridErrorControl", "HOErrorControl", "REErrorControl", "NewtonRaphson", "BackTracking", "TrustRegion", "BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
            "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b",
            "EnsembleProblem", "EnsembleSolution", "EnsembleB200", "compile_device_function",
            "successful_retcode"]
@@ -156,6 +156,52 @@ def TwoPointBVProblem(f, u0, tspan, p=(), **kw) -> BVProblem:
 class DefectControl:
     """CORE/src/calc_errors.jl:54-60"""
     defect_threshold: float = 0.1
+
+
+@dataclass(frozen=True)
+class HOErrorControl:
+    """CORE/src/calc_errors.jl:126 — global error from the method of order + 2 on the same mesh"""
+
+
+@dataclass(frozen=True)
+class REErrorControl:
+    """CORE/src/calc_errors.jl:139 — Richardson extrapolation: the same method on the halved mesh"""
+
+
+@dataclass(frozen=True)
+class GlobalErrorControl:
+    """CORE/src/calc_errors.jl:67-73"""
+    method: object = field(default_factory=HOErrorControl)
+
+
+@dataclass(frozen=True)
+class SequentialErrorControl:
+    """CORE/src/calc_errors.jl:80-87: defect control first, global-error control once the defect passes"""
+    defect: DefectControl = field(default_factory=DefectControl)
+    global_error: GlobalErrorControl = field(default_factory=GlobalErrorControl)
+
+
+@dataclass(frozen=True)
+class HybridErrorControl:
+    """CORE/src/calc_errors.jl:94-106: error = DE * defect + GE * global error"""
+    DE: float = 1.0
+    GE: float = 1.0
+    defect: DefectControl = field(default_factory=DefectControl)
+    global_error: GlobalErrorControl = field(default_factory=GlobalErrorControl)
+
+
+def _controller_fields(c):
+    """controller -> (code, ge_method, DE, GE, defect_threshold) of the C ABI"""
+    gm = lambda g: 1 if isinstance(g.method, REErrorControl) else 0  # noqa: E731
+    if isinstance(c, DefectControl):
+        return 0, 0, 1.0, 1.0, float(c.defect_threshold)
+    if isinstance(c, GlobalErrorControl):
+        return 1, gm(c), 1.0, 1.0, 0.1
+    if isinstance(c, SequentialErrorControl):
+        return 2, gm(c.global_error), 1.0, 1.0, float(c.defect.defect_threshold)
+    if isinstance(c, HybridErrorControl):
+        return 3, gm(c.global_error), float(c.DE), float(c.GE), float(c.defect.defect_threshold)
+    raise NotImplementedError(f"unknown error controller {type(c).__name__}")
 
 
 @dataclass(frozen=True)
@@ -297,8 +343,7 @@ class MIRKCache:
                  adaptive: bool = True, controller: DefectControl = DefectControl(), nlsolve_kwargs=None,
                  optimize_kwargs=None, verbose=None, device: int = 0, chunk: int = 0,
                  reinterp_inplace: bool = False):
-        if not isinstance(controller, DefectControl):
-            raise NotImplementedError("only DefectControl is on the B200 path")
+        ctrl, gem, DE, GE, thr = _controller_fields(controller)
         self.prob, self.alg, self.verbose = prob, alg, verbose
         self.nlsolve_kwargs = dict(nlsolve_kwargs or {})
         self.nlsolve_kwargs.setdefault("abstol", abstol)
@@ -310,9 +355,9 @@ class MIRKCache:
         p = prob.p
         self._p = p
         desc = B.Desc(prob.f.problem_id, alg.order, float(self.nlsolve_kwargs["abstol"]), int(bool(adaptive)),
-                      float(controller.defect_threshold), int(alg.max_num_subintervals),
+                      thr, int(alg.max_num_subintervals),
                       int(self.nlsolve_kwargs.get("maxiters", 1000)), int(reinterp_inplace), int(chunk), int(device),
-                      len(p), _d(p) if len(p) else None, _nlsolve_code(alg.nlsolve))
+                      len(p), _d(p) if len(p) else None, _nlsolve_code(alg.nlsolve), ctrl, gem, DE, GE)
         self._h = B.Handle()
         B.check(B.lib().mirk_create(C.byref(desc), C.byref(self._h)))
         t0, t1 = prob.tspan

@@ -116,6 +116,40 @@ __global__ void k_fill_nodes(int N, int n, const double* __restrict__ u0, double
     if (i < (size_t)N * n) y[i] = u0[i % n];
 }
 
+// ---- global-error estimate (MIRK/src/adaptivity.jl:464-567) -------------------------------------------------------
+// halve_sol: nodes copied, midpoints averaged (guess of the Richardson solve on the halved mesh)
+__global__ void k_halve_sol(int n, int N, const double* __restrict__ y, double* __restrict__ y2) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)(2 * (N - 1) + 1) * n) return;
+    const size_t j = e / n;
+    const int k = (int)(e % n);
+    y2[e] = (j & 1) ? (y[(j / 2 + 1) * n + k] + y[(j / 2) * n + k]) / 2.0 : y[(j / 2) * n + k];
+}
+// err = (y_high[stride * i] - y) / (1 + |y|) per node, and its max-norm per node into nm
+__global__ void k_ge_node(int n, int N, int stride, const double* __restrict__ yh, const double* __restrict__ y,
+                          double* __restrict__ err, double* __restrict__ nm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double m = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double lo = y[(size_t)i * n + k];
+        const double e = (yh[(size_t)i * stride * n + k] - lo) / (1.0 + fabs(lo));
+        err[(size_t)i * n + k] = e;
+        if (!(fabs(e) <= m)) m = fabs(e);
+    }
+    nm[i] = m;
+}
+// GE_subinterval!: interval i keeps node i's error vector if its norm is >= node i + 1's, else node i + 1's
+__global__ void k_ge_pick(int n, int N, const double* __restrict__ err, const double* __restrict__ nm,
+                          double* __restrict__ errors, double* __restrict__ est, unsigned long long* __restrict__ norm_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N - 1) return;
+    const int pick = nm[i] >= nm[i + 1] ? i : i + 1;
+    for (int k = 0; k < n; k++) errors[(size_t)i * n + k] = err[(size_t)pick * n + k];
+    est[i] = nm[pick];
+    atomicMax(norm_bits, (unsigned long long)__double_as_longlong(nm[pick]));
+}
+
 // ---- half_mesh! (MIRK/src/adaptivity.jl:287-304) -------------------------------------------------
 __global__ void k_half_mesh(int N, const double* __restrict__ mesh, double* __restrict__ mesh_new) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,9 +167,13 @@ __global__ void k_half_mesh(int N, const double* __restrict__ mesh, double* __re
 // sweep restarts its integral at every emitted node, so the order is part of the result).
 // est[i] = |errors_i|_inf.  out[0] = new node count, out[1] = 0 success / 1 failure.
 // With use_smem the mesh and s_hat live in shared memory (2 N doubles), else s_hat overwrites est.
+// The four controllers' selectors differ only in the exponent 1 / expo_den (order + 1; order for GlobalErrorControl),
+// the halving threshold rho (1 for DefectControl, 2 otherwise) and, for HybridErrorControl, s_hat being the sum of the
+// powers of two estimates (est2 != nullptr).
 __global__ void __launch_bounds__(1024)
-k_mesh_select(int order, int N, const double* __restrict__ mesh, double* __restrict__ est, double abstol,
-              int max_sub, int cap, double* __restrict__ mesh_new, int* __restrict__ out, int use_smem) {
+k_mesh_select(int expo_den, double rho, int N, const double* __restrict__ mesh, double* __restrict__ est,
+              const double* __restrict__ est2, double abstol, int max_sub, int cap, double* __restrict__ mesh_new,
+              int* __restrict__ out, int use_smem) {
     extern __shared__ double sm_sel[];
     __shared__ int s_mode, s_ns;
     const int ni = N - 1, tid = threadIdx.x, T = blockDim.x;
@@ -146,8 +184,12 @@ k_mesh_select(int order, int N, const double* __restrict__ mesh, double* __restr
         for (int i = tid; i < N; i += T) m2[i] = mesh[i];
         ms = m2;
     }
-    const double ex = 1.0 / (double)(order + 1);
-    for (int i = tid; i < ni; i += T) sh[i] = pow(est[i] / abstol, ex);
+    const double ex = 1.0 / (double)expo_den;
+    for (int i = tid; i < ni; i += T) {
+        double v = pow(est[i] / abstol, ex);
+        if (est2) v = v + pow(est2[i] / abstol, ex);
+        sh[i] = v;
+    }
     __syncthreads();
     if (tid == 0) {
         double r1 = 0.0, r2 = 0.0;
@@ -160,7 +202,7 @@ k_mesh_select(int order, int N, const double* __restrict__ mesh, double* __restr
         const double n_ = 0.1 * ni;
         if (fabs((double)(n_predict - ni)) < n_) n_predict = (long long)nearbyint(ni + n_);
         int mode, ns;
-        if (r1 <= 1.0 * r3) {  // rho = 1.0
+        if (r1 <= rho * r3) {
             ns = 2 * ni;
             mode = 1;
         } else {

@@ -186,6 +186,11 @@ struct mirk_solver_s {
            *nl_Jg = nullptr, *nl_sc = nullptr;
     size_t nl_cap = 0;
     double* h_sc = nullptr;  // pinned: scalar results of the reductions
+    // global-error controllers: companion handle (order + 2 on the same mesh / same order on the halved mesh), the
+    // second estimate of HybridErrorControl, scratch
+    mirk_solver_s* hi = nullptr;
+    double *est2 = nullptr, *ge_tmp = nullptr, *ge_nm = nullptr;
+    size_t ge_cap = 0;
     int *bc_nodes = nullptr, *m_dev = nullptr, *iold = nullptr, *sel_out = nullptr;
     size_t scratch_cap = 0, Mfinal_cap = 0, tbuf_cap = 0;
     // host-visible words: [0] residual norm bits, [1] defect bits, [2] status
@@ -1194,7 +1199,11 @@ static int refine_mesh(mirk_solver_s* S, int* info_out, int* Nnew_out) {
     const int smem_needed = (int)(sizeof(double) * 2 * (size_t)N);
     const int use_smem = smem_needed <= kSmemLimit;
     // the mesh selector wants the convergence order p (alg_order): 6 for the MIRK6I code
-    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0, S->st>>>(S->desc.order == kMIRK6I ? 6 : S->desc.order, N, S->mesh, S->est, S->desc.abstol,
+    // the controllers' selectors (MIRK/adaptivity.jl:23-243): exponent 1 / (p + 1), GlobalErrorControl 1 / p; halving
+    // threshold rho = 1 for DefectControl, 2 for the others; Hybrid sums the powers of the defect and global estimates
+    const int pconv = S->desc.order == kMIRK6I ? 6 : S->desc.order, ctrl = S->desc.controller;
+    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0, S->st>>>(ctrl == 1 ? pconv : pconv + 1, ctrl == 0 ? 1.0 : 2.0, N, S->mesh, S->est,
+                                                                  ctrl == 3 ? S->est2 : nullptr, S->desc.abstol,
                                                                   S->desc.max_num_subintervals, S->Ncap, S->mesh_new,
                                                                   S->sel_out, use_smem);
     S->launches++;
@@ -1239,6 +1248,63 @@ static int halve_and_zero(mirk_solver_s* S) {
     S->jac_valid = S->resid_valid = false;
     S->plan.valid = false; S->graph_epoch++;
     return sync_host_mesh(S);
+}
+
+// ---- global-error estimate (MIRK/adaptivity.jl:464-567; oracle: orc_global_error) ------------------------------------
+// errors (N-1) x n and est (N-1) on the device, the norm in *norm_out; returns MIRK_RET_FAILURE through *info when the
+// method of order + 2 does not exist
+extern "C" int mirk_create(const mirk_desc* desc, mirk_handle* out);
+extern "C" int mirk_destroy(mirk_handle h);
+extern "C" int mirk_set_mesh_guess_device(mirk_handle S, int32_t n_mesh, const double* mesh, const double* d_y);
+static int global_error(mirk_solver_s* S, double* errors, double* est, double* norm_out, int* info) {
+    const int n = S->n, N = S->N, method = S->desc.ge_method;
+    const int pconv = S->desc.order == kMIRK6I ? 6 : S->desc.order;
+    int order_hi = S->desc.order;
+    if (method == 0) {
+        if (S->desc.order == kMIRK6I || pconv + 2 > 6) { *info = MIRK_RET_FAILURE; *norm_out = 2.0 * S->desc.abstol; return MIRK_OK; }
+        order_hi = pconv + 2;
+    }
+    if (S->hi && S->hi->desc.order != order_hi) { mirk_destroy(S->hi); S->hi = nullptr; }
+    if (!S->hi) {
+        mirk_desc d = S->desc;
+        d.order = order_hi; d.adaptive = 0; d.controller = 0; d.n_params = (int)S->h_p.size(); d.params = S->h_p.data();
+        CKS(mirk_create(&d, &S->hi));
+    }
+    const int Nh = method == 0 ? N : 2 * (N - 1) + 1;
+    if ((size_t)Nh * n > S->ge_cap) {
+        dfree(S->ge_tmp); dfree(S->ge_nm);
+        CK(dalloc(&S->ge_tmp, (size_t)Nh * n));
+        CK(dalloc(&S->ge_nm, (size_t)Nh));
+        S->ge_cap = (size_t)Nh * n;
+    }
+    std::vector<double> hm(Nh);
+    const double* guess = S->y;
+    if (method == 0) {
+        hm = S->h_mesh;
+    } else {
+        for (int i = 0; i < N; i++) hm[2 * i] = S->h_mesh[i];
+        for (int i = 0; i < N - 1; i++) hm[2 * i + 1] = (hm[2 * i + 2] + hm[2 * i]) / 2.0;
+        k_halve_sol<<<(unsigned)(((size_t)Nh * n + 255) / 256), 256, 0, S->st>>>(n, N, S->y, S->ge_tmp);
+        S->launches++;
+        guess = S->ge_tmp;
+    }
+    CK(cudaStreamSynchronize(S->st));  // the companion handle reads the guess on its own stream
+    CKS(mirk_set_mesh_guess_device(S->hi, Nh, hm.data(), guess));
+    int it = 0, ret = 0;
+    double nrm = 0;
+    CKS(newton_solve(S->hi, &it, &nrm, &ret));  // (its outcome is not looked at, as in the reference)
+    CK(cudaStreamSynchronize(S->hi->st));
+    CK(cudaSetDevice(S->desc.device));
+    CK(cudaMemsetAsync(S->words + 1, 0, sizeof(unsigned long long), S->st));
+    k_ge_node<<<(N + 127) / 128, 128, 0, S->st>>>(n, N, method == 0 ? 1 : 2, S->hi->y, S->y, S->ge_tmp, S->ge_nm);
+    k_ge_pick<<<(N + 127) / 128, 128, 0, S->st>>>(n, N, S->ge_tmp, S->ge_nm, errors, est, S->words + 1);
+    S->launches += 2;
+    CKS(launch_check("global_error"));
+    CKS(read_words(S));
+    double norm = bits_to_double(S->h_words[1]);
+    if (method == 1) norm = norm * pow(2.0, pconv) / (pow(2.0, pconv) - 1.0);
+    *norm_out = norm;
+    return MIRK_OK;
 }
 
 // ---- C ABI ---------------------------------------------------------------------------------------
@@ -1394,6 +1460,8 @@ int mirk_destroy(mirk_handle S) {
     cudaSetDevice(S->desc.device);
     if (S->st) cudaStreamSynchronize(S->st);
     free_buffers(S);
+    if (S->hi) mirk_destroy(S->hi);
+    dfree(S->est2); dfree(S->ge_tmp); dfree(S->ge_nm);
     dfree(S->jscratch);
     dfree(S->nl_y0); dfree(S->nl_yb); dfree(S->nl_up); dfree(S->nl_du); dfree(S->nl_g); dfree(S->nl_fu); dfree(S->nl_Jg);
     dfree(S->nl_sc);
@@ -1441,6 +1509,7 @@ int mirk_create(const mirk_desc* desc, mirk_handle* out) {
     S->desc = *desc;
     S->desc.params = nullptr;
     if (S->desc.maxiters < 0) S->desc.maxiters = 0;
+    if (S->desc.controller < 0 || S->desc.controller > 3 || S->desc.ge_method < 0 || S->desc.ge_method > 1) { delete S; return fail(MIRK_ERR_ARG, "controller must be 0..3 and ge_method 0 or 1"); }
     if (S->desc.nlsolve < 0 || S->desc.nlsolve > 3) { delete S; return fail(MIRK_ERR_ARG, "nlsolve must be 0 (default polyalgorithm), 1, 2 or 3"); }
     S->ops = ops;
     S->n = ops->n; S->L = ops->n_bc; S->s = ops->s; S->si = ops->s_star - ops->s;
@@ -1710,9 +1779,36 @@ int mirk_solve(mirk_handle S, mirk_result* out) {
             break;
         }
         if (info == MIRK_RET_SUCCESS) {
-            CKS(eval_defect(S, &error_norm));
+            // error_estimate!(cache, controller, ...) (MIRK/adaptivity.jl:355-369 dispatch; oracle: orc_solve)
+            const int ctrl = S->desc.controller;
+            if (ctrl == 0) {          // DefectControl
+                CKS(eval_defect(S, &error_norm));
+                if (!(error_norm <= S->desc.defect_threshold)) info = MIRK_RET_FAILURE;
+            } else if (ctrl == 1) {   // GlobalErrorControl: no threshold test
+                if (S->ops->problem_type == 0) {  // Standard problems keep their interpolation stages current (quirk Q7)
+                    S->ops->interp_setup(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki);
+                    S->launches++;
+                    S->ki_dirty = true;
+                }
+                CKS(global_error(S, S->errors, S->est, &error_norm, &info));
+            } else if (ctrl == 2) {   // SequentialErrorControl: defect first, global error once it passes
+                CKS(eval_defect(S, &error_norm));
+                if (!(error_norm <= S->desc.defect_threshold)) info = MIRK_RET_FAILURE;
+                if (error_norm <= abstol) {
+                    int ginfo = MIRK_RET_SUCCESS;
+                    double ge = 0;
+                    CKS(global_error(S, S->errors, S->est, &ge, &ginfo));
+                    if (ginfo != MIRK_RET_SUCCESS) info = MIRK_RET_FAILURE; else { error_norm = ge; info = MIRK_RET_SUCCESS; }
+                }
+            } else {                  // HybridErrorControl: DE * defect + GE * global error, always Success
+                double dn = 0, ge = 0;
+                CKS(eval_defect(S, &dn));
+                if (!S->est2) CK(dalloc(&S->est2, (size_t)S->Ncap));
+                // the global estimate's per-interval vectors are not needed by the selector, only their norms (est2)
+                CKS(global_error(S, S->delta, S->est2, &ge, &info));
+                if (info == MIRK_RET_SUCCESS) error_norm = S->desc.DE * dn + S->desc.GE * ge;
+            }
             out->hist_defect[h] = error_norm;
-            if (!(error_norm <= S->desc.defect_threshold)) info = MIRK_RET_FAILURE;
             if (info == MIRK_RET_SUCCESS && error_norm > abstol) {
                 int Nn = 0;
                 CKS(refine_mesh(S, &info, &Nn));

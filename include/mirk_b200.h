@@ -62,6 +62,11 @@ typedef struct {
                                       NewtonRaphson -> NewtonRaphson + BackTracking -> TrustRegion, each restarting
                                       from the original iterate (CORE/default_internal_solve.jl:31-45); 1, 2, 3 = that
                                       single solver */
+    int32_t controller;            /* 0 DefectControl, 1 GlobalErrorControl, 2 SequentialErrorControl,
+                                      3 HybridErrorControl (CORE/calc_errors.jl:54-106, MIRK/adaptivity.jl:77-243,464-567) */
+    int32_t ge_method;             /* global-error estimate: 0 HOErrorControl (method of order + 2 on the same mesh),
+                                      1 REErrorControl (Richardson: same method on the halved mesh) */
+    double DE, GE;                 /* HybridErrorControl weights: error = DE * defect + GE * global error */
 } mirk_desc;
 
 typedef struct {

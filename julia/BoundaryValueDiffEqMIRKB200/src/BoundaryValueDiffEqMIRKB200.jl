@@ -102,6 +102,10 @@ struct MirkDesc
     n_params::Int32
     params::Ptr{Float64}
     nlsolve::Int32
+    controller::Int32
+    ge_method::Int32
+    DE::Float64
+    GE::Float64
 end
 
 struct MirkResult
@@ -179,17 +183,30 @@ function nlsolve_code(alg)
     throw(ArgumentError("nlsolve = $(typeof(alg)) cannot run on the B200 backend (supported: nothing, NewtonRaphson(), NewtonRaphson(linesearch = BackTracking()), TrustRegion())"))
 end
 
+# controller -> (code, global-error method, DE, GE, defect_threshold) of the C ABI (CORE/src/calc_errors.jl:54-139)
+ge_method_code(m) = occursin("REErrorControl", string(typeof(m))) ? Int32(1) : Int32(0)
+controller_fields(c::DefectControl) = (Int32(0), Int32(0), 1.0, 1.0, Float64(c.defect_threshold))
+function controller_fields(c)
+    name = string(nameof(typeof(c)))
+    name == "GlobalErrorControl" && return (Int32(1), ge_method_code(c.method), 1.0, 1.0, 0.1)
+    name == "SequentialErrorControl" &&
+        return (Int32(2), ge_method_code(c.global_error.method), 1.0, 1.0, Float64(c.defect.defect_threshold))
+    name == "HybridErrorControl" &&
+        return (Int32(3), ge_method_code(c.global_error.method), Float64(c.DE), Float64(c.GE), Float64(c.defect.defect_threshold))
+    throw(ArgumentError("unknown error controller $(typeof(c))"))
+end
+
 function __init_b200(prob::BVProblem, alg, order::Integer, device::Integer; dt = 0.0, abstol = 1e-6, adaptive = true,
         controller = DefectControl(), nlsolve_kwargs = (; abstol = abstol), optimize_kwargs = (;),
         verbose = DEFAULT_VERBOSE, kwargs...)
     f = device_function(prob)
     f === nothing && throw(ArgumentError("the B200 backend needs prob.f to wrap a BVPDeviceFunction"))
     alg.optimize === nothing || throw(ArgumentError("`optimize` solvers are not supported by the B200 backend"))
-    controller isa DefectControl || throw(ArgumentError("the B200 backend implements DefectControl and the global-error controllers through `controller_code`"))
+    ctrl, gem, DE, GE, thr = controller_fields(controller)
     p = prob.p isa SciMLBase.NullParameters ? Float64[] : collect(Float64, prob.p)
     desc = MirkDesc(problem_id(f), order, get(nlsolve_kwargs, :abstol, abstol), adaptive,
-        controller.defect_threshold, alg.max_num_subintervals, get(nlsolve_kwargs, :maxiters, 1000), 0, 0,
-        device, length(p), pointer(p), nlsolve_code(alg.nlsolve))
+        thr, alg.max_num_subintervals, get(nlsolve_kwargs, :maxiters, 1000), 0, 0,
+        device, length(p), pointer(p), nlsolve_code(alg.nlsolve), ctrl, gem, DE, GE)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve p check(ccall((:mirk_create, libmirkb200[]), Cint, (Ref{MirkDesc}, Ref{Ptr{Cvoid}}), desc, h))
     t0, t1 = prob.tspan

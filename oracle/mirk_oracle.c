@@ -31,6 +31,7 @@ void orc_default_options(orc_options *o) {
     o->max_num_subintervals = 3000; /* MIRK/algorithms.jl:55-61 */
     o->maxiters = 1000;
     o->reinterp_inplace = 0; /* see DESIGN.md "Q3": 1 reproduces the reference's in-place hazard */
+    o->controller = 0; o->ge_method = 0; o->DE = 1.0; o->GE = 1.0;
     o->nlsolve = 0; /* the reference default: NewtonRaphson -> NewtonRaphson + BackTracking -> TrustRegion */
     o->max_outer = 1000; /* safety net only: the reference loop has no cap (mirk.jl:296-322) */
 }
@@ -1036,13 +1037,29 @@ double orc_defect(const orc_problem *P, const orc_tableau *T, const double *p, i
 
 int orc_mesh_select(int order, int n, int N, const double *mesh, const double *errors, double abstol,
                     int max_num_subintervals, int *N_new, double *mesh_new) {
+    return orc_mesh_select_ex(order, n, N, mesh, errors, NULL, abstol, max_num_subintervals,
+                              orc_convergence_order(order) + 1, 1.0, N_new, mesh_new);
+}
+
+/* the four mesh selectors of MIRK/adaptivity.jl:23-243 differ in three things only: the exponent 1 / expo_den of
+ * s_hat (order + 1 for DefectControl / Sequential / Hybrid, order for GlobalErrorControl), the halving threshold rho
+ * (1 for DefectControl, 2 for the others) and, for HybridErrorControl, s_hat being the SUM of the powers of two error
+ * arrays (defect and global error, errors2 != NULL). */
+int orc_mesh_select_ex(int order, int n, int N, const double *mesh, const double *errors, const double *errors2,
+                       double abstol, int max_num_subintervals, int expo_den, double rho, int *N_new, double *mesh_new) {
+    (void)order;
     const int ni = N - 1;
     double *sh = (double *)malloc(sizeof(double) * ni);
     double r1 = 0.0, r2 = 0.0;
     for (int i = 0; i < ni; i++) {
         double e = 0.0;
         for (int k = 0; k < n; k++) if (fabs(errors[(size_t)i * n + k]) > e) e = fabs(errors[(size_t)i * n + k]);
-        sh[i] = pow(e / abstol, 1.0 / (orc_convergence_order(order) + 1));
+        sh[i] = pow(e / abstol, 1.0 / expo_den);
+        if (errors2) {
+            double e2 = 0.0;
+            for (int k = 0; k < n; k++) if (fabs(errors2[(size_t)i * n + k]) > e2) e2 = fabs(errors2[(size_t)i * n + k]);
+            sh[i] = sh[i] + pow(e2 / abstol, 1.0 / expo_den);
+        }
         if (sh[i] > r1) r1 = sh[i];
         r2 += sh[i];
     }
@@ -1051,7 +1068,7 @@ int orc_mesh_select(int order, int n, int N, const double *mesh, const double *e
     const double n_ = 0.1 * ni;
     if (fabs((double)(n_predict - ni)) < n_) n_predict = (long)nearbyint(ni + n_);
     int info = ORC_SUCCESS;
-    if (r1 <= 1.0 * r3) { /* rho = 1.0 */
+    if (r1 <= rho * r3) {
         const int ns = 2 * ni;
         if (ns > max_num_subintervals) {
             info = ORC_FAILURE;
@@ -1140,6 +1157,68 @@ void orc_reinterp(const orc_problem *P, const orc_tableau *T, int N_old, const d
 /* adaptive outer loop (MIRK/mirk.jl:286-388; Appendix A.8)                                     */
 /* ------------------------------------------------------------------------------------------ */
 
+/* ---- global-error estimates (MIRK/adaptivity.jl:464-567) -------------------------------------------------------
+ * HO  (HOErrorControl):  the same mesh solved again with the method of order + 2 (MIRK2 -> 4, 3 -> 5, 4 -> 6), current
+ *     solution as the guess, non-adaptive;  err = (y_high - y) / (1 + |y|) per node.
+ * RE  (REErrorControl):  the mesh halved (halve_sol: nodes copied, midpoints averaged), same method, non-adaptive;
+ *     err = (y_half[1:2:end] - y) / (1 + |y|), norm scaled by 2^p / (2^p - 1).
+ * GE_subinterval!: interval i keeps the error vector of node i if its max-norm is >= that of node i + 1, else that of
+ * node i + 1.  Returns the error norm, < 0 when the higher-order method does not exist. */
+double orc_global_error(const orc_problem *P, int order, const double *p, int N, const double *mesh, const double *y,
+                        const orc_options *opt, int method, double *errors) {
+    const int n = P->n, pconv = orc_convergence_order(order);
+    orc_tableau Th;
+    int Nh = N;
+    double *mh = NULL, *yh = NULL;
+    if (method == 0) {
+        if (order == ORC_MIRK6I || pconv + 2 > 6 || orc_tableau_get(pconv + 2, &Th)) return -1.0;
+        mh = (double *)malloc(sizeof(double) * N);
+        yh = (double *)malloc(sizeof(double) * (size_t)N * n);
+        memcpy(mh, mesh, sizeof(double) * N);
+        memcpy(yh, y, sizeof(double) * (size_t)N * n);
+    } else {
+        orc_tableau_get(order, &Th);
+        Nh = 2 * (N - 1) + 1;
+        mh = (double *)malloc(sizeof(double) * Nh);
+        yh = (double *)malloc(sizeof(double) * (size_t)Nh * n);
+        for (int i = 0; i < N; i++) {
+            mh[2 * i] = mesh[i];
+            memcpy(yh + (size_t)2 * i * n, y + (size_t)i * n, sizeof(double) * n);
+        }
+        for (int i = 0; i < N - 1; i++) {
+            mh[2 * i + 1] = (mh[2 * i + 2] + mh[2 * i]) / 2.0;
+            for (int k = 0; k < n; k++) yh[(size_t)(2 * i + 1) * n + k] = (yh[(size_t)(2 * i + 2) * n + k] + yh[(size_t)2 * i * n + k]) / 2.0;
+        }
+    }
+    const int sh = Th.s, sih = Th.s_star - Th.s;
+    double *Kh = (double *)calloc((size_t)(Nh - 1) * sh * n, sizeof(double));
+    double *Kih = (double *)calloc((size_t)(Nh - 1) * (sih > 0 ? sih : 1) * n, sizeof(double));
+    double rn = 0.0;
+    int its = 0;
+    orc_nlsolve(P, &Th, p, Nh, mh, yh, Kh, Kih, opt->abstol, opt->maxiters, opt->nlsolve, &rn, &its);
+    const int stride = method == 0 ? 1 : 2;
+    double *err = (double *)malloc(sizeof(double) * (size_t)N * n), *nm = (double *)malloc(sizeof(double) * N);
+    for (int i = 0; i < N; i++) {
+        double m = 0.0;
+        for (int k = 0; k < n; k++) {
+            const double lo = y[(size_t)i * n + k];
+            const double e = (yh[(size_t)i * stride * n + k] - lo) / (1.0 + fabs(lo));
+            err[(size_t)i * n + k] = e;
+            if (!(fabs(e) <= m)) m = fabs(e);
+        }
+        nm[i] = m;
+    }
+    double norm = 0.0;
+    for (int i = 0; i < N - 1; i++) {
+        const int pick = nm[i] >= nm[i + 1] ? i : i + 1;
+        memcpy(errors + (size_t)i * n, err + (size_t)pick * n, sizeof(double) * n);
+        if (!(nm[pick] <= norm)) norm = nm[pick];
+    }
+    free(mh); free(yh); free(Kh); free(Kih); free(err); free(nm);
+    if (method == 1) norm = norm * pow(2.0, pconv) / (pow(2.0, pconv) - 1.0);
+    return norm;
+}
+
 int orc_solve(const orc_problem *P, int order, const double *p, int N0, const double *mesh0,
               const double *y0, const orc_options *opt, orc_result *out) {
     orc_tableau T;
@@ -1170,15 +1249,43 @@ int orc_solve(const orc_problem *P, int order, const double *p, int N0, const do
         if (out->n_hist < 64) out->n_hist++;
         if (!opt->adaptive) break;
         if (info == ORC_SUCCESS) {
-            double *errors = (double *)malloc(sizeof(double) * (size_t)(N - 1) * n);
-            error_norm = orc_defect(P, &T, p, N, mesh, y, Kd, Ki, errors);
+            /* error_estimate!(cache, controller, ...) — MIRK/adaptivity.jl:355-369 (dispatch), :370-461 (defect), :464-567 */
+            double *errors = (double *)malloc(sizeof(double) * 2 * (size_t)(N - 1) * n);
+            double *errors2 = NULL;
+            const int pconv = orc_convergence_order(order);
+            int expo_den = pconv + 1;
+            double rho = 1.0;
+            if (opt->controller == 0) {          /* DefectControl */
+                error_norm = orc_defect(P, &T, p, N, mesh, y, Kd, Ki, errors);
+                if (!(error_norm <= opt->defect_threshold)) info = ORC_FAILURE;
+            } else if (opt->controller == 1) {   /* GlobalErrorControl: no threshold test */
+                if (P->problem_type == 0) orc_interp_setup(P, &T, p, N, mesh, y, Kd, Ki); /* filled by every loss call (Q7) */
+                error_norm = orc_global_error(P, order, p, N, mesh, y, opt, opt->ge_method, errors);
+                expo_den = pconv;
+                rho = 2.0;
+                if (error_norm < 0.0) { info = ORC_FAILURE; error_norm = 2.0 * opt->abstol; }
+            } else if (opt->controller == 2) {   /* SequentialErrorControl: defect first, global error once it passes */
+                error_norm = orc_defect(P, &T, p, N, mesh, y, Kd, Ki, errors);
+                if (!(error_norm <= opt->defect_threshold)) info = ORC_FAILURE;
+                if (error_norm <= opt->abstol) {
+                    const double ge = orc_global_error(P, order, p, N, mesh, y, opt, opt->ge_method, errors);
+                    if (ge < 0.0) info = ORC_FAILURE; else { error_norm = ge; info = ORC_SUCCESS; }
+                }
+                rho = 2.0;
+            } else {                             /* HybridErrorControl: DE * defect + GE * global error, always Success */
+                errors2 = errors + (size_t)(N - 1) * n;
+                const double dn = orc_defect(P, &T, p, N, mesh, y, Kd, Ki, errors);
+                const double ge = orc_global_error(P, order, p, N, mesh, y, opt, opt->ge_method, errors2);
+                if (ge < 0.0) { info = ORC_FAILURE; error_norm = 2.0 * opt->abstol; }
+                else error_norm = opt->DE * dn + opt->GE * ge;
+                rho = 2.0;
+            }
             out->hist_defect[h] = error_norm;
-            if (!(error_norm <= opt->defect_threshold)) info = ORC_FAILURE;
             if (info == ORC_SUCCESS && error_norm > opt->abstol) {
                 int Nn = 0;
                 double *mesh_new = (double *)malloc(sizeof(double) * (4 * (size_t)(N - 1) + 1));
-                info = orc_mesh_select(order, n, N, mesh, errors, opt->abstol,
-                                       opt->max_num_subintervals, &Nn, mesh_new);
+                info = orc_mesh_select_ex(order, n, N, mesh, errors, errors2, opt->abstol,
+                                          opt->max_num_subintervals, expo_den, rho, &Nn, mesh_new);
                 if (info == ORC_SUCCESS) {
                     double *y_new = (double *)malloc(sizeof(double) * (size_t)Nn * n);
                     orc_reinterp(P, &T, N, mesh, y, Kd, Ki, Nn, mesh_new, y_new, opt->reinterp_inplace);

@@ -75,6 +75,10 @@ typedef struct {
     int max_outer;             /* safety cap on adaptive outer iterations       */
     int nlsolve;               /* 0 default polyalgorithm (CORE/default_internal_solve.jl:31-45); 1 NewtonRaphson,
                                   2 NewtonRaphson + BackTracking, 3 TrustRegion */
+    int controller;            /* 0 DefectControl, 1 GlobalErrorControl, 2 SequentialErrorControl, 3 HybridErrorControl
+                                  (CORE/src/calc_errors.jl:54-106) */
+    int ge_method;             /* 0 HOErrorControl (order + 2), 1 REErrorControl (Richardson on the halved mesh) */
+    double DE, GE;             /* HybridErrorControl weights */
 } orc_options;
 
 typedef struct {
@@ -127,6 +131,10 @@ double orc_defect(const orc_problem *P, const orc_tableau *T, const double *p, i
                   const double *mesh, const double *y, const double *Kd, double *Ki, double *errors);
 int orc_mesh_select(int order, int n, int N, const double *mesh, const double *errors, double abstol,
                     int max_num_subintervals, int *N_new, double *mesh_new /* cap 4N */);
+int orc_mesh_select_ex(int order, int n, int N, const double *mesh, const double *errors, const double *errors2,
+                       double abstol, int max_num_subintervals, int expo_den, double rho, int *N_new, double *mesh_new);
+double orc_global_error(const orc_problem *P, int order, const double *p, int N, const double *mesh, const double *y,
+                        const orc_options *opt, int method, double *errors);
 void orc_reinterp(const orc_problem *P, const orc_tableau *T, int N_old, const double *mesh_old,
                   const double *y_old, const double *Kd, const double *Ki, int N_new,
                   const double *mesh_new, double *y_new, int inplace_quirk);

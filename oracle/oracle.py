@@ -44,7 +44,8 @@ class Tableau(C.Structure):
 class Options(C.Structure):
     _fields_ = [("abstol", C.c_double), ("adaptive", C.c_int), ("defect_threshold", C.c_double),
                 ("max_num_subintervals", C.c_int), ("maxiters", C.c_int),
-                ("reinterp_inplace", C.c_int), ("max_outer", C.c_int), ("nlsolve", C.c_int)]
+                ("reinterp_inplace", C.c_int), ("max_outer", C.c_int), ("nlsolve", C.c_int),
+                ("controller", C.c_int), ("ge_method", C.c_int), ("DE", C.c_double), ("GE", C.c_double)]
 
 
 class Result(C.Structure):

@@ -16,6 +16,7 @@ int main(void) {
     OFF(mirk_desc, defect_threshold); OFF(mirk_desc, max_num_subintervals); OFF(mirk_desc, maxiters);
     OFF(mirk_desc, reinterp_inplace); OFF(mirk_desc, chunk); OFF(mirk_desc, device); OFF(mirk_desc, n_params);
     OFF(mirk_desc, params); OFF(mirk_desc, nlsolve);
+    OFF(mirk_desc, controller); OFF(mirk_desc, ge_method); OFF(mirk_desc, DE); OFF(mirk_desc, GE);
     SZ(mirk_problem_info);
     OFF(mirk_problem_info, n); OFF(mirk_problem_info, n_params); OFF(mirk_problem_info, problem_type);
     OFF(mirk_problem_info, n_bc); OFF(mirk_problem_info, n_bca); OFF(mirk_problem_info, max_bc_pts);

@@ -535,3 +535,35 @@ def test_adaptive_singular_problem_fails_like_the_reference_would(M, oracle):
     sol = M.solve(M.BVProblem("lane_emden", [1.0, 0.0], (0.0, 1.0), p=[]), M.MIRK4(max_num_subintervals=200), dt=0.05)
     assert sol.retcode == ref.retcode == M.ReturnCode.Failure
     assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+
+
+@pytest.mark.parametrize("ge", ["HO", "RE"])
+@pytest.mark.parametrize("ctrl", ["global", "sequential", "hybrid"])
+@pytest.mark.parametrize("name,order,p,u0,tspan,dt", [
+    ("pendulum", 4, [9.81], PENDULUM_U0, PENDULUM_T, 0.05),         # mirk_basic_tests.jl:413-436 (abstol = 1e-5)
+    ("linear2_tp", 4, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.2),
+    ("pendulum", 3, [9.81], PENDULUM_U0, PENDULUM_T, 0.05),         # HO: MIRK3 -> MIRK5
+])
+def test_global_error_controllers_match_oracle(M, oracle, name, order, p, u0, tspan, dt, ctrl, ge):
+    """GlobalErrorControl / SequentialErrorControl / HybridErrorControl with both global-error estimates (method of
+    order + 2 on the same mesh; Richardson on the halved mesh): error-norm history, mesh history, Newton counts and the
+    solution against the oracle (MIRK/src/adaptivity.jl:77-243, 464-567)."""
+    O = oracle
+    method = M.HOErrorControl() if ge == "HO" else M.REErrorControl()
+    controller = {"global": M.GlobalErrorControl(method=method),
+                  "sequential": M.SequentialErrorControl(global_error=M.GlobalErrorControl(method=method)),
+                  "hybrid": M.HybridErrorControl(DE=1.0, GE=0.5, global_error=M.GlobalErrorControl(method=method))}[ctrl]
+    code = {"global": 1, "sequential": 2, "hybrid": 3}[ctrl]
+    ref = O.solve_dt(O.builtin(name), order, p, u0, tspan, dt, abstol=1e-5, controller=code, ge_method=0 if ge == "HO" else 1,
+                     DE=1.0, GE=0.5)
+    sol = M.solve(M.BVProblem(name, u0, tspan, p=p), _alg(M, order), dt=dt, abstol=1e-5, controller=controller)
+    assert sol.retcode == ref.retcode == 0
+    assert sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+    assert np.allclose(sol.original["hist_defect"], ref.hist_defect, rtol=1e-6, atol=1e-14)
+    assert _rel(sol.u, ref.u) < 1e-10
+
+
+def test_high_order_estimate_needs_an_existing_method(M):
+    """HOErrorControl on MIRK6 would need MIRK8, which does not exist (the reference raises; here: ReturnCode.Failure)"""
+    sol = M.solve(M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[9.81]), M.MIRK6(), dt=0.05, controller=M.GlobalErrorControl())
+    assert sol.retcode == M.ReturnCode.Failure
