@@ -76,6 +76,7 @@ SYMBOLS = {
     "mirk_residual": (C.c_int, [Handle, dp, dp]),
     "mirk_jacobian_blocks": (C.c_int, [Handle, dp, dp, ip, dp, ip]),
     "mirk_linear_solve": (C.c_int, [Handle, dp]),
+    "mirk_abd_solve": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, C.c_int32, ip, dp, dp, dp, C.c_int32]),
     "mirk_newton_step": (C.c_int, [Handle, dp]),
     "mirk_newton_solve": (C.c_int, [Handle, ip, dp]),
     "mirk_nlsolve_stats": (C.c_int, [Handle, ip, ip]),

@@ -29,7 +29,7 @@ import numpy as np
 from . import _lib as B
 
 __all__ = ["GlobalErrorControl", "SequentialErrorControl", "HybridErrorControl", "HOErrorControl", "REErrorControl", "NewtonRaphson", "BackTracking", "TrustRegion", "BVPDeviceFunction", "BVProblem", "TwoPointBVProblem", "MIRK2", "MIRK3", "MIRK4", "MIRK5", "MIRK6", "MIRK6I", "DefectControl",
-           "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b",
+           "BVPJacobianAlgorithm", "ReturnCode", "BVSolution", "MIRKCache", "init", "solve", "solve_b", "abd_solve",
            "EnsembleProblem", "EnsembleSolution", "EnsembleB200", "compile_device_function",
            "successful_retcode"]
 
@@ -476,6 +476,18 @@ class MIRKCache:
         launches = C.c_int64(0)
         st = B.check(B.lib().mirk_bench_newton_steps(self._h, int(steps), C.byref(tot), ph, C.byref(launches)))
         return st, tot.value, list(ph), launches.value
+
+
+def abd_solve(Lb, Rb, bc_nodes, Bc, rhs, two_point=False, La=0, device=0):
+    """The almost-block-diagonal solver on its own (what FIRK's expanded form and MIRKN share with MIRK): delta with
+    [boundary rows; blockbidiag(Lb_i, Rb_i)] delta = rhs.  Lb, Rb: (N-1, n, n); Bc: (m, n, n) on nodes bc_nodes."""
+    Lb, Rb, Bc, rhs = _arr(Lb), _arr(Rb), _arr(Bc), _arr(rhs)
+    nm1, n, _ = Lb.shape
+    nodes = np.ascontiguousarray(bc_nodes, dtype=np.int32)
+    delta = np.zeros((nm1 + 1, n))
+    st = B.check(B.lib().mirk_abd_solve(n, nm1 + 1, int(bool(two_point)), int(La), _d(Lb), _d(Rb), len(nodes), _i(nodes), _d(Bc),
+                                        _d(rhs), _d(delta), int(device)))
+    return st, delta
 
 
 def mesh_uniform(t0, t1, nint) -> np.ndarray:

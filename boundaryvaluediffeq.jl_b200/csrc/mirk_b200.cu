@@ -1715,6 +1715,70 @@ int mirk_newton_solve(mirk_handle S, int32_t* iters, double* resid_norm) {
     return ret;
 }
 
+// The almost-block-diagonal solver on its own: J delta = rhs for
+//     J = [ boundary rows (L x nN, blocks Bc[k] on nodes bc_nodes[k]) ; blockbidiag(Lb_i, Rb_i), i = 0..N-2 ]
+// with ANY block size n (fast paths for n = 2, 4, 6, 8, 16, 32, 64, 128, the generic kernels otherwise) — what the
+// sibling solvers of the reference share with MIRK: the FIRK expanded form has this skeleton with blocks of
+// n (s + 1) (lib/BoundaryValueDiffEqFIRK/src/sparse_jacobians.jl:35-70), MIRKN with 2n
+// (lib/BoundaryValueDiffEqMIRKN/src/collocation.jl:8-41).  rhs is in the residual order of the problem type
+// (two_point = 0: [bc(L); Phi], 1: [bc_a(La); Phi; bc_b]).  Square systems only (L = n); host arrays in and out.
+int mirk_abd_solve(int32_t n, int32_t N, int32_t two_point, int32_t La, const double* Lb, const double* Rb, int32_t m,
+                   const int32_t* bc_nodes, const double* Bc, const double* rhs, double* delta, int32_t device) {
+    if (!Lb || !Rb || !bc_nodes || !Bc || !rhs || !delta) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (n < 1 || N < 2 || m < 1 || m > 16) return fail(MIRK_ERR_ARG, "need n >= 1, N >= 2, 1 <= m <= 16 boundary blocks");
+    const int L = n;
+    if (two_point && (La < 0 || La > L)) return fail(MIRK_ERR_ARG, "0 <= La <= n");
+    for (int k = 0; k < m; k++)
+        if (bc_nodes[k] < 0 || bc_nodes[k] >= N) return fail(MIRK_ERR_ARG, "boundary node out of range");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MIRK_ERR_NO_DEVICE, "no CUDA device: libmirkb200 has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(MIRK_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(device));
+    // a bare solver state: no problem functor, just the buffers the elimination touches
+    mirk_solver_s* S = new mirk_solver_s();
+    S->n = n; S->L = L; S->La = two_point ? La : L; S->N = N; S->use_graph = false;
+    memset(&S->desc, 0, sizeof(S->desc));
+    S->desc.device = device;
+    int rc = MIRK_OK;
+    auto body = [&]() -> int {
+        const size_t nn = (size_t)n * n, nb = (size_t)(N - 1) * nn, nr = (size_t)L + (size_t)(N - 1) * n;
+        CK(cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+        CK(dalloc(&S->Lb, nb)); CK(dalloc(&S->Rb, nb)); CK(dalloc(&S->resid, nr + n));
+        CK(dalloc(&S->TL, (size_t)N * nn)); CK(dalloc(&S->TR, (size_t)N * nn)); CK(dalloc(&S->rt, (size_t)N * n));
+        CK(dalloc(&S->delta, (size_t)N * n));
+        CK(dalloc(&S->Bc, (size_t)m * L * n)); CK(dalloc(&S->bc_nodes, 16)); CK(dalloc(&S->m_dev, 1));
+        CK(dalloc(&S->words, 4));
+        CK(cudaMemset(S->words, 0, 4 * sizeof(unsigned long long)));
+        CK(cudaMallocHost((void**)&S->h_words, 4 * sizeof(unsigned long long)));
+        S->Ncap = N;
+        CK(cudaMemcpyAsync(S->Lb, Lb, nb * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->Rb, Rb, nb * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->resid, rhs, nr * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->Bc, Bc, (size_t)m * L * n * sizeof(double), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->bc_nodes, bc_nodes, m * sizeof(int), cudaMemcpyHostToDevice, S->st));
+        CK(cudaMemcpyAsync(S->m_dev, &m, sizeof(int), cudaMemcpyHostToDevice, S->st));
+        cudaFuncSetAttribute(k_reduce_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaFuncSetAttribute(k_final_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (warp_reduce_supported(n)) set_warp_tail_smem(n, kTailDynLimit);
+        CKS(build_plan_for(S, S->plan, N, std::vector<int>(bc_nodes, bc_nodes + m), S->Lb, S->Rb, S->resid + S->La));
+        SolveCtx C = main_ctx(S);
+        CKS(abd_reduce(S, C));
+        CKS(abd_final(S, C));
+        CKS(abd_backsub(S, C));
+        CKS(read_words(S));
+        CK(cudaMemcpyAsync(delta, S->delta, (size_t)N * n * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+        return S->h_words[2] ? MIRK_RET_FAILURE : MIRK_RET_SUCCESS;
+    };
+    rc = body();
+    mirk_destroy(S);
+    return rc;
+}
+
 int mirk_nlsolve_stats(mirk_handle S, int32_t* steps3, int32_t* retcodes3) {
     if (!S) return fail(MIRK_ERR_ARG, "NULL handle");
     for (int k = 0; k < 3; k++) {

@@ -124,6 +124,14 @@ int mirk_jacobian_blocks(mirk_handle h, double* Lb, double* Rb, int32_t* bc_node
 /* J \ F for the current iterate (stands in for LinearSolve inside NonlinearSolve); delta is N×n, may be NULL.
  * Requires mirk_residual + mirk_jacobian_blocks state; leaves y untouched. */
 int mirk_linear_solve(mirk_handle h, double* delta);
+/* The almost-block-diagonal solver on its own (what FIRK's expanded form — blocks of n (s + 1),
+ * lib/BoundaryValueDiffEqFIRK/src/sparse_jacobians.jl:35-70 — and MIRKN — lib/BoundaryValueDiffEqMIRKN/src/
+ * collocation.jl:8-41 — share with MIRK): solves J delta = rhs for J = [boundary rows; blockbidiag(Lb_i, Rb_i)] with any
+ * block size n.  Lb, Rb: (N-1) row-major n x n blocks; Bc[m][n][n]: boundary rows' blocks on nodes bc_nodes[m] (0-based);
+ * rhs in residual order (two_point = 0: [bc; Phi], 1: [bc_a(La); Phi; bc_b]); delta[N][n].  Square systems (n boundary
+ * rows) only; host arrays; returns MIRK_RET_SUCCESS / MIRK_RET_FAILURE (singular block). */
+int mirk_abd_solve(int32_t n, int32_t N, int32_t two_point, int32_t La, const double* Lb, const double* Rb, int32_t m,
+                   const int32_t* bc_nodes, const double* Bc, const double* rhs, double* delta, int32_t device);
 /* one NewtonRaphson iteration: J d = F, y -= d, F(y) ; returns the new |F|_inf */
 int mirk_newton_step(mirk_handle h, double* resid_norm);
 /* __internal_solve(nlprob, alg; abstol, maxiters) with alg per desc.nlsolve (CORE/default_internal_solve.jl:31-45,

@@ -567,3 +567,35 @@ def test_high_order_estimate_needs_an_existing_method(M):
     """HOErrorControl on MIRK6 would need MIRK8, which does not exist (the reference raises; here: ReturnCode.Failure)"""
     sol = M.solve(M.BVProblem("pendulum", PENDULUM_U0, PENDULUM_T, p=[9.81]), M.MIRK6(), dt=0.05, controller=M.GlobalErrorControl())
     assert sol.retcode == M.ReturnCode.Failure
+
+
+@pytest.mark.parametrize("n,N,two_point", [(3, 40, False), (5, 17, True), (12, 60, False), (8, 300, True), (24, 33, True), (16, 500, False)])
+def test_standalone_abd_solver_for_sibling_block_sizes(M, n, N, two_point):
+    """mirk_abd_solve: the block cyclic reduction as a service for block sizes MIRK itself never produces — FIRK's
+    expanded form couples n (s + 1) unknowns per node (e.g. n = 4, s = 2 -> 12; n = 8, s = 2 -> 24), MIRKN 2n —
+    against a dense solve, with interior boundary nodes for the Standard form."""
+    rng = np.random.default_rng(n * 1000 + N)
+    Lb = -np.eye(n)[None] + 0.3 * rng.standard_normal((N - 1, n, n)) / np.sqrt(n)
+    Rb = np.eye(n)[None] + 0.3 * rng.standard_normal((N - 1, n, n)) / np.sqrt(n)
+    La = n // 2 if two_point else n
+    nodes = [0, N - 1] if two_point else [0, N // 3, N - 1]
+    Bc = rng.standard_normal((len(nodes), n, n))
+    if two_point:
+        Bc[0, La:] = 0.0     # rows [0, La) see the first node only, the rest the last node only
+        Bc[1, :La] = 0.0
+    rhs = rng.standard_normal(n + (N - 1) * n)
+    J = np.zeros((n * N, n * N))
+    off = La
+    for i in range(N - 1):
+        J[off + i * n: off + (i + 1) * n, i * n:(i + 1) * n] = Lb[i]
+        J[off + i * n: off + (i + 1) * n, (i + 1) * n:(i + 2) * n] = Rb[i]
+    for k, nd in enumerate(nodes):
+        J[:La, nd * n:(nd + 1) * n] += Bc[k][:La]
+        if La < n:
+            J[La + (N - 1) * n:, nd * n:(nd + 1) * n] += Bc[k][La:]
+    st, delta = M.abd_solve(Lb, Rb, nodes, Bc, rhs, two_point=two_point, La=La)
+    assert st == 0
+    ref = np.linalg.solve(J, rhs).reshape(N, n)
+    assert np.max(np.abs(delta - ref)) < 1e-9 * max(1.0, np.max(np.abs(ref)))
+    back = np.abs(J @ delta.ravel() - rhs) / np.maximum(1.0, np.abs(J) @ np.abs(delta.ravel()))
+    assert np.max(back) < 1e-12
