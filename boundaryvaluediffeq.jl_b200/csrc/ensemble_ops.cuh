@@ -23,24 +23,27 @@ template <class P, int ORDER> struct EnsImpl {
     }
     // warp per trajectory, state in shared memory (n <= 2): persistent CTAs pulling trajectories from a counter
     static constexpr bool kWarp = P::n <= 2;
+    // dynamic shared memory of ONE warp at capacity NC (a CTA holds 1, 2 or 4 warps, whatever fits)
     static size_t warp_smem_bytes(int NC) {
-        if constexpr (kWarp) return sizeof(double) * kEnsWarpsPerBlock * EnsWarpLayout<P, ORDER>::warp_doubles(NC);
+        if constexpr (kWarp) return sizeof(double) * EnsWarpLayout<P, ORDER>::warp_doubles(NC);
         else return 0;
     }
     static cudaError_t run_warp(cudaStream_t st, const EnsWarpArgs& w) {
         if constexpr (kWarp) {
-            const int smem = (int)warp_smem_bytes(w.NCs);
+            int wpb = kEnsWarpsPerBlock;
+            while (wpb > 1 && warp_smem_bytes(w.NCs) * wpb > (size_t)220 * 1024) wpb >>= 1;
+            const int smem = (int)(warp_smem_bytes(w.NCs) * wpb);
             cudaError_t e = cudaFuncSetAttribute(k_ensemble_warp<P, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
             int dev = 0, sms = 148, occ = 1;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_warp<P, ORDER>, kEnsWarpsPerBlock * 32, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ensemble_warp<P, ORDER>, wpb * 32, smem);
             if (occ < 1) occ = 1;
             long long blocks = (long long)sms * occ;
-            const long long need = (w.a.ntraj + kEnsWarpsPerBlock - 1) / kEnsWarpsPerBlock;
+            const long long need = (w.nwork + wpb - 1) / wpb;
             if (blocks > need) blocks = need;
-            k_ensemble_warp<P, ORDER><<<(unsigned)blocks, kEnsWarpsPerBlock * 32, smem, st>>>(w);
+            k_ensemble_warp<P, ORDER><<<(unsigned)blocks, wpb * 32, smem, st>>>(w);
             return cudaGetLastError();
         } else {
             return cudaErrorNotSupported;

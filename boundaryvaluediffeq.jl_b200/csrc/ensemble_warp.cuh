@@ -38,6 +38,8 @@ struct EnsWarpArgs {
     double* out_mesh;                   // [ntraj][NCs]
     double* out_y;                      // [ntraj][NCs][n]
     double* y_first;                    // [ntraj][n]
+    const long long* idx;               // optional: work item t is global trajectory idx[t] (re-runs of overflowed ones)
+    long long nwork;                    // work items (a.ntraj when idx is null)
 };
 
 template <class P, int ORDER> struct EnsWarpLayout {
@@ -649,7 +651,7 @@ constexpr int kEnsWarpsPerBlock = 4;
 
 template <class P, int ORDER>
 __global__ void __launch_bounds__(kEnsWarpsPerBlock * 32, 4)
-k_ensemble_warp(EnsWarpArgs w) {
+k_ensemble_warp(EnsWarpArgs w) {  // blockDim.x / 32 warps per CTA (fewer at the large-capacity re-run stages)
     using ES = EnsWarpSolver<P, ORDER>;
     using LY = EnsWarpLayout<P, ORDER>;
     constexpr int n = P::n;
@@ -662,8 +664,8 @@ k_ensemble_warp(EnsWarpArgs w) {
         unsigned long long t = 0ull;
         if (lane == 0) t = atomicAdd(w.counter, 1ull);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= (unsigned long long)a.ntraj) break;
-        const long long tid = (long long)t;
+        if (t >= (unsigned long long)w.nwork) break;
+        const long long tid = w.idx ? w.idx[t] : (long long)t;  // global trajectory: parameters in, outcomes out
 #pragma unroll
         for (int k = 0; k < P::np; k++) S.p[k] = a.params[tid * P::np + k];
         S.N = a.N0;
@@ -697,8 +699,8 @@ k_ensemble_warp(EnsWarpArgs w) {
                 a.resid_norm[tid] = rn;
                 a.defect_norm[tid] = dn;
             }
-            double* om = w.out_mesh + (size_t)tid * w.NCs;
-            double* oy = w.out_y + (size_t)tid * w.NCs * n;
+            double* om = w.out_mesh + (size_t)t * w.NCs;      // solution slot = work item
+            double* oy = w.out_y + (size_t)t * w.NCs * n;
             for (int i = lane; i < S.N; i += 32) om[i] = S.mesh[i];
             for (int e = lane; e < S.N * n; e += 32) oy[e] = S.y[e];
             if (lane < n) w.y_first[tid * n + lane] = S.y[lane];

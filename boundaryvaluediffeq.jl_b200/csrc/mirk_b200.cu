@@ -2117,7 +2117,11 @@ struct mirk_ensemble_s {
     unsigned long long* counters = nullptr;  // [0] work counter, [1] overflow count
     long long* overflow_list = nullptr;
     double *out_mesh = nullptr, *out_y = nullptr;
-    std::vector<long long> h_overflow;        // overflowed trajectories of the last run, sorted (slab slot = position)
+    std::vector<long long> h_overflow;        // trajectories of the last run that ended on the HBM slab, sorted (slab slot = position)
+    // on-chip re-run stages of the last run: trajectories that outgrew a stage's capacity are re-run by the same warp
+    // kernel with a larger capacity (fewer warps per SM) before anything goes to an HBM slab
+    struct Stage { int NC = 0; std::vector<long long> list; long long* d_list = nullptr; double *mesh = nullptr, *y = nullptr; size_t cap = 0; };
+    Stage stages[2];
     // trajectories whose plain Newton solve failed under the default polyalgorithm: re-run on `single` (mirk_solve)
     unsigned long long* poly_count = nullptr;
     long long* poly_list = nullptr;
@@ -2139,6 +2143,7 @@ int mirk_ensemble_destroy(mirk_ensemble_handle E) {
     if (E->st) cudaStreamSynchronize(E->st);
     dfree(E->counters); dfree(E->overflow_list); dfree(E->out_mesh); dfree(E->out_y);
     dfree(E->poly_count); dfree(E->poly_list);
+    for (auto& sg : E->stages) { dfree(sg.d_list); dfree(sg.mesh); dfree(sg.y); }
     if (E->single) mirk_destroy(E->single);
     dfree(E->work); dfree(E->params); dfree(E->u0); dfree(E->mesh0); dfree(E->resid_norm); dfree(E->defect_norm);
     dfree(E->y_first); dfree(E->tmesh); dfree(E->ty); dfree(E->retcode); dfree(E->n_mesh); dfree(E->newton_iters);
@@ -2296,21 +2301,58 @@ int mirk_ensemble_run(mirk_ensemble_handle E, float* device_ms) {
         w.out_mesh = E->out_mesh;
         w.out_y = E->out_y;
         w.y_first = E->y_first;
+        w.idx = nullptr;
+        w.nwork = E->ntraj;
         CK(cudaMemsetAsync(E->counters, 0, 2 * sizeof(unsigned long long), E->st));
         CK(E->ops->run_warp(E->st, w));
-        // trajectories whose mesh outgrew the on-chip capacity: re-run them (only them) on HBM slabs of NC nodes
+        // trajectories whose mesh outgrew the on-chip capacity are re-run — only they — first by the same warp kernel
+        // at larger capacities (4x, then whatever one warp per SM can hold), and only past that on HBM slabs
         unsigned long long novf = 0;
         CK(cudaMemcpyAsync(&novf, E->counters + 1, sizeof(novf), cudaMemcpyDeviceToHost, E->st));
         CK(cudaStreamSynchronize(E->st));
         E->h_overflow.clear();
+        for (auto& sg : E->stages) { sg.list.clear(); sg.NC = 0; }
+        int cap_prev = E->NCs;
+        for (int si = 0; si < 2 && novf > 0 && cap_prev < E->NC; si++) {
+            int cap = si == 0 ? 4 * E->NCs : 1 << 20;
+            while (cap > cap_prev && E->ops->warp_smem_bytes(cap) > (size_t)220 * 1024) cap = (cap * 15) / 16;
+            cap = std::min(cap, E->NC);
+            if (cap <= cap_prev) break;
+            auto& sg = E->stages[si];
+            sg.NC = cap;
+            sg.list.resize(novf);
+            CK(cudaMemcpy(sg.list.data(), E->overflow_list, novf * sizeof(long long), cudaMemcpyDeviceToHost));
+            std::sort(sg.list.begin(), sg.list.end());
+            const size_t need = (size_t)novf * cap;
+            if (need > sg.cap) {
+                dfree(sg.d_list); dfree(sg.mesh); dfree(sg.y);
+                CK(dalloc(&sg.d_list, (size_t)novf));
+                CK(dalloc(&sg.mesh, need));
+                CK(dalloc(&sg.y, need * E->ops->n));
+                sg.cap = need;
+            }
+            CK(cudaMemcpyAsync(sg.d_list, sg.list.data(), novf * sizeof(long long), cudaMemcpyHostToDevice, E->st));
+            CK(cudaMemsetAsync(E->counters, 0, 2 * sizeof(unsigned long long), E->st));
+            EnsWarpArgs w2 = w;
+            w2.NCs = cap;
+            w2.idx = sg.d_list;
+            w2.nwork = (long long)novf;
+            w2.out_mesh = sg.mesh;
+            w2.out_y = sg.y;
+            CK(E->ops->run_warp(E->st, w2));
+            CK(cudaMemcpyAsync(&novf, E->counters + 1, sizeof(novf), cudaMemcpyDeviceToHost, E->st));
+            CK(cudaStreamSynchronize(E->st));
+            cap_prev = cap;
+        }
         if (novf > 0) {
             E->h_overflow.resize(novf);
             CK(cudaMemcpy(E->h_overflow.data(), E->overflow_list, novf * sizeof(long long), cudaMemcpyDeviceToHost));
             std::sort(E->h_overflow.begin(), E->h_overflow.end());
-            if (E->NC <= E->NCs) {
-                // the on-chip capacity IS the final capacity (node_cap): outgrowing it is a Failure, as in thread mode
+            if (E->NC <= cap_prev) {
+                // the capacity reached IS the final capacity (node_cap): outgrowing it is a Failure, as in thread mode
                 k_ensemble_mark_failed<<<(unsigned)((novf + 255) / 256), 256, 0, E->st>>>((long long)novf, E->overflow_list, E->retcode,
                                                                                        E->n_mesh);
+                E->h_overflow.clear();
             } else {
                 const size_t stride2 = (novf + 31) / 32 * 32, need = (size_t)E->ops->slots_per_node * E->NC * stride2;
                 if (need * sizeof(double) > ((size_t)96 << 30))
@@ -2443,6 +2485,15 @@ int mirk_ensemble_get_trajectory(mirk_ensemble_handle E, int64_t traj, int32_t* 
             } else {
                 src_mesh = E->out_mesh + (size_t)traj * E->NCs;
                 src_y = E->out_y + (size_t)traj * E->NCs * E->ops->n;
+                // the last re-run stage that took this trajectory holds its solution
+                for (const auto& sg : E->stages) {
+                    const auto f = std::lower_bound(sg.list.begin(), sg.list.end(), (long long)traj);
+                    if (sg.NC > 0 && f != sg.list.end() && *f == traj) {
+                        const size_t slot = (size_t)(f - sg.list.begin());
+                        src_mesh = sg.mesh + slot * sg.NC;
+                        src_y = sg.y + slot * sg.NC * E->ops->n;
+                    }
+                }
             }
         } else {
             k_ensemble_extract<<<(N + 127) / 128, 128, 0, E->st>>>(E->stride, E->NC, E->ops->n, E->ops->oMESH, E->ops->oY,

@@ -160,7 +160,7 @@ struct EnsembleOps {
     int n, np, slots_per_node, oMESH, oY;
     void (*run)(cudaStream_t, const EnsArgs& a);                     // thread per trajectory, HBM slab (ensemble.cuh)
     cudaError_t (*run_warp)(cudaStream_t, const EnsWarpArgs& w);      // warp per trajectory, on-chip state (n <= 2), or null
-    size_t (*warp_smem_bytes)(int NC);                                // dynamic shared memory of a CTA at capacity NC
+    size_t (*warp_smem_bytes)(int NC);                                // dynamic shared memory of ONE warp at capacity NC
 };
 const EnsembleOps* ensemble_ops_small(int id, int order);
 
