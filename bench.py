@@ -341,12 +341,15 @@ def run_newton(args):
     # overlap the kernels of the other.  Partitioned handles are collective, so both host threads of every rank
     # would have to interleave identically — the pipelined figure is taken at N = 1 only.
     e2e_value, e2e_mode = e2e_serial, "one handle, one host thread"
+    concurrent = None
     if world == 1:
-        cache2, _ = _make_cache(M, partition, cfg, 1, local, args)
-        bufs1 = pinned_set()
-        e2e_loop(cache2._h, bufs1, args.warmup)
-        half = (args.steps + 1) // 2
-        th = [threading.Thread(target=e2e_loop, args=(h, b, half)) for h, b in ((cache._h, bufs0), (cache2._h, bufs1))]
+        nh = max(2, args.e2e_handles)
+        extra_caches = [_make_cache(M, partition, cfg, 1, local, args)[0] for _ in range(nh - 1)]
+        handles = [(cache._h, bufs0)] + [(c._h, pinned_set()) for c in extra_caches]
+        for h, b in handles[1:]:
+            e2e_loop(h, b, args.warmup)
+        per = (args.steps + nh - 1) // nh
+        th = [threading.Thread(target=e2e_loop, args=(h, b, per)) for h, b in handles]
         barrier()
         t0 = time.perf_counter()
         for t in th:
@@ -354,9 +357,33 @@ def run_newton(args):
         for t in th:
             t.join()
         torch.cuda.synchronize()
-        e2e_value = 2 * half / (time.perf_counter() - t0)
-        e2e_mode = "two handles on two host threads (copies of one instance overlap kernels of the other)"
-        cache2.close()
+        e2e_value = nh * per / (time.perf_counter() - t0)
+        e2e_mode = (f"{nh} handles on {nh} host threads: independent problem instances in flight, so the copies of one overlap "
+                    "the kernels of another and the narrow upper levels of one elimination share the GPU with the wide phases of another")
+        # the same handles stepping device-resident problems concurrently: aggregate Newton steps/s when several
+        # independent problems are in flight (the narrow upper levels of one elimination leave most SMs idle for the
+        # wide phases of another) — reported beside `value`, which stays the single-problem figure
+        res_ms = [0.0] * nh
+
+        def dev_loop(k, c):
+            res_ms[k] = c.bench_newton_steps(args.steps)[1]
+
+        all_caches = [cache] + extra_caches
+        for c in extra_caches:
+            c.bench_newton_steps(3)
+        th = [threading.Thread(target=dev_loop, args=(k, c)) for k, c in enumerate(all_caches)]
+        barrier()
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        # (bench_newton_steps repeats its steps once more for the per-phase events: 2 x steps per handle)
+        concurrent = {"handles": nh, "value": 2 * nh * args.steps / (time.perf_counter() - t0), "unit": UNIT,
+                      "note": "device-resident, independent C2 problems on separate streams; wall clock around the threads"}
+        for c in extra_caches:
+            c.close()
     clocks = sampler.stop() if rank == 0 else None
 
     line = None
@@ -408,6 +435,7 @@ def run_newton(args):
                                         "note": "per GPU (per segment when partitioned); the per-kernel algorithmic bytes sum to this"},
                          "live_peaks": {"fp64_fma_tflops": fp64.value, "hbm_copy_gbs": hbm_live.value}},
             "phases_ms_per_step": dict(zip(PHASES, per_step_ms)),
+            "concurrent_problems": concurrent,
             "parity_vs_single_gpu": parity,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -537,6 +565,7 @@ def main():
     ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--c5-nint", type=int, default=1999999)
     ap.add_argument("--c4-nint", type=int, default=3999)
+    ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles / host threads of the end-to-end leg")
     ap.add_argument("--extra-timeout", type=float, default=300.0)
     ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
     args = ap.parse_args()
