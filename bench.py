@@ -342,9 +342,12 @@ def run_newton(args):
     # would have to interleave identically — the pipelined figure is taken at N = 1 only.
     e2e_value, e2e_mode = e2e_serial, "one handle, one host thread"
     concurrent = None
-    if world == 1:
+    # (partitioned handles are collective: every rank drives handle k from its host thread k, and each handle has its
+    #  own peer-memory exchange buffers, so the handles' collectives cannot interleave wrongly — not true of NCCL, whose
+    #  communicators would need a global launch order, so that flavour keeps the serial figure)
+    if world == 1 or getattr(cache, "exchange", None) == "p2p":
         nh = max(2, args.e2e_handles)
-        extra_caches = [_make_cache(M, partition, cfg, 1, local, args)[0] for _ in range(nh - 1)]
+        extra_caches = [_make_cache(M, partition, cfg, world, local, args)[0] for _ in range(nh - 1)]
         handles = [(cache._h, bufs0)] + [(c._h, pinned_set()) for c in extra_caches]
         for h, b in handles[1:]:
             e2e_loop(h, b, args.warmup)
@@ -357,7 +360,7 @@ def run_newton(args):
         for t in th:
             t.join()
         torch.cuda.synchronize()
-        e2e_value = nh * per / (time.perf_counter() - t0)
+        e2e_value = world * nh * per / allmax(time.perf_counter() - t0)
         e2e_mode = (f"{nh} handles on {nh} host threads: independent problem instances in flight, so the copies of one overlap "
                     "the kernels of another and the narrow upper levels of one elimination share the GPU with the wide phases of another")
         # the same handles stepping device-resident problems concurrently: aggregate Newton steps/s when several
@@ -368,20 +371,22 @@ def run_newton(args):
         def dev_loop(k, c):
             res_ms[k] = c.bench_newton_steps(args.steps)[1]
 
-        all_caches = [cache] + extra_caches
-        for c in extra_caches:
-            c.bench_newton_steps(3)
-        th = [threading.Thread(target=dev_loop, args=(k, c)) for k, c in enumerate(all_caches)]
+        if world == 1:
+            all_caches = [cache] + extra_caches
+            for c in extra_caches:
+                c.bench_newton_steps(3)
+            th = [threading.Thread(target=dev_loop, args=(k, c)) for k, c in enumerate(all_caches)]
+            barrier()
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            # (bench_newton_steps repeats its steps once more for the per-phase events: 2 x steps per handle)
+            concurrent = {"handles": nh, "value": 2 * nh * args.steps / (time.perf_counter() - t0), "unit": UNIT,
+                          "note": "device-resident, independent C2 problems on separate streams; wall clock around the threads"}
         barrier()
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        torch.cuda.synchronize()
-        # (bench_newton_steps repeats its steps once more for the per-phase events: 2 x steps per handle)
-        concurrent = {"handles": nh, "value": 2 * nh * args.steps / (time.perf_counter() - t0), "unit": UNIT,
-                      "note": "device-resident, independent C2 problems on separate streams; wall clock around the threads"}
         for c in extra_caches:
             c.close()
     clocks = sampler.stop() if rank == 0 else None
