@@ -385,6 +385,64 @@ __device__ __forceinline__ void warp_backsub_group(int g, const int* nodes, cons
     }
 }
 
+// Back substitution of one group for n = 16 with COALESCED factor loads.  warp_backsub_group gives every lane one factor
+// row, so each of its 8 LDG.128 per node touches 32 different 128-byte lines and the level-0 pass (one factor pair per
+// mesh node, 77 MB at C2) is bound by the L1 tag stage at ~3 TB/s.  Here lane i reads chunk i + 32k (k = 0..3) of the
+// node's contiguous 2 KB TL block and the same of TR (four 128-byte lines per request), which leaves it with columns
+// 2s, 2s+1 (s = i & 7) of rows 4k + (i >> 3): two-term partial dot products, summed over the 8 lanes of a row by three
+// xor-shuffle steps.  The new node's solution reaches the lanes that need it as the next right-hand vector by two
+// shuffles, so the right-to-left chain never touches shared memory.
+__device__ __forceinline__ void warp_backsub_group16c(int g, const int* nodes, const int* gs, const double* TL, const double* TR,
+                                                      const double* rt, double* delta, int lane, double* yup = nullptr) {
+    constexpr int n = 16;
+    constexpr size_t nn = (size_t)n * n;
+    const int k0 = gs[g], k1 = gs[g + 1];
+    if (k1 - k0 == 1) return;
+    const int sub = lane & 7, rg = lane >> 3;
+    const double2 da = *reinterpret_cast<const double2*>(delta + (size_t)nodes[k0] * n + 2 * sub);
+    double2 dr = *reinterpret_cast<const double2*>(delta + (size_t)nodes[k1] * n + 2 * sub);
+    // the factors do not depend on the running solution: nodes j-1 and j-2 are in flight while node j is computed
+    // (two nodes = 8 KB per warp keep enough bytes in flight for the HBM latency at 11 warps per SM)
+    double2 tl[4], tr[4], tl1[4], tr1[4];
+    double rtv[4], rtv1[4];
+    auto fetch = [&](int c, double2 (&l)[4], double2 (&r)[4], double (&t)[4]) {
+        const double2* pl = reinterpret_cast<const double2*>(TL + c * nn) + lane;
+        const double2* pr = reinterpret_cast<const double2*>(TR + c * nn) + lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { l[k] = pl[32 * k]; r[k] = pr[32 * k]; t[k] = rt[(size_t)c * n + 4 * k + rg]; }
+    };
+    fetch(nodes[k1 - 1], tl, tr, rtv);
+    if (k1 - 2 > k0) fetch(nodes[k1 - 2], tl1, tr1, rtv1);
+    // sources of the next right-hand pair: rows 2s, 2s+1 live in the lanes of row groups 2(s&1), 2(s&1)+1, slot s >> 1
+    const int src0 = 8 * (2 * (sub & 1)) + sub, src1 = src0 + 8;
+    for (int j = k1 - 1; j > k0; j--) {
+        const int c = nodes[j];
+        double2 tl2[4], tr2[4];
+        double rtv2[4];
+        if (j - 2 > k0) fetch(nodes[j - 2], tl2, tr2, rtv2);
+        double p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = fma(tl[k].x, da.x, tl[k].y * da.y) + fma(tr[k].x, dr.x, tr[k].y * dr.y);
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) p[k] += __shfl_xor_sync(kFullMask, p[k], m);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = rtv[k] - p[k];  // solution rows 4k + rg, in every lane of the row group
+        const double own = (sub & 2) ? ((sub & 1) ? p[3] : p[2]) : ((sub & 1) ? p[1] : p[0]);  // row 4 (sub & 3) + rg
+        if (sub < 4) {
+            delta[(size_t)c * n + 4 * sub + rg] = own;
+            if (yup) yup[(size_t)c * n + 4 * sub + rg] -= own;  // fused Newton update y -= delta (level 0 only)
+        }
+        const double v = (sub & 4) ? ((sub & 2) ? p[3] : p[2]) : ((sub & 2) ? p[1] : p[0]);  // slot sub >> 1
+        dr.x = __shfl_sync(kFullMask, v, src0);
+        dr.y = __shfl_sync(kFullMask, v, src1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tl[k] = tl1[k]; tr[k] = tr1[k]; rtv[k] = rtv1[k]; tl1[k] = tl2[k]; tr1[k] = tr2[k]; rtv1[k] = rtv2[k]; }
+    }
+}
+
 }  // namespace mirk
 #include "abd_mma.cuh"  // n = 16 on the FP64 tensor path (needs WarpABD above; included from here only)
 namespace mirk {
@@ -439,6 +497,9 @@ k_backsub_warp(int G, const int* __restrict__ nodes, const int* __restrict__ gs,
             yup[(size_t)b * n + lane] -= delta[(size_t)b * n + lane];
         }
     }
+#if !defined(MIRK_BACKSUB_ROWS)
+    if constexpr (n == 16) { warp_backsub_group16c(g, nodes, gs, TL, TR, rt, delta, lane, yup); return; }
+#endif
     warp_backsub_group<n>(g, nodes, gs, TL, TR, rt, delta, dbuf[wib][0], dbuf[wib][1], lane, yup);
 }
 
