@@ -347,6 +347,49 @@ def test_full_size_large_block_configs_match_golden(M, key, maker):
     cache.close()
 
 
+def test_c5_full_size_on_one_gpu_agrees_with_the_slice_golden(M):
+    """BASELINE config C5 at its FULL size on one B200 (n = 32, 2 000 000 nodes, MIRK6: 66 GB of Jacobian blocks and
+    factors).  The oracle needs ~10 minutes per step at this size, so the check is a size-independent property: the same
+    BVP on the 250 000-node mesh of the committed golden (an 8x coarser, still fully resolved 6th-order discretisation)
+    has the same solution (compared at the golden's nodes by Hermite interpolation), and Newton contracts to rounding level."""
+    import json
+    import os
+    import torch
+    from boundaryvaluediffeq_jl_b200 import configs
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120e9:
+        pytest.skip("needs ~100 GB of free HBM")
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "newton_golden_large.json")))["c5_slice"]
+    c = configs.c5_chain16(1999999)
+    cache = M.init(M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh), M.MIRK6(), adaptive=False)
+    _, nrm0 = cache.residual()
+    norms = [nrm0]
+    for _ in range(gold["steps"]):
+        st, nrm = cache.newton_step()
+        assert st == 0
+        norms.append(nrm)
+    # |F| is the h-scaled collocation residual (4e-6 at the linear guess): monotone, superlinear at the end
+    assert all(b < 0.5 * a for a, b in zip(norms, norms[1:])) and norms[-1] < 1e-3 * norms[-2] and norms[-1] < 1e-10, norms
+    t, u = cache.solution()
+    cache.close()
+    # the two meshes share no interior node (1 999 999 vs 249 999 intervals): compare the angles at the golden's nodes by
+    # cubic Hermite interpolation on the fine mesh (theta' = omega is part of the state; h = 2.5e-7, so the
+    # interpolation error is far below rounding)
+    cs = configs.c5_chain16(gold["nint"])
+    npend = 16
+    for name, idx in (("y_mid", cs.N // 2), ("y_q1", cs.N // 4), ("y_last", cs.N - 2)):
+        ts = cs.mesh[idx]
+        k = min(max(int(np.searchsorted(t, ts)) - 1, 0), len(t) - 2)
+        h = t[k + 1] - t[k]
+        x = (ts - t[k]) / h
+        th0, th1, om0, om1 = u[k, :npend], u[k + 1, :npend], u[k, npend:], u[k + 1, npend:]
+        th = ((1 + 2 * x) * (1 - x) ** 2) * th0 + (x * (1 - x) ** 2) * h * om0 + (x * x * (3 - 2 * x)) * th1 + (x * x * (x - 1)) * h * om1
+        ref = np.array(gold[name])[:npend]
+        assert np.max(np.abs(th - ref)) < 1e-9 * max(1.0, np.max(np.abs(ref))), name
+    assert np.all(np.isfinite(u))
+    a, b = c.p[2:2 + npend], c.p[2 + npend:2 + 2 * npend]
+    assert np.max(np.abs(u[0, :npend] - a)) < 1e-12 and np.max(np.abs(u[-1, :npend] - b)) < 1e-12
+
 USER_FUNCTOR = r"""
 // u'' + lam * exp(u) = 0, u(0) = u(1) = 0 (1-D Bratu) as a user-supplied device functor
 struct UserBratu {
