@@ -1,4 +1,5 @@
-// abd_team.cuh — the n = 16 merge of the ABD reduction by a TEAM of NW warps (NW = 1, 2, 4), DMMA fragment layout.
+// abd_team.cuh — the n = 16 merge of the ABD reduction by a TEAM of NW warps (NW = 1, 2, 4), DMMA fragment layout, and the
+// upper levels of the reduction tree as THREAD-BLOCK CLUSTERS (k_seg_cluster16).
 //
 // Same algorithm, pivots, relation and factor formats as abd_mma.cuh (one warp per merge).  There a merge is a serial
 // stream of ~1 650 warp instructions that one warp retires at one per ~5 cycles (4.1 us, profiles/r01_notes.md): the
@@ -15,6 +16,8 @@
 //     (E) W[:, live columns] += G (rows of this warp x 4) * P (4 x 48): TRW DMMA per live tile column
 // The per-row bookkeeping (rhs, pivot column myq, 1/pivot) is lane-per-row and replicated in every warp.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "abd_warp.cuh"
 
 namespace mirk {
@@ -237,6 +240,49 @@ template <int NW> struct TeamABD16 {
         }
         if (wv == 0 && ((carried >> lane) & 1u)) orr[__popc(carried & ((1u << lane) - 1u))] = rhs;
     }
+    // incoming relation from a staged copy in shared memory (rows [L | R | r | pad], WarpABD<16>::stage_stride doubles each)
+    __device__ __forceinline__ static void load_incoming_staged(double (&w)[TRW][TJ][2], double& rhs, unsigned freem, const double* st,
+                                                                int lane, int wv) {
+        const int g = lane >> 2, t = lane & 3;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(st);
+        constexpr int SS = WarpABD<16>::stage_stride;
+#pragma unroll
+        for (int trl = 0; trl < TRW; trl++) {
+            const int r = 8 * (wv * TRW + trl) + g;
+            if ((freem >> r) & 1u) {
+                const int idx = __popc(freem & ((1u << r) - 1u));
+                const unsigned row = sa + 8u * (unsigned)(idx * SS + 2 * t);
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    const double2 e = lds_v2f64(row + 8u * (unsigned)(8 * jj)), b = lds_v2f64(row + 8u * (unsigned)(n + 8 * jj));
+                    w[trl][jj][0] = e.x; w[trl][jj][1] = e.y;
+                    w[trl][2 + jj][0] = 0.0; w[trl][2 + jj][1] = 0.0;
+                    w[trl][4 + jj][0] = b.x; w[trl][4 + jj][1] = b.y;
+                }
+            }
+        }
+        if ((freem >> lane) & 1u) rhs = lds_f64(sa + 8u * (unsigned)(__popc(freem & ((1u << lane) - 1u)) * SS + 2 * n));
+    }
+    // the 16 carried rows, in row order, into a staged copy (dst: generic pointer, possibly another CTA's shared memory):
+    // the relation (L, R, r) = (A part, E part, rhs) of the carried rows
+    __device__ __forceinline__ static void store_relation_staged(const double (&w)[TRW][TJ][2], double rhs, unsigned carried, double* dst,
+                                                                 int lane, int wv) {
+        const int g = lane >> 2, t = lane & 3;
+        constexpr int SS = WarpABD<16>::stage_stride;
+#pragma unroll
+        for (int trl = 0; trl < TRW; trl++) {
+            const int r = 8 * (wv * TRW + trl) + g;
+            if ((carried >> r) & 1u) {
+                double* row = dst + __popc(carried & ((1u << r) - 1u)) * SS + 2 * t;
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    *reinterpret_cast<double2*>(row + 8 * jj) = make_double2(w[trl][2 + jj][0], w[trl][2 + jj][1]);
+                    *reinterpret_cast<double2*>(row + n + 8 * jj) = make_double2(w[trl][jj][0], w[trl][jj][1]);
+                }
+            }
+        }
+        if (wv == 0 && ((carried >> lane) & 1u)) dst[__popc(carried & ((1u << lane) - 1u)) * SS + 2 * n] = rhs;
+    }
 };
 
 // One group of one reduction level by a team (arguments as warp_reduce_group; CG: read the relations past L1 —
@@ -282,148 +328,93 @@ k_reduce_team16(int G, const double* __restrict__ inL, const double* __restrict_
         if (lane == 0 && wv == 0) atomicExch(status, 1);
 }
 
-// ---- the reduction TREE above level 0 in two launches (two-point problems: pure radix-2 pairing, one root) ----------
-// k_tree_up16    one team per group of the tree's first level.  A team merges its group, publishes the collapsed relation
-//                and arrives at the parent group's counter; the LAST arriver of a parent continues with the parent's merge
-//                (the relations of its sibling were written by another CTA: read past L1), every other team exits — no
-//                spinning, no co-residency requirement, no launch or grid barrier between levels.  The team that merges
-//                the root also runs the closing solve on the two kept nodes + the boundary rows.
-// k_tree_down16  back substitution of the tree, one warp per group of the first level.  Warp b owns the merges
-//                (l, b >> l) for l <= ctz(b) — the left spine of the sub-tree it is the leftmost leaf of — and walks them
-//                top down with the running solution in registers; the right child of a merge waits for the merge's flag
-//                (one waiter per flag, which resets it).  Launched cooperatively: all warps are co-resident by contract.
-#if defined(MIRK_TREE_PROF)  // experiments: latest start time (globaltimer, ns) of a merge of each tree level
-__device__ unsigned long long g_tree_prof[4 * (kMaxTail + 2)];
-#endif
-struct TreeSync {
-    unsigned* cnt;           // arrival counters, one per group of levels >= 1 (self-resetting)
-    unsigned* flag;          // completion flags of the down sweep, same indexing (reset by their one waiter)
-    int off[kMaxTail + 1];   // offset of level l
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int NW>
-__global__ void __launch_bounds__(32 * NW)
-k_tree_up16(const TailArgs a, const TreeSync ts) {
-    extern __shared__ double tail_smem[];
-    using TA = TeamABD16<NW>;
-    __shared__ __align__(16) double sm[TA::smem_doubles];
-    __shared__ int s_last;
-    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-    int g = blockIdx.x;
-    for (int l = 0;; l++) {
-#if defined(MIRK_TREE_PROF)
-#define TREE_STAMP(ph) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); atomicMax(&g_tree_prof[4 * l + (ph)], t_); } } while (0)
+// ---- a SEGMENT of <= 4 radix-2 levels of the tree by thread-block clusters of 8 CTAs (one team of 4 warps each) -------
+// Same level tables and block-to-sub-tree mapping as k_tail_warp with multi = 1 (TailArgs: cluster c owns groups
+// [8c, 8c + 8) of the segment's first level), other execution: the 8 merges of a sub-tree's first level run on 8 DIFFERENT SMs instead of 8 warps of one (no contention for
+// one SM's shared-memory pipe), every merge is the 5 300-cycle team merge instead of the 8 000-cycle one-warp merge, and a
+// level boundary is ONE cluster barrier: the right partner writes its collapsed relation straight into the left partner's
+// shared memory (DSMEM, staged format of the level-0 kernel) while the left partner's relation never leaves its registers.
+// Factors of the eliminated nodes go to global memory as everywhere.  Requires pure pairing (gs[g] = 2g) inside the segment.
+// Measured (B200, profiles/r02/notes.md): 3.0 us per level (2.4 merge + 0.6 cluster barrier) against 5.5 us in
+// k_tail_warp; a cluster launch costs ~4 us more than a plain one and a segment of 834 groups (105 clusters, 840 CTAs)
+// does not fit one wave of co-scheduled clusters, so the host uses this kernel for segments of <= 148 groups only
+// (C2: the 105 -> 7 segment, 21.7 -> 15.9 us) and the one-SM kernels elsewhere (the one-block tail is dominated by its
+// closing solve and back substitution: no gain there).
+constexpr int kClusterCTAs = 8;
+#if defined(MIRK_SEG_PROF)  // experiments: globaltimer stamps of cluster 0, rank 0
+__device__ unsigned long long g_seg_prof[64];
+#define SEG_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_seg_prof[i] = t_; } } while (0)
 #else
-#define TREE_STAMP(ph) do { } while (0)
+#define SEG_STAMP(i) do { } while (0)
 #endif
-        TREE_STAMP(0);
-        // a singular block is reported and the protocol goes on (garbage flows up): the counters stay consistent
-        if (!team_reduce_group16<NW, true>(g, a.inL[l], a.inR[l], a.inr[l], a.outL[l], a.outR[l], a.outr[l], a.nodes[l], a.gs[l],
-                                           a.TL, a.TR, a.rt, sm, lane, wv, 1))
-            if (threadIdx.x == 0) atomicExch(a.status, 1);
-        TREE_STAMP(1);
-        if (l + 1 == a.nlev) break;  // that was the root
-        __threadfence();             // this thread's part of the relation is visible device-wide ...
-        TA::sync(1);                 // ... and so is every other thread's, before the arrival is counted
-        TREE_STAMP(2);
-        if (threadIdx.x == 0) {
-            const int p = g >> 1;
-            const int nchild = a.gs[l + 1][p + 1] - a.gs[l + 1][p];
-            unsigned* c = ts.cnt + ts.off[l + 1] + p;
-            const unsigned old = atomicAdd(c, 1u);
-            const int last = old + 1u == (unsigned)nchild;
-            if (last) *c = 0u;  // nobody touches it again in this solve
-            s_last = last;     // (the sibling's relation is read past L1 — ld.global.cg — after this barrier)
-        }
-        TA::sync(1);
-        TREE_STAMP(3);
-        if (!s_last) return;
-        g >>= 1;
-    }
-    __syncthreads();
-    if (a.Q > 0)
-    final_solve_body(16, a.Q, a.kept, a.relL, a.relR, a.relr, a.L, a.La, a.m_ptr, a.bc_nodes, a.Bc, a.resid, a.tail_off, a.M, a.delta,
-                     a.status, tail_smem);
-}
 
-__global__ void __launch_bounds__(32)
-k_tree_down16(const TailArgs a, const TreeSync ts) {
+__global__ void __cluster_dims__(kClusterCTAs, 1, 1) __launch_bounds__(128)
+k_seg_cluster16(const TailArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    using TA = TeamABD16<4>;
     constexpr int n = 16;
     constexpr size_t nn = (size_t)n * n;
-    const int lane = threadIdx.x, b = blockIdx.x;
-    const int half = lane >> 4, q = lane & 15;
-    int lt = a.nlev - 1;
-    if (b != 0 && __ffs(b) - 1 < lt) lt = __ffs(b) - 1;
-    // factor row q of (half ? TR : TL) and rt of the eliminated node of merge (l, b >> l); has = the group is a pair
-    double rv[n], rtv = 0.0;
-    int c = 0, na = 0, nb = 0;
-    bool has = false;
-    auto fetch = [&](int l) {
-        const int g = b >> l;
-        const int k0 = a.gs[l][g], k1 = a.gs[l][g + 1];
-        has = k1 - k0 == 2;
-        na = a.nodes[l][k0];
-        nb = a.nodes[l][k1];
-        if (has) {
-            c = a.nodes[l][k0 + 1];
-            const double* row = (half ? a.TR : a.TL) + c * nn + (size_t)q * n;
-#pragma unroll
-            for (int k = 0; k < n; k += 2) {
-                const double2 v = ldcg_v2f64(row + k);
-                rv[k] = v.x; rv[k + 1] = v.y;
+    __shared__ __align__(16) double sm[TA::smem_doubles];
+    __shared__ __align__(16) double stage[2][WarpABD<16>::stage_doubles];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int rank = (int)cluster.block_rank(), cl = (int)blockIdx.x / kClusterCTAs;
+    const int leaf = kClusterCTAs * cl + rank;  // this CTA's group of the segment's first level
+    double w[TA::TRW][TA::TJ][2];
+    double rhs = 0.0;
+    unsigned carried = 0x0000ffffu;
+    bool have = false, ok = true;
+    SEG_STAMP(0);
+    {
+        if (leaf < a.G[0]) {
+            const int k0 = a.gs[0][leaf], k1 = a.gs[0][leaf + 1];
+            TA::load_carried<false>(w, rhs, a.inL[0] + k0 * nn, a.inR[0] + k0 * nn, a.inr[0] + (size_t)k0 * n, lane, wv);
+            for (int j = k0 + 1; j < k1; j++) {
+                TA::load_incoming<false>(w, rhs, ~carried, a.inL[0] + j * nn, a.inR[0] + j * nn, a.inr[0] + (size_t)j * n, lane, wv);
+                int myq;
+                double myinv;
+                ok = TA::eliminate(w, rhs, lane, wv, 1, sm, myq, myinv) && ok;
+                const int c = a.nodes[0][j];
+                carried = TA::store_factors_and_shift(w, rhs, myq, myinv, a.TL + c * nn, a.TR + c * nn, a.rt + (size_t)c * n, lane, wv);
             }
-            rtv = ldcg_f64(a.rt + (size_t)c * n + q);
+            have = true;
         }
-    };
-    fetch(lt);
-    if (lt + 1 < a.nlev) {  // the right child of merge (lt + 1, b >> (lt + 1)): wait for its solution
-        unsigned* f = ts.flag + ts.off[lt + 1] + (b >> (lt + 1));
-        if (lane == 0) {
-            while (*(volatile unsigned*)f == 0u) { }
-            *(volatile unsigned*)f = 0u;
-            __threadfence();
+        SEG_STAMP(1);
+        for (int t = 1; t < a.nlev; t++) {
+            const int half = 1 << (t - 1);
+            double* buf = stage[t & 1];
+            if (have && (rank & (2 * half - 1)) == half) {  // right partner: hand the relation over and retire
+                TA::store_relation_staged(w, rhs, carried, cluster.map_shared_rank(buf, rank - half), lane, wv);
+                have = false;
+            }
+            cluster.sync();
+            SEG_STAMP(2 * t);
+            if (have && (rank & (2 * half - 1)) == 0) {
+                const int g = leaf >> t;
+                const int k0 = a.gs[t][g], k1 = a.gs[t][g + 1];
+                if (k1 - k0 == 2) {  // (a lone relation at the end of a level passes through)
+                    TA::load_incoming_staged(w, rhs, ~carried, buf, lane, wv);
+                    int myq;
+                    double myinv;
+                    ok = TA::eliminate(w, rhs, lane, wv, 1, sm, myq, myinv) && ok;
+                    const int c = a.nodes[t][k0 + 1];
+                    carried = TA::store_factors_and_shift(w, rhs, myq, myinv, a.TL + c * nn, a.TR + c * nn, a.rt + (size_t)c * n, lane, wv);
+                }
+            }
+            SEG_STAMP(2 * t + 1);
+            // (the buffers alternate, so the next level's writer cannot overtake this level's reader: one barrier per level)
         }
-        __syncwarp();
+        if (have) {
+            const int g = leaf >> (a.nlev - 1), l = a.nlev - 1;
+            TA::store_relation(w, rhs, carried, a.outL[l] + g * nn, a.outR[l] + g * nn, a.outr[l] + (size_t)g * n, lane, wv);
+        }
+        if (!ok && threadIdx.x == 0) atomicExch(a.status, 1);
     }
-    // x = element q of the solution at (half ? nb : na)
-    double x = ldcg_f64(a.delta + (size_t)(half ? nb : na) * n + q);
-    for (int l = lt; l >= 0; l--) {
-        double d16 = 0.0;
-        const int cc = c;
-        const bool had = has;
-        if (has) {
-            double p4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < n; k++) p4[k & 3] = fma(rv[k], __shfl_sync(kFullMask, x, 16 * half + k), p4[k & 3]);
-            double acc = (p4[0] + p4[1]) + (p4[2] + p4[3]);
-            acc += __shfl_xor_sync(kFullMask, acc, 16);
-            d16 = rtv - acc;  // element q of the eliminated node's solution, in both halves
-            if (half == 0) a.delta[(size_t)c * n + q] = d16;
-        }
-        if (l >= 1) {
-            const int g = b >> l;
-            if (2 * g + 1 < a.G[l - 1]) {  // a right child waits for this merge
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) *(volatile unsigned*)(ts.flag + ts.off[l] + g) = 1u;
-            }
-            // descend into the left child (l - 1, 2g): its ends are (na, c) when this merge was a pair, else the same ends
-            fetch(l - 1);
-            if (had) {
-                if (nb == cc && half == 1) x = d16;
-                if (na == cc && half == 0) x = d16;
-            }
-        }
-    }
+}
+
+inline cudaError_t launch_seg_cluster16(cudaStream_t st, const TailArgs& a, int clusters) {
+    k_seg_cluster16<<<clusters * kClusterCTAs, 128, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace mirk

@@ -23,6 +23,7 @@
 #include "abd_block.cuh"
 #include "abd_pair.cuh"
 #include "abd_warp.cuh"
+#include "abd_team.cuh"
 #include "ensemble.cuh"
 #include "ensemble_warp.cuh"
 #include "generic_kernels.cuh"
@@ -585,6 +586,13 @@ static void fill_tail_levels(TailArgs& a, const Plan& P, const SolveCtx& C, int 
     a.TL = C.TL; a.TR = C.TR; a.rt = C.rt; a.delta = C.delta; a.status = status;
 }
 
+// n = 16: narrow segments of the upper levels as thread-block clusters (abd_team.cuh: k_seg_cluster16);
+// MIRK_CLUSTER_TREE=0 keeps the one-SM segment kernel everywhere (A/B runs)
+static bool use_cluster_tree() {
+    static const bool on = !(getenv("MIRK_CLUSTER_TREE") && atoi(getenv("MIRK_CLUSTER_TREE")) == 0);
+    return on;
+}
+
 static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int l_end = kMaxLev) {
     Plan& P = *C.P;
     const int n = S->n;
@@ -599,7 +607,9 @@ static int abd_reduce(mirk_solver_s* S, const SolveCtx& C, int l_begin = 0, int 
             fill_tail_levels(a, P, C, l, P.seg[si + 1], (int*)(S->words + 2));
             a.mode = 1;
             a.multi = 1;
-            CK(launch_warp_tail(S->st, n, a, (P.G[l] + kTailWarps - 1) / kTailWarps, 0));
+            static const int cluster_max_groups = getenv("MIRK_CLUSTER_MAXG") ? atoi(getenv("MIRK_CLUSTER_MAXG")) : 148;
+            if (n == 16 && use_cluster_tree() && P.G[l] <= cluster_max_groups) CK(launch_seg_cluster16(S->st, a, (P.G[l] + kClusterCTAs - 1) / kClusterCTAs));
+            else CK(launch_warp_tail(S->st, n, a, (P.G[l] + kTailWarps - 1) / kTailWarps, 0));
             S->launches++;
             l = P.seg[si + 1] - 1;
             continue;

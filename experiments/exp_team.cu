@@ -5,7 +5,7 @@
 #include <cmath>
 #include <vector>
 #include <random>
-#include "abd_team.cuh"
+#include "abd_tree_exp.cuh"
 using namespace mirk;
 struct Prob {
     int R, G; double *L, *Rr, *r, *oL, *oR, *orr, *TL, *TR, *rt; int *nodes, *gs, *status;
@@ -125,6 +125,41 @@ template <class F> static float best_us(F&& f, int reps = 7) {
     for (int i = 0; i < reps; i++) { cudaEventRecord(e0); f(); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
     return best * 1e3f;
 }
+// levels [l0, l0 + nl) of the tree as ONE segment launch: k_tail_warp (multi) against k_seg_cluster16
+static void run_segment(int R, int l0, int nl) {
+    Tree T = make_tree(R);
+    // run the levels below l0 once so that the segment's inputs exist
+    for (int l = 0; l < l0; l++) { const int G = T.G[l]; k_reduce_warp<16, 3><<<G, 32>>>(G, T.a.inL[l], T.a.inR[l], T.a.inr[l], T.a.outL[l], T.a.outR[l], T.a.outr[l], T.a.nodes[l], T.a.gs[l], T.TL, T.TR, T.rt, T.status); }
+    cudaDeviceSynchronize();
+    if (l0 + nl > T.nlev) nl = T.nlev - l0;
+    TailArgs a; memset(&a, 0, sizeof(a));
+    a.nlev = nl; a.mode = 1; a.multi = 1;
+    for (int t = 0; t < nl; t++) { const int l = l0 + t; a.G[t] = T.G[l]; a.nodes[t] = T.a.nodes[l]; a.gs[t] = T.a.gs[l]; a.inL[t] = T.a.inL[l]; a.inR[t] = T.a.inR[l]; a.inr[t] = T.a.inr[l]; a.outL[t] = T.a.outL[l]; a.outR[t] = T.a.outR[l]; a.outr[t] = T.a.outr[l]; }
+    a.TL = T.TL; a.TR = T.TR; a.rt = T.rt; a.delta = T.delta; a.status = T.status;
+    const int G0 = T.G[l0], Gl = T.G[l0 + nl - 1];
+    const size_t olen = (size_t)Gl * (2 * 256 + 16);
+    std::vector<double> o0(olen), o1(olen);
+    float t_old = best_us([&] { k_tail_warp<16><<<(G0 + kTailWarps - 1) / kTailWarps, kTailWarps * 32>>>(a); });
+    cudaMemcpy(o0.data(), a.outL[nl - 1], 8 * olen, cudaMemcpyDeviceToHost);
+    cudaMemset(a.outL[nl - 1], 0, 8 * olen);
+    float t_new = best_us([&] { launch_seg_cluster16(0, a, (G0 + kClusterCTAs - 1) / kClusterCTAs); });
+    cudaMemcpy(o1.data(), a.outL[nl - 1], 8 * olen, cudaMemcpyDeviceToHost);
+    float t_lvl = best_us([&] { for (int t = 0; t < nl; t++) { const int G = a.G[t]; k_reduce_team16<4, 1><<<G, 128>>>(G, a.inL[t], a.inR[t], a.inr[t], a.outL[t], a.outR[t], a.outr[t], a.nodes[t], a.gs[t], T.TL, T.TR, T.rt, T.status); } });
+    printf("segment R=%5d levels [%d,%d) groups %4d -> %3d : k_tail_warp %6.1f us | k_seg_cluster16 %6.1f us | %d team launches %6.1f us | max |out diff| %.2e %s\n",
+           R, l0, l0 + nl, G0, Gl, t_old, t_new, nl, t_lvl, maxdiff(o0, o1), cudaGetErrorString(cudaGetLastError()));
+#if defined(MIRK_SEG_PROF)
+    {
+        unsigned long long z[64] = {0}, h[64];
+        cudaMemcpyToSymbol(g_seg_prof, z, sizeof(z));
+        launch_seg_cluster16(0, a, (G0 + kClusterCTAs - 1) / kClusterCTAs);
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_seg_prof, sizeof(h));
+        printf("  cluster 0 rank 0 stamps (ns): start");
+        for (int i = 1; i < 16 && h[i]; i++) printf(" %lld", (long long)(h[i] - h[0]));
+        printf("\n");
+    }
+#endif
+}
 static void run_tree(int R) {
     constexpr int n = 16;
     Tree T = make_tree(R);
@@ -176,6 +211,10 @@ static void prof(int NW) {
 int main() {
 #if defined(MIRK_TEAM_PROF)
     prof(4); prof(2); prof(1);
+    return 0;
+#endif
+    run_segment(1667, 0, 4); run_segment(1667, 4, 4); run_segment(1667, 8, 4); run_segment(64, 0, 4); run_segment(8, 0, 3);
+#if defined(MIRK_SEG_PROF)
     return 0;
 #endif
     run_tree(1667); run_tree(209); run_tree(27); run_tree(4);
