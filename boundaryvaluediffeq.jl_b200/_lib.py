@@ -82,6 +82,7 @@ SYMBOLS = {
     "mirk_nlsolve_stats": (C.c_int, [Handle, ip, ip]),
     "mirk_defect": (C.c_int, [Handle, dp, dp]),
     "mirk_refine_mesh": (C.c_int, [Handle, ip]),
+    "mirk_mesh_select": (C.c_int, [C.c_int32, C.c_double, C.c_int32, C.c_int32, dp, dp, ip, dp, C.c_int32]),
     "mirk_solve": (C.c_int, [Handle, C.POINTER(Result)]),
     "mirk_get_mesh_size": (C.c_int, [Handle, ip]),
     "mirk_get_solution": (C.c_int, [Handle, dp, dp]),

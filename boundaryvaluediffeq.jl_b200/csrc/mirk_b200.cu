@@ -1819,6 +1819,41 @@ int mirk_refine_mesh(mirk_handle S, int32_t* n_mesh_new) {
     return info;
 }
 
+int mirk_mesh_select(int32_t order, double abstol, int32_t max_num_subintervals, int32_t n_mesh, const double* mesh,
+                     const double* est, int32_t* n_mesh_new, double* mesh_new, int32_t device) {
+    if (!mesh || !est || !n_mesh_new || !mesh_new) return fail(MIRK_ERR_ARG, "NULL argument");
+    if (n_mesh < 2) return fail(MIRK_ERR_ARG, "a mesh needs at least two nodes");
+    if (order < 2 || order > kMIRK6I) return fail(MIRK_ERR_UNSUPPORTED, "order must be 2..7");
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(MIRK_ERR_NO_DEVICE, "no CUDA device"); }
+    const int N = n_mesh, cap = std::max(N, max_num_subintervals + 1);
+    double *d_mesh = nullptr, *d_est = nullptr, *d_new = nullptr;
+    int* d_out = nullptr;
+    auto cleanup = [&]() { dfree(d_mesh); dfree(d_est); dfree(d_new); dfree(d_out); };
+    if (dalloc(&d_mesh, (size_t)N) != cudaSuccess || dalloc(&d_est, (size_t)N) != cudaSuccess ||
+        dalloc(&d_new, (size_t)cap) != cudaSuccess || dalloc(&d_out, (size_t)2) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return fail(MIRK_ERR_CUDA, "allocation failed");
+    }
+    cudaMemcpy(d_mesh, mesh, sizeof(double) * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_est, est, sizeof(double) * (N - 1), cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(k_mesh_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    const int smem_needed = (int)(sizeof(double) * 2 * (size_t)N);
+    const int use_smem = smem_needed <= kSmemLimit;
+    const int pconv = order == kMIRK6I ? 6 : order;
+    // DefectControl's selector: exponent 1 / (p + 1), halving threshold rho = 1 (MIRK/adaptivity.jl:23-75)
+    k_mesh_select<<<1, 1024, use_smem ? smem_needed : 0>>>(pconv + 1, 1.0, N, d_mesh, d_est, nullptr, abstol, max_num_subintervals, cap,
+                                                           d_new, d_out, use_smem);
+    int out[2] = {N, MIRK_RET_FAILURE};
+    const cudaError_t e = cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost);
+    int rc = out[1];
+    if (e != cudaSuccess) { cudaGetLastError(); cleanup(); return fail(MIRK_ERR_CUDA, std::string("mesh_select: ") + cudaGetErrorString(e)); }
+    *n_mesh_new = out[0];
+    if (rc == MIRK_RET_SUCCESS) cudaMemcpy(mesh_new, d_new, sizeof(double) * out[0], cudaMemcpyDeviceToHost);
+    cleanup();
+    return rc;
+}
+
 int mirk_solve(mirk_handle S, mirk_result* out) {
     NEED_GUESS(S);
     if (!out) return fail(MIRK_ERR_ARG, "result is NULL");

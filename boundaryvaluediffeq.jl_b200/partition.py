@@ -2,9 +2,14 @@
 
 No counterpart in the reference (its hot path is one thread); SURVEY.md §8(e) defines it.  Residual,
 Jacobian blocks and the block cyclic reduction are local to a segment; per Newton step the ranks
-exchange one small reduced interface relation (NCCL all-gather inside libmirkb200, on the solver's
-stream) and an 8-byte all-reduce of |F|_inf.  torch.distributed is used here only to hand the NCCL
-unique id to every rank and to gather solutions for the caller.
+exchange one small reduced interface relation (peer-memory pushes over NVLink, or an NCCL all-gather inside
+libmirkb200 on the solver's stream) and max-reduce three words.  torch.distributed is used here only to hand the
+IPC handles / the NCCL unique id to every rank and to gather small host arrays for the caller.
+
+`init_partitioned` gives the collective handle on a FIXED mesh; `solve_partitioned` runs the reference's adaptive outer
+loop (DefectControl; MIRK/src/mirk.jl:286-388) around it: the defect estimate and the re-interpolation are local to a
+segment, the mesh selector runs on the gathered per-interval estimates (mirk_mesh_select: the same kernel the
+single-GPU driver uses), and every new mesh is re-partitioned into equal segments.
 """
 from __future__ import annotations
 
@@ -125,3 +130,124 @@ def gather_solution(cache: MIRKCache, n_nodes: int, group=None) -> np.ndarray:
     for (lo, hi), o in reversed(list(zip(parts, outs))):
         full[lo:hi + 1] = o.cpu().numpy()[:hi - lo + 1]
     return full
+
+
+class PartitionedSolution:
+    """What solve_partitioned returns on every rank: sol.t, sol.u (N, n), sol.retcode, the per-outer-iteration
+    histories mirk_result carries (hist_n_mesh, hist_newton, hist_defect) and the last norms."""
+
+    def __init__(self, t, u, retcode, hist_n_mesh, hist_newton, hist_defect, resid_norm, defect_norm):
+        self.t, self.u, self.retcode = t, u, retcode
+        self.hist_n_mesh, self.hist_newton, self.hist_defect = hist_n_mesh, hist_newton, hist_defect
+        self.resid_norm, self.defect_norm = resid_norm, defect_norm
+
+
+def _allgather_obj(obj, group=None):
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def mesh_select(order: int, abstol: float, max_num_subintervals: int, mesh, est, device: int = 0):
+    """mesh_selector! on a (global) mesh and its per-interval error estimates: (retcode, new mesh or None)."""
+    mesh, est = _arr(mesh), _arr(est)
+    out = np.zeros(max(len(mesh), int(max_num_subintervals) + 1))
+    nn = C.c_int32(0)
+    rc = B.check(B.lib().mirk_mesh_select(int(order), float(abstol), int(max_num_subintervals), len(mesh),
+                                          mesh.ctypes.data_as(B.dp), est.ctypes.data_as(B.dp), C.byref(nn),
+                                          out.ctypes.data_as(B.dp), int(device)))
+    return rc, (out[:nn.value].copy() if rc == 0 else None)
+
+
+def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abstol: float = 1e-6, adaptive: bool = True,
+                      defect_threshold: float = 0.1, group=None, device: Optional[int] = None,
+                      exchange: Optional[str] = None, max_outer: int = 1000, **kw) -> PartitionedSolution:
+    """Collective.  `solve(prob, alg; dt, abstol, adaptive)` of a TwoPointBVProblem whose mesh is partitioned over the
+    ranks of `group`: the outer loop of `solve!` with DefectControl (MIRK/src/mirk.jl:286-388; same order of
+    operations as mirk_solve in csrc/mirk_b200.cu).  Every rank passes the same problem and gets the same result."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    t0, t1 = float(prob.tspan[0]), float(prob.tspan[1])
+    if prob.mesh is not None:
+        mesh, y = _arr(prob.mesh).copy(), _arr(prob.u0).copy()
+    else:
+        if not dt > 0.0:
+            raise ValueError("dt must be positive")
+        from .api import mesh_uniform
+        mesh = mesh_uniform(t0, t1, int(np.ceil((t1 - t0) / dt)))
+        y = np.tile(_arr(prob.u0).reshape(1, -1), (len(mesh), 1))
+    max_sub = int(alg.max_num_subintervals)
+    cache = None
+    hist_n, hist_it, hist_d = [], [], []
+    info, err_norm, resid_norm = 0, 2.0 * abstol, float("nan")
+    try:
+        while True:
+            N = len(mesh)
+            lo, hi = partition_mesh(N, world)[rank]
+            if cache is None:
+                full = BVProblem(prob.f, y, (t0, t1), p=prob.p, mesh=mesh)
+                cache, _ = init_partitioned(full, alg, group=group, device=device, exchange=exchange, abstol=abstol, **kw)
+            else:
+                ms, ys = np.ascontiguousarray(mesh[lo:hi + 1]), np.ascontiguousarray(y[lo:hi + 1])
+                B.check(B.lib().mirk_set_mesh_guess(cache._h, hi - lo + 1, ms.ctypes.data_as(B.dp), ys.ctypes.data_as(B.dp)))
+            info, iters, resid_norm = cache.newton_solve()
+            solved_mesh = mesh
+            err_norm = 2.0 * abstol
+            hist_n.append(N); hist_it.append(iters); hist_d.append(float("nan"))
+            if not adaptive or len(hist_n) >= max_outer:
+                break
+            if info == 0:
+                d_loc, errs = cache.defect()
+                est_loc = np.max(np.abs(errs), axis=1) if errs.size else np.zeros(0)
+                parts = _allgather_obj((float(d_loc), est_loc), group)
+                # NaN-propagating maximum, as the device reduction
+                ds = [d for d, _ in parts]
+                err_norm = float("nan") if any(d != d for d in ds) else max(ds)
+                est = np.concatenate([e for _, e in parts])
+                if not (err_norm <= defect_threshold):
+                    info = 1
+                hist_d[-1] = err_norm
+                if info == 0 and err_norm > abstol:
+                    rc, mesh_new = mesh_select(alg.order, abstol, max_sub, mesh, est, device)
+                    if rc != 0:
+                        info = rc
+                        break
+                    # new guess = old interpolant at the new nodes; node t belongs to the rank whose segment holds the
+                    # interval searchsortedfirst(mesh, t) - 1 (CORE/utils.jl:119-121): (mesh[lo], mesh[hi]], t0 to rank 0
+                    mine = (mesh_new > mesh[lo]) & (mesh_new <= mesh[hi])
+                    if rank == 0:
+                        mine |= mesh_new <= mesh[lo]
+                    if rank == world - 1:
+                        mine |= mesh_new > mesh[hi]
+                    idx = np.nonzero(mine)[0]
+                    ts = np.ascontiguousarray(mesh_new[idx])
+                    vals = np.zeros((len(ts), cache.n))
+                    if len(ts):
+                        B.check(B.lib().mirk_interp(cache._h, ts.ctypes.data_as(B.dp), len(ts), 0, vals.ctypes.data_as(B.dp)))
+                    y_new = np.zeros((len(mesh_new), cache.n))
+                    for ii, vv in _allgather_obj((idx, vals), group):
+                        y_new[ii] = vv
+                    mesh, y = mesh_new, y_new
+                    continue
+            if info != 0:
+                if 2 * (N - 1) > max_sub:
+                    info = 1
+                    break
+                half = np.empty(2 * N - 1)
+                half[0::2] = mesh
+                half[1::2] = (mesh[1:] + mesh[:-1]) / 2.0
+                mesh, y = half, np.zeros((2 * N - 1, cache.n))   # halve-and-zero restart (quirk Q4)
+                info = 0
+            if not (info == 0 and err_norm > abstol):
+                break
+        if info == 0 and adaptive and err_norm > abstol:
+            info = 2  # MaxIters (the safety net of the outer loop)
+        u = gather_solution(cache, len(solved_mesh), group)
+        return PartitionedSolution(solved_mesh, u, info, hist_n, hist_it, hist_d, resid_norm, err_norm)
+    finally:
+        if cache is not None:
+            dist.barrier(group=group)  # nobody frees its exchange buffer while a peer may still push into it
+            cache.close()

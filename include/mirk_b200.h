@@ -147,6 +147,14 @@ int mirk_defect(mirk_handle h, double* errors, double* defect_norm);
  * returns MIRK_RET_SUCCESS / MIRK_RET_FAILURE and the new node count */
 int mirk_refine_mesh(mirk_handle h, int32_t* n_mesh_new);
 
+/* mesh_selector! + redistribute! / half_mesh! of DefectControl (MIRK/adaptivity.jl:23-75,250-304) as a function of a mesh and
+ * its per-interval error estimates est[n_mesh - 1] = |errors[i]|_inf (host arrays): what the mesh-partitioned mode runs on
+ * the estimates gathered from every rank (partition.solve_partitioned).  mesh_new must hold
+ * max(n_mesh, max_num_subintervals + 1) entries.  Returns MIRK_RET_SUCCESS and *n_mesh_new, or MIRK_RET_FAILURE when the
+ * new mesh would exceed max_num_subintervals (mesh_new untouched). */
+int mirk_mesh_select(int32_t order, double abstol, int32_t max_num_subintervals, int32_t n_mesh, const double* mesh,
+                     const double* est, int32_t* n_mesh_new, double* mesh_new, int32_t device);
+
 /* -- SciMLBase.solve!(cache) (MIRK/mirk.jl:286-388) ---------------------------------------------- */
 int mirk_solve(mirk_handle h, mirk_result* result);
 
@@ -171,7 +179,9 @@ int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
 
 /* -- mesh-partitioned single problem (no reference counterpart: the reference is single-threaded).
  *    Every rank creates a handle on its GPU holding one contiguous mesh segment (neighbours share their
- *    boundary node) of a TwoPointBVProblem on a fixed mesh, then attaches it to a communicator.  From then
+ *    boundary node) of a TwoPointBVProblem, then attaches it to a communicator.  The handle's mesh is fixed between
+ *    mirk_set_mesh_guess calls; the adaptive outer loop runs above the ABI (partition.solve_partitioned: local defect
+ *    estimates, mirk_mesh_select on the gathered estimates, local re-interpolation, re-partitioning).  From then
  *    on mirk_residual / mirk_newton_step / mirk_newton_solve / mirk_solve / mirk_bench_newton_steps are
  *    COLLECTIVE calls: per Newton step one 8-byte all-reduce(max) of |F|_inf and one all-gather of the
  *    (2n^2 + n + 2Ln + L)-double reduced interface relation per rank, over NCCL on the solver's stream.

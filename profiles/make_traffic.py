@@ -36,6 +36,8 @@ def phase_of(name, seen_reduce, tail_seen):
         return "abd_reduce_level0" if not seen_reduce else "abd_reduce_upper"
     if "k_backsub" in name:
         return "abd_backsub"
+    if "k_seg_cluster" in name:
+        return "abd_reduce_upper"
     if "k_tail_warp" in name or "k_final" in name:
         return None  # decided by position
     return "other"
