@@ -21,8 +21,9 @@ each does identical work.
 
   value    device-resident throughput: K steps timed with CUDA events on the solver's stream (max over ranks)
   e2e      the same step through the C ABI with HOST buffers: (this rank's segment of) mesh + guess copied
-           host->device from pinned memory, one Newton step, solution copied back, every step.  Two handles on
-           two host threads keep two independent problem instances in flight so copies overlap kernels
+           host->device from pinned memory, one Newton step, solution copied back, every step.  `--e2e-handles`
+           (default 12) handles on as many host threads keep independent problem instances in flight, so copies
+           overlap kernels and the latency-bound phases of one elimination share the GPU with those of another
            (`e2e.serial_value` is the one-handle, one-thread figure).
   roofline the dominant kernel's algorithmic bytes (its share of SURVEY §8d's B = 32 n^2 N + 16 n N) / its
            CUDA-event duration against the measured HBM copy peak, plus the FP64 fraction (C2 sits at
@@ -351,7 +352,8 @@ def run_newton(args):
         handles = [(cache._h, bufs0)] + [(c._h, pinned_set()) for c in extra_caches]
         for h, b in handles[1:]:
             e2e_loop(h, b, args.warmup)
-        per = (args.steps + nh - 1) // nh
+        # at least 8 steps per handle: with fewer the start-up of the host threads is what gets timed
+        per = max(8, (args.steps + nh - 1) // nh)
         th = [threading.Thread(target=e2e_loop, args=(h, b, per)) for h, b in handles]
         barrier()
         t0 = time.perf_counter()
@@ -361,7 +363,7 @@ def run_newton(args):
             t.join()
         torch.cuda.synchronize()
         e2e_value = world * nh * per / allmax(time.perf_counter() - t0)
-        e2e_mode = (f"{nh} handles on {nh} host threads: independent problem instances in flight, so the copies of one overlap "
+        e2e_mode = (f"{nh} handles on {nh} host threads, {per} steps each: independent problem instances in flight, so the copies of one overlap "
                     "the kernels of another and the narrow upper levels of one elimination share the GPU with the wide phases of another")
         # the same handles stepping device-resident problems concurrently: aggregate Newton steps/s when several
         # independent problems are in flight (the narrow upper levels of one elimination leave most SMs idle for the
@@ -570,7 +572,7 @@ def main():
     ap.add_argument("--ensemble-scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--c5-nint", type=int, default=1999999)
     ap.add_argument("--c4-nint", type=int, default=3999)
-    ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles / host threads of the end-to-end leg")
+    ap.add_argument("--e2e-handles", type=int, default=12, help="independent handles / host threads of the end-to-end leg")
     ap.add_argument("--extra-timeout", type=float, default=300.0)
     ap.add_argument("--profile", action="store_true", help="device-timed steps only (for ncu runs; prints no bench line)")
     args = ap.parse_args()
