@@ -348,6 +348,10 @@ def run_newton(args):
     #  communicators would need a global launch order, so that flavour keeps the serial figure)
     if world == 1 or getattr(cache, "exchange", None) == "p2p":
         nh = max(2, args.e2e_handles)
+        if world > 1:
+            # partitioned handles spin on their peers inside kernels: more concurrent streams than hardware queues
+            # (CUDA_DEVICE_MAX_CONNECTIONS = 8) would put one handle's push behind another handle's wait
+            nh = min(nh, 4)
         extra_caches = [_make_cache(M, partition, cfg, world, local, args)[0] for _ in range(nh - 1)]
         handles = [(cache._h, bufs0)] + [(c._h, pinned_set()) for c in extra_caches]
         for h, b in handles[1:]:
