@@ -365,6 +365,9 @@ k_seg_cluster16(const TailArgs a) {
     unsigned carried = 0x0000ffffu;
     bool have = false, ok = true;
     SEG_STAMP(0);
+    // A CTA's shared memory may only be written remotely once that CTA runs: every CTA arrives at the cluster barrier
+    // now and waits for it behind its first-level merge (split barrier: the wait is free by then)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     {
         if (leaf < a.G[0]) {
             const int k0 = a.gs[0][leaf], k1 = a.gs[0][leaf + 1];
@@ -379,6 +382,7 @@ k_seg_cluster16(const TailArgs a) {
             }
             have = true;
         }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         SEG_STAMP(1);
         for (int t = 1; t < a.nlev; t++) {
             const int half = 1 << (t - 1);
