@@ -225,6 +225,34 @@ def test_defect_and_mesh_selection_match_oracle(M, oracle):
     cache.close()
 
 
+def test_standalone_mesh_selector_matches_the_oracle_and_the_handle(M, oracle):
+    """mirk_mesh_select (the mesh selector on caller-given estimates: what the mesh-partitioned mode runs on the gathered
+    per-interval estimates) against the oracle's mesh_selector! restatement and against mirk_refine_mesh on the same
+    data; and its failure path (new mesh beyond max_num_subintervals)."""
+    from boundaryvaluediffeq_jl_b200 import partition
+    O = oracle
+    P = O.builtin("layer")
+    p = [0.01]
+    mesh = O.mesh_uniform(-1.0, 1.0, 40)
+    ws = O.Workspace(P, 4, p, mesh, np.zeros((41, 2)))
+    assert ws.newton()[0] == 0
+    _, err_ref = ws.defect()
+    info_ref, mesh_ref = O.mesh_select(4, mesh, err_ref)
+    cache = M.init(M.BVProblem("layer", np.zeros((41, 2)), (-1.0, 1.0), p=p), M.MIRK4())
+    assert cache.newton_solve()[0] == 0
+    _, err = cache.defect()
+    est = np.max(np.abs(err), axis=1)
+    rc, mesh_new = partition.mesh_select(4, 1e-6, 3000, mesh, est)
+    assert rc == info_ref == 0 and len(mesh_new) == len(mesh_ref)
+    assert _rel(mesh_new, mesh_ref) < 1e-9
+    info, Nn = cache.refine_mesh()
+    t, _ = cache.solution()
+    assert info == 0 and Nn == len(mesh_new) and np.array_equal(t, mesh_new)   # the same kernel on the same numbers
+    cache.close()
+    rc, none = partition.mesh_select(4, 1e-6, len(mesh_ref) - 2, mesh, est)
+    assert rc == 1 and none is None
+
+
 def test_reinterp_inplace_quirk_Q3_matches_oracle(M, oracle):
     O = oracle
     args = ("layer", 4, [0.01], [0.0, 0.0], (-1.0, 1.0), 0.05)
