@@ -327,6 +327,27 @@ def test_headline_config_newton_properties_at_full_size(M):
     cache.close()
 
 
+@pytest.mark.parametrize("nint", [130, 297, 700, 1531, 2500, 5003, 9001])
+def test_n16_reduction_shapes_satisfy_the_block_equations(M, nint):
+    """The n = 16 reduction over many mesh sizes — i.e. many shapes of the tree above level 0: one-SM segments, cluster
+    segments (k_seg_cluster16) with full and partly filled clusters, lone relations at the end of a level, tails of 1-3
+    levels.  Size-independent check: the update satisfies every block row L_i d_i + R_i d_{i+1} = Phi_i and the boundary
+    rows, and it does not depend on the kernel choice (MIRK_CLUSTER_TREE is read once per process, so the comparison is
+    against the block equations, not against a second build)."""
+    from boundaryvaluediffeq_jl_b200 import configs
+    c = configs.c2_chain8(nint)
+    cache = M.init(M.BVProblem(c.problem, c.y0, c.tspan, p=c.p, mesh=c.mesh), M.MIRK6(), adaptive=False)
+    r, _ = cache.residual()
+    Lb, Rb, nodes, Bc = cache.jacobian_blocks()
+    st, d = cache.linear_solve()
+    assert st == 0
+    phi = r[8:8 + (c.N - 1) * 16].reshape(c.N - 1, 16)
+    lhs = np.einsum("ijk,ik->ij", Lb, d[:-1]) + np.einsum("ijk,ik->ij", Rb, d[1:])
+    assert np.max(np.abs(lhs - phi)) < 1e-9 * max(1.0, np.max(np.abs(phi)))
+    assert np.max(np.abs(d[0, :8] - r[:8])) < 1e-12 and np.max(np.abs(d[-1, :8] - r[-8:])) < 1e-12
+    cache.close()
+
+
 @pytest.mark.parametrize("key,maker,nint", [("c5_short", "c5_chain16", 999), ("c4_short", "c4_bratu64", 99)])
 def test_large_block_problems_match_golden(M, key, maker, nint):
     """The problems of BASELINE configs C5 (n = 32, MIRK6) and C4 (n = 128, MIRK4) on short meshes against the
