@@ -9,6 +9,11 @@
 
 namespace mirk {
 
+// functor trait (problems.cuh): does P declare `static constexpr bool bc_uses_derivative = true`?
+template <class P, class = void> struct BcUsesDerivative { static constexpr bool value = false; };
+template <class P> struct BcUsesDerivative<P, decltype((void)P::bc_uses_derivative)> { static constexpr bool value = P::bc_uses_derivative; };
+
+
 struct Dual {
     double v, d;
     __host__ __device__ __forceinline__ Dual() : v(0.0), d(0.0) {}

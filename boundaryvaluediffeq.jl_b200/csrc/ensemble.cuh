@@ -74,6 +74,7 @@ template <class P, int ORDER> struct EnsSolver {
     using TB = Tableau<ORDER>;
     using LY = EnsLayout<P, ORDER>;
     static constexpr int n = P::n, s = TB::s, si = TB::si, L = P::n_bc, rows = 2 * n, cols = 3 * n + 1;
+    static_assert(!BcUsesDerivative<P>::value, "boundary conditions on sol(t, Val{1}) are not offered by the ensemble kernels");
     static constexpr int QMAX = P::max_bc_pts + 2, DMAX = QMAX * n;
     static constexpr int UF = ens_unroll(P::n);
 

@@ -80,6 +80,7 @@ template <class P, int ORDER> struct EnsWarpSolver {
                          DMAX = LY::DMAX, ND = 2 * n, rows = 2 * n, cols = 3 * n + 1, LV = 5;
     using MD = DualN<ND>;
     static_assert(QMAX + 2 + P::max_bc_pts <= 16, "the integer scratch of a warp holds 16 entries");
+    static_assert(!BcUsesDerivative<P>::value, "boundary conditions on sol(t, Val{1}) are not offered by the ensemble kernels");
 
     // shared-memory views of this warp
     double *mesh, *mesh2, *y, *y2, *Kd, *phi, *est, *scr, *M;

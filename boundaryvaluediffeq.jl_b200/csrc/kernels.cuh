@@ -190,7 +190,10 @@ k_bc(int N, const double* __restrict__ mesh, const double* __restrict__ y,
      int* __restrict__ m_out, unsigned long long* __restrict__ norm_bits, int want_jac) {
     using TB = Tableau<ORDER>;
     constexpr int n = P::n, L = P::n_bc;
-    __shared__ double U[P::max_bc_pts * n];
+    // functors that read sol(t, Val{1}) get dU[k] = sol'(times[k]) behind U (problems.cuh: bc_uses_derivative)
+    constexpr bool kDeriv = BcUsesDerivative<P>::value;
+    constexpr int UW = kDeriv ? 2 : 1;
+    __shared__ double U[UW * P::max_bc_pts * n];
     __shared__ int s_m;
     if (threadIdx.x == 0) {
         double tm[P::max_bc_pts];
@@ -225,6 +228,29 @@ k_bc(int N, const double* __restrict__ mesh, const double* __restrict__ y,
                 }
             }
         }
+        if (kDeriv) {
+            // sol(t, Val{1}) of EvalSol (MIRK/src/interpolation.jl:277-292): no end-point short cut; interval(t), the
+            // derivative weights on the discrete and interpolation stages of that interval (plain Float64: a constant
+            // of the boundary Jacobian below)
+            for (int k = 0; k < m; k++) {
+                const double t = tm[k];
+                const int i = interval_of(mesh, N, t);
+                const double ti = mesh[i], h = mesh[i + 1] - ti, tau = (t - ti) / h;
+                double yi[n], yi1[n];
+                for (int c = 0; c < n; c++) { yi[c] = y[(size_t)i * n + c]; yi1[c] = y[(size_t)(i + 1) * n + c]; }
+                const double* K = Kd + (size_t)i * TB::s * n;
+                double* KI = Ki + (size_t)i * TB::si * n;
+                interp_stages_interval<P, ORDER>(yi, yi1, h, ti, p, K, KI);
+                double w[TB::s_star], wp[TB::s_star];
+                TB::weights(tau, w, wp);
+                for (int c = 0; c < n; c++) {
+                    double z = 0.0;
+                    for (int r = 0; r < TB::s; r++) z += K[r * n + c] * wp[r];
+                    for (int r = 0; r < TB::si; r++) z += KI[r * n + c] * wp[TB::s + r];
+                    U[(m + k) * n + c] = z;
+                }
+            }
+        }
         *m_out = m;
     }
     __syncthreads();
@@ -232,8 +258,8 @@ k_bc(int N, const double* __restrict__ mesh, const double* __restrict__ y,
     const int La = P::problem_type == 1 ? P::n_bca : L;
     const size_t tail_off = (size_t)La + (size_t)(N - 1) * n;   // two-point: bc_b rows go last
     if (threadIdx.x == 0) {
-        double Uv[P::max_bc_pts * n], r[L];
-        for (int e = 0; e < m * n; e++) Uv[e] = U[e];
+        double Uv[UW * P::max_bc_pts * n], r[L];
+        for (int e = 0; e < UW * m * n; e++) Uv[e] = U[e];
         P::template bc<double>(r, Uv, p);
         unsigned long long mb = 0ull;
         for (int q = 0; q < L; q++) {
@@ -245,8 +271,8 @@ k_bc(int N, const double* __restrict__ mesh, const double* __restrict__ y,
     }
     if (want_jac) {
         for (int d = threadIdx.x; d < m * n; d += blockDim.x) {
-            Dual Ud[P::max_bc_pts * n], r[L];
-            for (int e = 0; e < m * n; e++) Ud[e] = Dual(U[e], e == d ? 1.0 : 0.0);
+            Dual Ud[UW * P::max_bc_pts * n], r[L];
+            for (int e = 0; e < UW * m * n; e++) Ud[e] = Dual(U[e], e == d ? 1.0 : 0.0);
             P::template bc<Dual>(r, Ud, p);
             const int k = d / n, c = d % n;
             for (int q = 0; q < L; q++) Bc[((size_t)k * L + q) * n + c] = r[q].d;

@@ -53,7 +53,7 @@ static int fail(int code, const std::string& msg) {
 // ---- registry -----------------------------------------------------------------------------------
 static const char* kBuiltinNames[problems::kNumBuiltin] = {
     "pendulum", "linear2", "linear2_tp", "swirling", "lotka", "torus", "layer", "chain8", "chain16",
-    "bratu64", "lane_emden"};
+    "bratu64", "lane_emden", "robin_sine"};
 
 struct Plugin {
     std::string name;
@@ -66,6 +66,7 @@ static const int kPluginBase = 1000;
 
 static const ProblemOps* find_ops(int id, int order) {
     using namespace problems;
+    if (id == kRobinSine) return (order == 4 || order == 6) ? ops_small(id, order) : nullptr;
     if ((id >= 0 && id <= kLayer) || id == kLaneEmden)
         return (order == 4 || order == 6) ? ops_small(id, order) : order == kMIRK6I ? ops_small_6i(id, order) : ops_small_235(id, order);
     if (id == kChain8) return ops_chain8(order);

@@ -1,4 +1,4 @@
-// built-in problems with n <= 6 (ids 0..6), MIRK4 and MIRK6
+// built-in problems with n <= 6 (ids 0..6, 10, 11), MIRK4 and MIRK6
 #include "ops.cuh"
 namespace mirk {
 using namespace problems;
@@ -16,6 +16,7 @@ const ProblemOps* ops_small(int id, int order) {
     case kTorus: OPS2(Torus, "torus")
     case kLayer: OPS2(Layer, "layer")
     case kLaneEmden: OPS2(LaneEmden, "lane_emden")
+    case kRobinSine: OPS2(RobinSine, "robin_sine")
     default: return nullptr;
     }
 }

@@ -9,6 +9,9 @@
 //     template<class T> static void bc(T* res, const T* U /* m×n */, const double* p)
 //   optional (singular BVPs, prob.singular_term):  static constexpr bool has_singular_term = true;
 //     template<class T> static void singular(T* out, const T* u, const double* p)     out = S u
+//   optional (bc! reads sol(t, Val{1}), MIRK/src/interpolation.jl:277-292):  static constexpr bool bc_uses_derivative = true;
+//     U[k] (m x n) is then followed by dU[k] = sol'(times[k]) (m x n more entries: U[m*n + k*n + c]).  As in the
+//     reference the derivative is built from the Float64 stage buffers: it is a constant of the boundary Jacobian
 // `T` is double for residuals; for Jacobians it is mirk::Dual (plain forward mode) or the pair mirk::RecVal /
 // mirk::TapeDual of the taped kernel (tape.cuh) — one templated source serves all, like ForwardDiff on the
 // Julia side.  Write elementary functions unqualified after `using namespace mirk::fn;` (sin, cos, exp, log,
@@ -221,10 +224,31 @@ struct LaneEmden {
         r[1] = U[2] - 0.84147098480789650665;  // sin(1)
     }
 };
+// 11: u'' = -u with a boundary condition on the DERIVATIVE of the interpolant (sol(t, Val{1}) inside bc!,
+//     MIRK/src/interpolation.jl:277-292; the reference's tests reach it through maxsol / minsol, mirk_basic_tests.jl:453-479):
+//     u1(t0) = 0,  u1(t1) - 1 + alpha (u1'(tm) - c) = 0,  tm = (t0 + t1) / 2;  p = [alpha, c].
+//     On [0, pi/2] with c = cos(pi/4) the solution is (sin t, cos t).
+struct RobinSine {
+    static constexpr int n = 2, np = 2, n_bc = 2, n_bca = 0, problem_type = 0, max_bc_pts = 3;
+    static constexpr bool bc_uses_derivative = true;
+    MIRK_PF f(T* du, const T* u, const double*, double) {
+        du[0] = u[1];
+        du[1] = -u[0];
+    }
+    MIRK_PT bc_times(double* tm, const double*, double t0, double t1) {
+        tm[0] = t0; tm[1] = (t0 + t1) / 2; tm[2] = t1; return 3;
+    }
+    MIRK_PF bc(T* r, const T* U, const double* p) {
+        const T* dU = U + 3 * n;
+        r[0] = U[0];
+        r[1] = U[4] - 1.0 + p[0] * (dU[2] - p[1]);
+    }
+};
+
 
 enum BuiltinId {
     kPendulum = 0, kLinear2 = 1, kLinear2TP = 2, kSwirling = 3, kLotka = 4, kTorus = 5, kLayer = 6,
-    kChain8 = 7, kChain16 = 8, kBratu64 = 9, kLaneEmden = 10, kNumBuiltin = 11
+    kChain8 = 7, kChain16 = 8, kBratu64 = 9, kLaneEmden = 10, kRobinSine = 11, kNumBuiltin = 12
 };
 
 }  // namespace problems

@@ -394,6 +394,10 @@ static int bc_gather(const orc_problem *P, const orc_tableau *T, const double *p
     }
     const int m = P->bc_times(times, p, mesh[0], mesh[N - 1], P->ctx);
     for (int k = 0; k < m; k++) orc_eval_sol(P, T, N, mesh, y, Kd, Ki, times[k], 0, 1, U + k * n);
+    /* sol(t, Val{1}) inside bc! (interpolation.jl:277-292): no end-point short cut, interval(t) and the derivative
+     * weights on the stage buffers of that interval */
+    if (P->bc_uses_derivative)
+        for (int k = 0; k < m; k++) orc_eval_sol(P, T, N, mesh, y, Kd, Ki, times[k], 1, 0, U + (size_t)(m + k) * n);
     return m;
 }
 
@@ -404,7 +408,7 @@ void orc_loss(const orc_problem *P, const orc_tableau *T, const double *p, int N
               const double *y, double *Kd, double *Ki, double *resid) {
     const int n = P->n, L = P->n_bc;
     double times[ORC_MAX_BC_PTS];
-    double *U = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * n);
+    double *U = (double *)malloc(sizeof(double) * 2 * ORC_MAX_BC_PTS * n);
     double *bc = (double *)malloc(sizeof(double) * L);
     if (P->problem_type == 0) {
         orc_phi(P, T, p, N, mesh, y, Kd, resid + L);
@@ -501,7 +505,7 @@ int orc_bc_jac(const orc_problem *P, const orc_tableau *T, const double *p, int 
                const double *y, const double *Kd, const double *Ki, int *nodes, double *B) {
     const int n = P->n, L = P->n_bc;
     double times[ORC_MAX_BC_PTS];
-    double *U = (double *)malloc(sizeof(double) * ORC_MAX_BC_PTS * n);
+    double *U = (double *)malloc(sizeof(double) * 2 * ORC_MAX_BC_PTS * n);
     const int m = bc_gather(P, T, p, N, mesh, y, Kd, Ki, times, U);
     double *d = (double *)malloc(sizeof(double) * L * m * n);
     P->dbc(d, U, p, P->ctx);

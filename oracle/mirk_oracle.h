@@ -56,6 +56,9 @@ typedef struct {
     void *ctx;
     const double *singular_term; /* prob.singular_term: n×n row-major S of y' = S y / t + f(t, y), or NULL
                                     (CORE/src/utils.jl:932-941; added to the discrete stages with t > 0 only) */
+    int bc_uses_derivative;      /* bc! also reads sol(t, Val{1}) (MIRK/src/interpolation.jl:277-292): U[k] (m×n) is then
+                                    followed by dU[k] = sol'(times[k]) (m×n more doubles).  The derivative is built from the
+                                    Float64 stage buffers, so it carries no dual part: dbc stays L × (m*n), d/dU only */
 } orc_problem;
 
 typedef struct {

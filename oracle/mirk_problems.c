@@ -20,6 +20,8 @@
  *   8 chain16       SURVEY.md §8d C5: 16 pendula, n=32
  *   9 bratu64       SURVEY.md §8d C4: 2-D Bratu by method of lines, n=128
  *  10 lane_emden    lib/BoundaryValueDiffEqMIRK/test/Core/singular_bvp_tests.jl:15-61 (singular_term S = [0 0; 0 -2])
+ *  11 robin_sine    u'' = -u with sol(t, Val{1}) inside bc! (MIRK/src/interpolation.jl:277-292; mirk_basic_tests.jl:453-479 uses
+ *                   the derivative through maxsol / minsol)
  */
 #include "mirk_oracle.h"
 
@@ -327,10 +329,32 @@ static void lane_dbc(double *d, const double *U, const double *p, void *c) {
 }
 static const double LANE_S[4] = {0.0, 0.0, 0.0, -2.0};
 
-static const char *NAMES[] = {"pendulum", "linear2", "linear2_tp", "swirling", "lotka",
-                              "torus", "layer", "chain8", "chain16", "bratu64", "lane_emden"};
+/* ---- 11: u'' = -u with a boundary condition that reads the DERIVATIVE of the interpolant (sol(t, Val{1}) inside bc!,
+ *      MIRK/src/interpolation.jl:277-292):  u1(t0) = 0,  u1(t1) - 1 + alpha (u1'(tm) - c) = 0,  tm = (t0 + t1) / 2;
+ *      p = [alpha, c].  On [0, pi/2] with c = cos(pi/4) the solution is (sin t, cos t).  The derivative comes from the
+ *      Float64 stage buffers: it contributes nothing to the boundary Jacobian (Newton converges linearly in that row). */
+static int robin_times(double *tm, const double *p, double t0, double t1, void *c) {
+    (void)p; (void)c;
+    tm[0] = t0; tm[1] = (t0 + t1) / 2; tm[2] = t1;
+    return 3;
+}
+static void robin_bc(double *r, const double *U, const double *p, void *c) {
+    (void)c;
+    const double *dU = U + 3 * 2;
+    r[0] = U[0];
+    r[1] = U[4] - 1.0 + p[0] * (dU[2] - p[1]);
+}
+static void robin_dbc(double *d, const double *U, const double *p, void *c) {
+    (void)U; (void)p; (void)c;
+    memset(d, 0, sizeof(double) * 2 * 6);
+    d[0 * 6 + 0] = 1.0;
+    d[1 * 6 + 4] = 1.0;
+}
 
-const char *orc_builtin_name(int id) { return (id >= 0 && id < 11) ? NAMES[id] : 0; }
+static const char *NAMES[] = {"pendulum", "linear2", "linear2_tp", "swirling", "lotka",
+                              "torus", "layer", "chain8", "chain16", "bratu64", "lane_emden", "robin_sine"};
+
+const char *orc_builtin_name(int id) { return (id >= 0 && id < 12) ? NAMES[id] : 0; }
 
 int orc_builtin_problem(int id, orc_problem *P) {
     memset(P, 0, sizeof(*P));
@@ -348,6 +372,10 @@ int orc_builtin_problem(int id, orc_problem *P) {
     case 10:
         *P = (orc_problem){2, 0, 1, 2, 1, lane_f, lane_df, ends_times, lane_bc, lane_dbc, 0};
         P->singular_term = LANE_S;
+        break;
+    case 11:
+        *P = (orc_problem){2, 2, 0, 2, 0, lane_f, lane_df, robin_times, robin_bc, robin_dbc, 0};
+        P->bc_uses_derivative = 1;
         break;
     default: return -1;
     }

@@ -30,7 +30,8 @@ SUCCESS, FAILURE, MAXITERS, UNSTABLE, STALLED = 0, 1, 2, 3, 4
 class Problem(C.Structure):
     _fields_ = [("n", C.c_int), ("n_p", C.c_int), ("problem_type", C.c_int), ("n_bc", C.c_int),
                 ("n_bca", C.c_int), ("f", RHS_FN), ("dfdu", JAC_FN), ("bc_times", TIMES_FN),
-                ("bc", BC_FN), ("dbc", BCJ_FN), ("ctx", C.c_void_p), ("singular_term", dp)]
+                ("bc", BC_FN), ("dbc", BCJ_FN), ("ctx", C.c_void_p), ("singular_term", dp),
+                ("bc_uses_derivative", C.c_int)]
 
 
 class Tableau(C.Structure):
@@ -118,7 +119,7 @@ def _arr(x):
 
 
 PROBLEM_IDS = {"pendulum": 0, "linear2": 1, "linear2_tp": 2, "swirling": 3, "lotka": 4,
-               "torus": 5, "layer": 6, "chain8": 7, "chain16": 8, "bratu64": 9, "lane_emden": 10}
+               "torus": 5, "layer": 6, "chain8": 7, "chain16": 8, "bratu64": 9, "lane_emden": 10, "robin_sine": 11}
 
 
 def builtin(name_or_id) -> Problem:

@@ -62,6 +62,9 @@ CASES = [
     ("pendulum", 2, [9.81], PENDULUM_T, 32), ("pendulum", 3, [9.81], PENDULUM_T, 32), ("pendulum", 5, [9.81], PENDULUM_T, 32),
     ("swirling", 5, [0.01], (0.0, 1.0), 31), ("torus", 3, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 20),
     ("linear2_tp", 2, [1.0, 5.0, 0.0], (0.0, 5.0), 17),
+    # a boundary condition that reads sol(t, Val{1}) (interpolation.jl:277-292): the derivative of the interpolant at an
+    # interior time enters the residual and, as in the reference, not the boundary Jacobian
+    ("robin_sine", 4, [0.1, math.cos(math.pi / 4)], (0.0, math.pi / 2), 21), ("robin_sine", 6, [0.3, 0.5], (0.0, math.pi / 2), 16),
 ]
 
 
@@ -170,6 +173,10 @@ SOLVES = [
     ("linear2_tp", 2, [1.0, 5.0, 0.0], [5.0, -3.5], (0.0, 5.0), 0.2, {"abstol": 1e-4}),
     ("swirling", 5, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),
     ("torus", 5, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05, {"tol": 1e-9}),  # 2e-10 measured
+    # sol(t, Val{1}) inside bc!: u'' = -u, u(0) = 0, u(pi/2) - 1 + alpha (u'(pi/4) - cos(pi/4)) = 0 -> (sin t, cos t);
+    # the derivative row has no Jacobian (reference semantics), so Newton converges linearly: 5 steps
+    ("robin_sine", 4, [0.1, math.cos(math.pi / 4)], [0.0, 1.0], (0.0, math.pi / 2), 0.05, {}),
+    ("robin_sine", 6, [0.1, math.cos(math.pi / 4)], [0.0, 1.0], (0.0, math.pi / 2), 0.1, {}),
 ]
 
 

@@ -563,3 +563,22 @@ def test_singular_term_lane_emden(oracle):
         ym[k] -= eps
         Jfd[:, k] = (O.Workspace(P, 4, [], mesh, yp.reshape(y.shape)).loss() - O.Workspace(P, 4, [], mesh, ym.reshape(y.shape)).loss()) / (2 * eps)
     assert np.max(np.abs(J - Jfd)) < 1e-6 * max(1.0, np.max(np.abs(J)))
+
+
+def test_derivative_boundary_condition_known_answer(oracle):
+    """bc! reading sol(t, Val{1}) (MIRK/src/interpolation.jl:277-292): u'' = -u, u(0) = 0,
+    u(pi/2) - 1 + alpha (u'(pi/4) - cos(pi/4)) = 0 has the solution (sin t, cos t) for every alpha.  The derivative is
+    built from the Float64 stage buffers, so the boundary Jacobian ignores it and Newton converges linearly in that row
+    (rate ~ alpha): more steps than the 1 a linear problem needs, and a final error set by abstol, not by the mesh."""
+    import math
+    O = oracle
+    P = O.builtin("robin_sine")
+    for order, dt in ((4, 0.05), (6, 0.1)):
+        ref = O.solve_dt(P, order, [0.1, math.cos(math.pi / 4)], [0.0, 1.0], (0.0, math.pi / 2), dt)
+        assert ref.retcode == 0 and ref.hist_newton[0] > 2
+        t, u = np.asarray(ref.t), np.asarray(ref.u)
+        assert np.max(np.abs(u[:, 0] - np.sin(t))) < 5e-6 and np.max(np.abs(u[:, 1] - np.cos(t))) < 5e-6
+        # with alpha = 0 the condition is the plain Dirichlet one: one Newton step, discretisation-level error
+        ref0 = O.solve_dt(P, order, [0.0, 0.0], [0.0, 1.0], (0.0, math.pi / 2), dt)
+        assert ref0.retcode == 0 and ref0.hist_newton[0] == 1
+        assert np.max(np.abs(np.asarray(ref0.u)[:, 0] - np.sin(np.asarray(ref0.t)))) < 1e-7
