@@ -273,7 +273,9 @@ __global__ void k_part_pack(int n, int L, int La, const double* __restrict__ rel
 }
 // gathered payloads -> contiguous relation arrays of the interface system + its boundary blocks:
 // block 0 (node 0) = rank 0's bc_a rows, block 1 (node G) = rank G-1's bc_b rows; if_resid = [bc_a ; bc_b]
-__global__ void k_part_unpack(int n, int G, int L, int La, const double* __restrict__ recv, double* __restrict__ oL,
+// (standard != 0: a Standard problem, whose boundary rows couple both outer ends — every rank evaluated them on the
+//  exchanged end states, so both blocks and all rows come from rank 0's payload)
+__global__ void k_part_unpack(int n, int G, int L, int La, int standard, const double* __restrict__ recv, double* __restrict__ oL,
                               double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
                               double* __restrict__ oresid) {
     const int nn = n * n, tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
@@ -289,7 +291,7 @@ __global__ void k_part_unpack(int n, int G, int L, int La, const double* __restr
     for (int e = tid; e < L * n; e += T) {
         const int q = e / n;
         oBc[e] = q < La ? b0[e] : 0.0;                        // block 0: Bc[0][q][c]
-        oBc[L * n + e] = q < La ? 0.0 : bG[L * n + e];        // block 1: Bc[1][q][c]
+        oBc[L * n + e] = standard ? b0[L * n + e] : (q < La ? 0.0 : bG[L * n + e]);  // block 1: Bc[1][q][c]
     }
     for (int q = tid; q < L; q += T) oresid[q] = q < La ? b0[2 * L * n + q] : bG[2 * L * n + q];
 }
@@ -306,10 +308,13 @@ constexpr int kMaxPeers = 16;
 struct XchgLayout {
     int G;
     size_t P;
+    int n;  // states: sizes the two "ghost" slots [t, y(t)] of the outer ends (Standard problems: bc couples both ends)
     __host__ __device__ size_t off_nslot() const { return (size_t)2 * G * P; }
     __host__ __device__ size_t off_pflag() const { return off_nslot() + (size_t)2 * G * 4; }
     __host__ __device__ size_t off_nflag() const { return off_pflag() + (size_t)2 * G; }
-    __host__ __device__ size_t total() const { return off_nflag() + (size_t)2 * G; }
+    __host__ __device__ size_t off_gslot() const { return off_nflag() + (size_t)2 * G; }          // [parity][end][1 + n]
+    __host__ __device__ size_t off_gflag() const { return off_gslot() + (size_t)2 * 2 * (n + 1); }  // [parity][end]
+    __host__ __device__ size_t total() const { return off_gflag() + (size_t)2 * 2; }
 };
 struct XchgPeers {
     double* buf[kMaxPeers];
@@ -367,7 +372,7 @@ k_part_push(int n, int L, int La, const double* __restrict__ relL, const double*
 }
 // wait for every rank's relation of this epoch, then unpack into the interface system (as k_part_unpack)
 // (body: one whole block, any size >= G threads)
-__device__ __forceinline__ void part_wait_unpack_body(int n, int L, int La, double* __restrict__ xbuf, const XchgLayout& lay,
+__device__ __forceinline__ void part_wait_unpack_body(int n, int L, int La, int standard, double* __restrict__ xbuf, const XchgLayout& lay,
                                                       double* __restrict__ oL, double* __restrict__ oR, double* __restrict__ orr,
                                                       double* __restrict__ oBc, double* __restrict__ oresid,
                                                       unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
@@ -391,17 +396,17 @@ __device__ __forceinline__ void part_wait_unpack_body(int n, int L, int La, doub
     for (int i = tid; i < L * n; i += T) {
         const int q = i / n;
         oBc[i] = q < La ? __ldcg(b0 + i) : 0.0;
-        oBc[L * n + i] = q < La ? 0.0 : __ldcg(bG + L * n + i);
+        oBc[L * n + i] = standard ? __ldcg(b0 + L * n + i) : (q < La ? 0.0 : __ldcg(bG + L * n + i));
     }
     for (int q = tid; q < L; q += T) oresid[q] = q < La ? __ldcg(b0 + 2 * L * n + q) : __ldcg(bG + 2 * L * n + q);
     __syncthreads();
     if (tid == 0) *epoch_ptr = e;
 }
 __global__ void __launch_bounds__(1024)
-k_part_wait_unpack(int n, int L, int La, double* __restrict__ xbuf, XchgLayout lay, double* __restrict__ oL,
+k_part_wait_unpack(int n, int L, int La, int standard, double* __restrict__ xbuf, XchgLayout lay, double* __restrict__ oL,
                    double* __restrict__ oR, double* __restrict__ orr, double* __restrict__ oBc,
                    double* __restrict__ oresid, unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status) {
-    part_wait_unpack_body(n, L, La, xbuf, lay, oL, oR, orr, oBc, oresid, epoch_ptr, status);
+    part_wait_unpack_body(n, L, La, standard, xbuf, lay, oL, oR, orr, oBc, oresid, epoch_ptr, status);
 }
 // all-reduce(max) of words[0..3) (|F|_inf bits, defect bits, status) over the ranks: push, wait, reduce — one warp
 // (bc_* != nullptr: the rows of the boundary conditions this rank owns are folded into words[0] first — the work of
@@ -448,6 +453,55 @@ k_words_allmax(unsigned long long* __restrict__ words, double* __restrict__ xbuf
         w0 = a > w0 ? a : w0; w1 = b > w1 ? b : w1; w2 = c > w2 ? c : w2;
     }
     if (lane == 0) { words[0] = w0; words[1] = w1; words[2] = w2; *epoch_ptr = e; }
+}
+
+// ---- Standard problems in the mesh-partitioned mode: bc!(res, sol, p, t) couples BOTH outer ends, so before every
+// boundary evaluation rank 0 hands [t_first, y(t_first)] and the last rank [t_last, y(t_last)] to everybody; each rank
+// then evaluates the boundary rows and their two blocks on that two-node "ghost" mesh (identical results everywhere).
+// Peer-memory flavour: one warp; pushes into every peer's ghost slot, waits for both slots of this epoch, copies them out.
+__global__ void __launch_bounds__(32)
+k_part_ends_bcast(int n, int N, const double* __restrict__ mesh, const double* __restrict__ y, double* __restrict__ xbuf,
+                  XchgPeers peers, XchgLayout lay, int rank, unsigned long long* __restrict__ epoch_ptr, int* __restrict__ status,
+                  double* __restrict__ gmesh, double* __restrict__ gy) {
+    const int lane = threadIdx.x, G = lay.G;
+    const unsigned long long e = *epoch_ptr + 1ull, par = e & 1ull;
+    for (int end = 0; end < 2; end++) {
+        if (rank != (end ? G - 1 : 0)) continue;
+        const int node = end ? N - 1 : 0;
+        if (lane < G) {
+            double* dst = peers.buf[lane] + lay.off_gslot() + (par * 2 + end) * (size_t)(n + 1);
+            dst[0] = mesh[node];
+            for (int c = 0; c < n; c++) dst[1 + c] = y[(size_t)node * n + c];
+            st_release_sys(reinterpret_cast<unsigned long long*>(peers.buf[lane] + lay.off_gflag()) + par * 2 + end, e);
+        }
+    }
+    __syncwarp();
+    if (lane < 2) {
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xbuf + lay.off_gflag()) + par * 2 + lane;
+        if (!xchg_wait(fl, e)) atomicExch(status, 3);
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * (n + 1); i += 32) {
+        const int end = i / (n + 1), k = i % (n + 1);
+        const double v = __ldcg(xbuf + lay.off_gslot() + (par * 2 + end) * (size_t)(n + 1) + k);
+        if (k == 0) gmesh[end] = v; else gy[(size_t)end * n + k - 1] = v;
+    }
+    if (lane == 0) *epoch_ptr = e;
+}
+// NCCL flavour: every rank contributes [t_first, y_first, t_last, y_last]; after the all-gather the ghost mesh is rank 0's
+// first half and the last rank's second half
+__global__ void k_part_ends_pack(int n, int N, const double* __restrict__ mesh, const double* __restrict__ y, double* __restrict__ out) {
+    for (int i = threadIdx.x; i < 2 * (n + 1); i += blockDim.x) {
+        const int end = i / (n + 1), k = i % (n + 1), node = end ? N - 1 : 0;
+        out[i] = k == 0 ? mesh[node] : y[(size_t)node * n + k - 1];
+    }
+}
+__global__ void k_part_ends_unpack(int n, int G, const double* __restrict__ recv, double* __restrict__ gmesh, double* __restrict__ gy) {
+    for (int i = threadIdx.x; i < 2 * (n + 1); i += blockDim.x) {
+        const int end = i / (n + 1), k = i % (n + 1);
+        const double v = recv[(size_t)(end ? G - 1 : 0) * 2 * (n + 1) + i];
+        if (k == 0) gmesh[end] = v; else gy[(size_t)end * n + k - 1] = v;
+    }
 }
 
 // |bc rows|_inf of the rows this rank owns (a-rows on rank 0, b-rows on the last rank) into norm_bits

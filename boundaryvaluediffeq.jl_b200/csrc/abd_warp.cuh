@@ -599,7 +599,7 @@ struct PartPushArgs {
     unsigned long long* epoch;
 };
 struct PartIfaceArgs {
-    int L, La, rank, Nloc;
+    int L, La, standard, rank, Nloc;
     double* xbuf;
     XchgLayout lay;
     double *if_L, *if_R, *if_r, *if_Bc, *if_resid, *if_delta, *delta;
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kTailWarps * 32, 1)
 k_part_interface(const PartIfaceArgs w, const TailArgs ai, const TailArgs al) {
     extern __shared__ double tail_smem[];
     __shared__ __align__(16) TailSmem<n> sm;
-    part_wait_unpack_body(n, w.L, w.La, w.xbuf, w.lay, w.if_L, w.if_R, w.if_r, w.if_Bc, w.if_resid, w.epoch, w.status);
+    part_wait_unpack_body(n, w.L, w.La, w.standard, w.xbuf, w.lay, w.if_L, w.if_R, w.if_r, w.if_Bc, w.if_resid, w.epoch, w.status);
     __syncthreads();
     tail_body<n>(ai, sm, tail_smem);  // interface system: reduce, closing solve, back substitution
     __syncthreads();

@@ -213,6 +213,9 @@ struct mirk_solver_s {
     XchgPeers peers;
     XchgLayout xlay;
     unsigned long long* xepoch = nullptr;
+    // Standard problems (boundary rows couple both outer ends): the two-node ghost mesh the boundary rows are evaluated on
+    bool part_standard = false;
+    double *gmesh = nullptr, *gy = nullptr, *gsend = nullptr, *grecv = nullptr;
     // interface system on the nranks+1 segment end nodes
     Plan iplan;
     double *if_L = nullptr, *if_R = nullptr, *if_r = nullptr, *if_TL = nullptr, *if_TR = nullptr, *if_rt = nullptr,
@@ -485,7 +488,22 @@ static int launch_check(const char* what) {
 // the norm is then max-reduced over the ranks so every rank takes the same Newton decisions
 static int eval_bc(mirk_solver_s* S, int want_jac, bool into_norm) {
     unsigned long long* nb = (into_norm && !S->part) ? S->words : S->words + 3;
-    S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev, nb, want_jac);
+    if (S->part && S->part_standard) {
+        // both outer end states to every rank, then the boundary rows on the two-node ghost mesh (abd.cuh)
+        if (S->p2p) {
+            k_part_ends_bcast<<<1, 32, 0, S->st>>>(S->n, S->N, S->mesh, S->y, S->xbuf, S->peers, S->xlay, S->rank, S->xepoch + 2,
+                                                   (int*)(S->words + 2), S->gmesh, S->gy);
+            S->launches++;
+        } else {
+            k_part_ends_pack<<<1, 64, 0, S->st>>>(S->n, S->N, S->mesh, S->y, S->gsend);
+            CKN(g_nccl.AllGather(S->gsend, S->grecv, (size_t)2 * (S->n + 1), ncclDouble, S->comm, S->st));
+            k_part_ends_unpack<<<1, 64, 0, S->st>>>(S->n, S->nranks, S->grecv, S->gmesh, S->gy);
+            S->launches += 2;
+        }
+        S->ops->bc(S->st, 2, S->gmesh, S->gy, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev, nb, want_jac);
+    } else {
+        S->ops->bc(S->st, S->N, S->mesh, S->y, S->p, S->Kd, S->Ki, S->resid, S->bc_nodes, S->Bc, S->m_dev, nb, want_jac);
+    }
     S->launches++;
     if (S->ops->problem_type == 0) S->ki_dirty = true;  // interior boundary times fill their interval's Ki
     if (S->part && into_norm) {
@@ -659,13 +677,13 @@ static int part_exchange_and_close(mirk_solver_s* S) {
         // pack + all-gather as ONE kernel pushing into every peer's exchange buffer over NVLink; wait + unpack the other
         k_part_push<<<1, 1024, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
                                            tail_off, S->peers, S->xlay, S->rank, S->xepoch);
-        k_part_wait_unpack<<<1, 1024, 0, S->st>>>(n, S->L, S->La, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc,
+        k_part_wait_unpack<<<1, 1024, 0, S->st>>>(n, S->L, S->La, S->part_standard ? 1 : 0, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc,
                                                   S->if_resid, S->xepoch, (int*)(S->words + 2));
     } else {
         k_part_pack<<<8, 256, 0, S->st>>>(n, S->L, S->La, P.relL[P.nlev], P.relR[P.nlev], P.relr[P.nlev], S->Bc, S->resid,
                                           tail_off, S->sendbuf);
         CKN(g_nccl.AllGather(S->sendbuf, S->recvbuf, pay, ncclDouble, S->comm, S->st));
-        k_part_unpack<<<8, 256, 0, S->st>>>(n, G, S->L, S->La, S->recvbuf, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid);
+        k_part_unpack<<<8, 256, 0, S->st>>>(n, G, S->L, S->La, S->part_standard ? 1 : 0, S->recvbuf, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid);
     }
     S->launches += 2;
     SolveCtx I{&S->iplan, S->if_TL, S->if_TR, S->if_rt, S->if_delta, S->if_Bc, S->if_bc_nodes, S->if_m, S->if_resid,
@@ -722,7 +740,7 @@ static int abd_final(mirk_solver_s* S, const SolveCtx& C) {
             ai.delta = I.delta;
             TailArgs al = a;
             al.mode = 4;
-            PartIfaceArgs w{S->L, S->La, S->rank, S->N, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid,
+            PartIfaceArgs w{S->L, S->La, S->part_standard ? 1 : 0, S->rank, S->N, S->xbuf, S->xlay, S->if_L, S->if_R, S->if_r, S->if_Bc, S->if_resid,
                             S->if_delta, S->delta, S->xepoch, (int*)(S->words + 2)};
             CK(launch_part_interface(S->st, n, w, ai, al, final_smem_bytes(Di, mi_smem)));
             S->launches += 2;
@@ -1392,6 +1410,11 @@ static int part_setup_interface(mirk_solver_s* S, int rank, int nranks) {
     const int hb[2] = {0, nranks}, hm = 2;
     CK(cudaMemcpy(S->if_bc_nodes, hb, sizeof(hb), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(S->if_m, &hm, sizeof(int), cudaMemcpyHostToDevice));
+    S->part_standard = S->ops->problem_type != 1;
+    if (S->part_standard) {
+        CK(dalloc(&S->gmesh, (size_t)2)); CK(dalloc(&S->gy, (size_t)2 * S->n));
+        CK(dalloc(&S->gsend, (size_t)2 * (S->n + 1))); CK(dalloc(&S->grecv, (size_t)2 * (S->n + 1) * nranks));
+    }
     S->rank = rank;
     S->nranks = nranks;
     // interface plan: nranks relations on nranks+1 nodes, the two outer ends carry the boundary rows
@@ -1403,7 +1426,15 @@ static int part_setup_interface(mirk_solver_s* S, int rank, int nranks) {
 }
 static int part_check(mirk_solver_s* S, int rank, int nranks) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MIRK_ERR_ARG, "bad rank / nranks");
-    if (S->ops->problem_type != 1) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning needs a TwoPointBVProblem");
+    if (S->ops->problem_type != 1) {
+        // a Standard problem qualifies when its boundary condition reads the solution at the two END POINTS only (then the
+        // rows are evaluated on the exchanged end states); interior evaluation times would need the owning rank's interpolant
+        if (!S->have_guess) return fail(MIRK_ERR_STATE, "no mesh/guess set");
+        int bcn[16];
+        const int m = S->ops->bc_nodes_host(S->N, S->h_mesh.data(), S->h_p.data(), bcn);
+        if (!(m == 2 && bcn[0] == 0 && bcn[1] == S->N - 1))
+            return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning of a Standard problem needs boundary conditions at the two end points only");
+    }
     if (S->desc.adaptive) return fail(MIRK_ERR_UNSUPPORTED, "mesh partitioning runs on a fixed mesh (adaptive = false)");
     if (S->part) return fail(MIRK_ERR_STATE, "already attached");
     return MIRK_OK;
@@ -1429,11 +1460,11 @@ int mirk_partition_p2p_export(mirk_handle S, int32_t rank, int32_t nranks, void*
     if (nranks > kMaxPeers) return fail(MIRK_ERR_UNSUPPORTED, "peer-memory exchange supports at most 16 ranks");
     if (S->xbuf) return fail(MIRK_ERR_STATE, "exchange buffer already exported");
     CK(cudaSetDevice(S->desc.device));
-    S->xlay = XchgLayout{nranks, part_payload_doubles(S->n, S->L)};
+    S->xlay = XchgLayout{nranks, part_payload_doubles(S->n, S->L), S->n};
     CK(dalloc(&S->xbuf, S->xlay.total()));
     CK(cudaMemset(S->xbuf, 0, S->xlay.total() * sizeof(double)));
-    CK(dalloc(&S->xepoch, 2));
-    CK(cudaMemset(S->xepoch, 0, 2 * sizeof(unsigned long long)));
+    CK(dalloc(&S->xepoch, 3));  // payload exchange, words max-reduce, end-state broadcast
+    CK(cudaMemset(S->xepoch, 0, 3 * sizeof(unsigned long long)));
     CK(cudaDeviceSynchronize());  // flags are zero before any peer can learn the handle
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t hnd;
@@ -1491,6 +1522,7 @@ int mirk_destroy(mirk_handle S) {
             if (r != S->rank && S->peers.buf[r]) cudaIpcCloseMemHandle(S->peers.buf[r]);
     dfree(S->xbuf);
     dfree(S->xepoch);
+    dfree(S->gmesh); dfree(S->gy); dfree(S->gsend); dfree(S->grecv);
     if (S->h_words) cudaFreeHost(S->h_words);
     if (S->st) cudaStreamDestroy(S->st);
     delete S;

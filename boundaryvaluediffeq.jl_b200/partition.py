@@ -85,8 +85,8 @@ def init_partitioned(prob: BVProblem, alg: _AbstractMIRK, group=None, device: Op
     "nccl": one ncclAllGather + one ncclAllReduce per Newton step on the solver's stream."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    if prob.f.info.problem_type != 1:
-        raise NotImplementedError("mesh partitioning needs a TwoPointBVProblem")
+    # (TwoPointBVProblems, and Standard problems whose boundary condition reads the two end points only: the library
+    #  refuses anything else with MIRK_ERR_UNSUPPORTED)
     y, mesh = _arr(prob.u0), _arr(prob.mesh)
     lo, hi = partition_mesh(len(mesh), world)[rank]
     if device is None:
@@ -163,7 +163,8 @@ def mesh_select(order: int, abstol: float, max_num_subintervals: int, mesh, est,
 def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abstol: float = 1e-6, adaptive: bool = True,
                       defect_threshold: float = 0.1, group=None, device: Optional[int] = None,
                       exchange: Optional[str] = None, max_outer: int = 1000, **kw) -> PartitionedSolution:
-    """Collective.  `solve(prob, alg; dt, abstol, adaptive)` of a TwoPointBVProblem whose mesh is partitioned over the
+    """Collective.  `solve(prob, alg; dt, abstol, adaptive)` of a BVProblem (two-point, or Standard with end-point boundary
+    conditions) whose mesh is partitioned over the
     ranks of `group`: the outer loop of `solve!` with DefectControl (MIRK/src/mirk.jl:286-388; same order of
     operations as mirk_solve in csrc/mirk_b200.cu).  Every rank passes the same problem and gets the same result."""
     import torch.distributed as dist

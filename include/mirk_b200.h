@@ -179,7 +179,9 @@ int mirk_measure_peaks(int32_t device, double* fp64_tflops, double* hbm_gbs);
 
 /* -- mesh-partitioned single problem (no reference counterpart: the reference is single-threaded).
  *    Every rank creates a handle on its GPU holding one contiguous mesh segment (neighbours share their
- *    boundary node) of a TwoPointBVProblem, then attaches it to a communicator.  The handle's mesh is fixed between
+ *    boundary node) of a TwoPointBVProblem — or of a Standard BVProblem whose boundary condition reads the solution at the
+ *    two END POINTS only: the outer end states are then exchanged before every boundary evaluation and each rank evaluates
+ *    the rows on them (interior evaluation times: MIRK_ERR_UNSUPPORTED) —, then attaches it to a communicator.  The handle's mesh is fixed between
  *    mirk_set_mesh_guess calls; the adaptive outer loop runs above the ABI (partition.solve_partitioned: local defect
  *    estimates, mirk_mesh_select on the gathered estimates, local re-interpolation, re-partitioning).  From then
  *    on mirk_residual / mirk_newton_step / mirk_newton_solve / mirk_solve / mirk_bench_newton_steps are

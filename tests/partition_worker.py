@@ -58,6 +58,48 @@ def main():
             print(f"  partitioned Newton step: {t.item() / 5:.3f} ms (phases us: {[round(1e3 * p / 5, 1) for p in ph[:7]]})", flush=True)
         dist.barrier()  # nobody frees its exchange buffer while a peer may still push into it
         cache.close()
+    # Standard problems (bc!(res, sol, p, t) sees both ends at once): the end states are exchanged before every boundary
+    # evaluation and each rank evaluates the rows on the two-node ghost mesh; both transports
+    for exchange, name, order, p, tspan, nint in (("p2p", "torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 37 * world + 4),
+                                                  ("nccl", "torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 37 * world + 4),
+                                                  ("p2p", "swirling", 6, [0.05], (0.0, 1.0), 64 * world + 1)):
+        alg = M.MIRK6() if order == 6 else M.MIRK4()
+        mesh = M.mesh_uniform(tspan[0], tspan[1], nint)
+        nst = 4 if name == "torus" else 6
+        y0 = np.zeros((nint + 1, nst))
+        if name == "torus":
+            y0[:, 0] = np.linspace(p[2], p[4], nint + 1); y0[:, 1] = np.linspace(p[3], p[5], nint + 1)
+        prob = M.BVProblem(name, y0, tspan, p=p, mesh=mesh)
+        cache, (lo, hi) = partition.init_partitioned(prob, alg, device=local, exchange=exchange)
+        _, nrm0 = cache.residual()
+        ret, it, nrm = cache.newton_solve()
+        full = partition.gather_solution(cache, nint + 1)
+        if rank == 0:
+            # (partitioned handles run plain NewtonRaphson: compare with the same solver)
+            ref = M.init(prob, (M.MIRK6 if order == 6 else M.MIRK4)(nlsolve=M.NewtonRaphson()), adaptive=False, device=local)
+            _, ref_nrm0 = ref.residual()
+            rret, rit, rnrm = ref.newton_solve()
+            _, u = ref.solution()
+            err = np.max(np.abs(full - u)) / max(1.0, np.max(np.abs(u)))
+            print(f"standard {name} MIRK{order} N={nint + 1} world={world} exchange={exchange}: iters {it} vs {rit}, |F| {nrm:.3e} vs {rnrm:.3e}, rel err {err:.2e}", flush=True)
+            assert (ret, it) == (rret, rit) and ret == 0
+            assert abs(nrm0 - ref_nrm0) <= 1e-12 * max(1.0, ref_nrm0)
+            assert err < 1e-9
+            ref.close()
+        dist.barrier()
+        cache.close()
+    # ... and adaptively: the boundary layer eps = 0.05 (Standard, end-point conditions) refines its mesh
+    if True:
+        prob = M.BVProblem("layer", [0.0, 0.0], (-1.0, 1.0), p=[0.05])
+        sol = partition.solve_partitioned(prob, M.MIRK4(), dt=2.0 / (12 * world + 3), abstol=1e-6, device=local)
+        if rank == 0:
+            ref = M.solve(prob, M.MIRK4(nlsolve=M.NewtonRaphson()), dt=2.0 / (12 * world + 3), abstol=1e-6, device=local)
+            print(f"adaptive standard layer world={world}: retcode {sol.retcode} vs {ref.retcode}, meshes {sol.hist_n_mesh} vs "
+                  f"{ref.original['hist_n_mesh']}, newton {sol.hist_newton} vs {ref.original['hist_newton']}", flush=True)
+            assert sol.retcode == ref.retcode == 0
+            assert sol.hist_n_mesh == ref.original["hist_n_mesh"] and sol.hist_newton == ref.original["hist_newton"]
+            assert np.max(np.abs(sol.u - ref.u)) / max(1.0, np.max(np.abs(ref.u))) < 1e-5
+        dist.barrier()
     # the adaptive outer loop over the partitioned handle (partition.solve_partitioned) against solve() on one GPU:
     # same Newton counts, same mesh-size history, same final mesh, solution to 1e-10
     for maker, order, nint, abstol in (("c2_chain8", 4, 16 * world + 5, 1e-8), ("c5_chain16", 6, 11 * world + 2, 1e-9)):
