@@ -356,8 +356,8 @@ def run_newton(args):
         handles = [(cache._h, bufs0)] + [(c._h, pinned_set()) for c in extra_caches]
         for h, b in handles[1:]:
             e2e_loop(h, b, args.warmup)
-        # at least 8 steps per handle: with fewer the start-up of the host threads is what gets timed
-        per = max(8, (args.steps + nh - 1) // nh)
+        # at least 24 steps per handle: with few the start-up of the host threads is what gets timed
+        per = max(24, (args.steps + nh - 1) // nh)
         th = [threading.Thread(target=e2e_loop, args=(h, b, per)) for h, b in handles]
         barrier()
         t0 = time.perf_counter()
