@@ -160,6 +160,20 @@ def mesh_select(order: int, abstol: float, max_num_subintervals: int, mesh, est,
     return rc, (out[:nn.value].copy() if rc == 0 else None)
 
 
+def owned_nodes(mesh, lo: int, hi: int, rank: int, world: int, mesh_new) -> np.ndarray:
+    """Which nodes of `mesh_new` the rank holding old nodes [lo, hi] re-interpolates: node t belongs to the rank whose
+    segment contains the interval the reference's `interval(mesh, t)` = clamp(searchsortedfirst(mesh, t) - 1, 1, N - 1)
+    picks (CORE/src/utils.jl:119-121), i.e. (mesh[lo], mesh[hi]]; t <= t0 goes to rank 0, anything beyond the last node
+    to the last rank.  Every new node is owned by exactly one rank."""
+    mesh, mesh_new = np.asarray(mesh), np.asarray(mesh_new)
+    mine = (mesh_new > mesh[lo]) & (mesh_new <= mesh[hi])
+    if rank == 0:
+        mine |= mesh_new <= mesh[lo]
+    if rank == world - 1:
+        mine |= mesh_new > mesh[hi]
+    return mine
+
+
 def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abstol: float = 1e-6, adaptive: bool = True,
                       defect_threshold: float = 0.1, group=None, device: Optional[int] = None,
                       exchange: Optional[str] = None, max_outer: int = 1000, **kw) -> PartitionedSolution:
@@ -216,14 +230,8 @@ def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abst
                     if rc != 0:
                         info = rc
                         break
-                    # new guess = old interpolant at the new nodes; node t belongs to the rank whose segment holds the
-                    # interval searchsortedfirst(mesh, t) - 1 (CORE/utils.jl:119-121): (mesh[lo], mesh[hi]], t0 to rank 0
-                    mine = (mesh_new > mesh[lo]) & (mesh_new <= mesh[hi])
-                    if rank == 0:
-                        mine |= mesh_new <= mesh[lo]
-                    if rank == world - 1:
-                        mine |= mesh_new > mesh[hi]
-                    idx = np.nonzero(mine)[0]
+                    # new guess = old interpolant at the new nodes, each evaluated by the rank that owns its old interval
+                    idx = np.nonzero(owned_nodes(mesh, lo, hi, rank, world, mesh_new))[0]
                     ts = np.ascontiguousarray(mesh_new[idx])
                     vals = np.zeros((len(ts), cache.n))
                     if len(ts):

@@ -234,3 +234,23 @@ def test_struct_layouts_agree_between_header_ctypes_and_julia(tmp_path):
         jsize, joffs = _julia_layout(jl)
         assert jsize == c["sizeof." + cname], (jl, jsize)
         assert joffs == fields, (jl, joffs, fields)
+
+
+def test_partitioned_reinterpolation_ownership_follows_the_reference_interval_rule():
+    """partition.owned_nodes: every node of a refined mesh is re-interpolated by exactly one rank, the one whose segment
+    holds interval(mesh, t) = clamp(searchsortedfirst(mesh, t) - 1, 1, N - 1) (CORE/src/utils.jl:119-121) — a new node that
+    coincides with an old one belongs to the interval on its LEFT, hence to the left rank at a segment boundary."""
+    from boundaryvaluediffeq_jl_b200 import partition
+    rng = np.random.default_rng(3)
+    mesh = np.sort(np.concatenate([[0.0, 1.0], rng.uniform(0, 1, 37)]))
+    new = np.sort(np.concatenate([mesh[::3], rng.uniform(0, 1, 80), [0.0, 1.0]]))
+    for world in (1, 2, 3, 5):
+        parts = partition.partition_mesh(len(mesh), world)
+        owners = np.zeros(len(new), dtype=int)
+        for r, (lo, hi) in enumerate(parts):
+            m = partition.owned_nodes(mesh, lo, hi, r, world, new)
+            owners += m
+            # the reference's interval of every owned node lies inside this rank's segment
+            iv = np.clip(np.searchsorted(mesh, new[m], side="left") - 1, 0, len(mesh) - 2)
+            assert np.all((iv >= lo) & (iv + 1 <= hi))
+        assert np.all(owners == 1)
