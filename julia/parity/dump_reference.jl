@@ -47,6 +47,13 @@ function layer_f!(du, u, p, t)
 end
 layer_bc!(res, sol, p, t) = (res[1] = sol(-1.0)[1] + 2.0; res[2] = sol(1.0)[1]; nothing)
 
+# u'' = -u with a boundary condition that reads the DERIVATIVE of the interpolant (sol(t, Val{1}),
+# lib/BoundaryValueDiffEqMIRK/src/interpolation.jl:277-292); p = [alpha, c]: u1(0) = 0, u1(pi/2) - 1 + alpha (u1'(pi/4) - c) = 0.
+# Pins what the repository assumes about it: the derivative is built from the Float64 stage buffers, so it does not enter
+# the boundary Jacobian and Newton converges linearly in that row (5 steps at alpha = 0.1, not the 1 of a linear problem).
+robin_f!(du, u, p, t) = (du[1] = u[2]; du[2] = -u[1]; nothing)
+robin_bc!(res, sol, p, t) = (res[1] = sol(0.0)[1]; res[2] = sol(pi / 2)[1] - 1.0 + p[1] * (sol(pi / 4, Val{1})[1] - p[2]); nothing)
+
 # chain of NP torsionally coupled pendula (BASELINE config C2 at a size the reference finishes quickly)
 function chain_f!(du, u, p, t)
     NP = length(u) ÷ 2
@@ -117,6 +124,9 @@ for (order, alg) in algs
         dt = 0.01, abstol = 1.0e-4)
     dump_case("ref_layer_mirk$(order).json", "layer", order,
         BVProblem(BVPFunction(layer_f!, layer_bc!; bcresid_prototype = zeros(2)), [0.0, 0.0], (-1.0, 1.0), [0.01]), alg; dt = 0.05)
+    dump_case("ref_robin_sine_mirk$(order).json", "robin_sine", order,
+        BVProblem(BVPFunction(robin_f!, robin_bc!; bcresid_prototype = zeros(2)), [0.0, 1.0], (0.0, pi / 2), [0.1, cos(pi / 4)]), alg;
+        dt = order == 4 ? 0.05 : 0.1)
     # a start from which plain NewtonRaphson fails: pins the polyalgorithm fallbacks and the halve-and-zero path
     dump_case("ref_lotka_hard_mirk$(order).json", "lotka", order,
         BVProblem(BVPFunction(lotka_f!, lotka_bc!; bcresid_prototype = zeros(2)), [5.0, 5.0], (0.0, 10.0), [7.5, 4.0, 8.5, 5.0]), alg; dt = 0.1)
