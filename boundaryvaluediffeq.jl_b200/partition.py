@@ -160,6 +160,23 @@ def mesh_select(order: int, abstol: float, max_num_subintervals: int, mesh, est,
     return rc, (out[:nn.value].copy() if rc == 0 else None)
 
 
+def gather_estimates(defect_local: float, est_local, group=None):
+    """(global defect norm, per-interval estimates of the whole mesh in rank order) from every rank's local ones; the
+    maximum propagates NaN like the device reduction does."""
+    parts = _allgather_obj((float(defect_local), np.asarray(est_local)), group)
+    ds = [d for d, _ in parts]
+    return (float("nan") if any(d != d for d in ds) else max(ds)), np.concatenate([e for _, e in parts])
+
+
+def gather_rows(idx, vals, n_rows: int, group=None) -> np.ndarray:
+    """Assemble an (n_rows, n) array from every rank's (row indices, rows): the new guess of the refined mesh."""
+    vals = np.asarray(vals)
+    out = np.zeros((n_rows, vals.shape[1]))
+    for ii, vv in _allgather_obj((np.asarray(idx), vals), group):
+        out[ii] = vv
+    return out
+
+
 def owned_nodes(mesh, lo: int, hi: int, rank: int, world: int, mesh_new) -> np.ndarray:
     """Which nodes of `mesh_new` the rank holding old nodes [lo, hi] re-interpolates: node t belongs to the rank whose
     segment contains the interval the reference's `interval(mesh, t)` = clamp(searchsortedfirst(mesh, t) - 1, 1, N - 1)
@@ -217,11 +234,7 @@ def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abst
             if info == 0:
                 d_loc, errs = cache.defect()
                 est_loc = np.max(np.abs(errs), axis=1) if errs.size else np.zeros(0)
-                parts = _allgather_obj((float(d_loc), est_loc), group)
-                # NaN-propagating maximum, as the device reduction
-                ds = [d for d, _ in parts]
-                err_norm = float("nan") if any(d != d for d in ds) else max(ds)
-                est = np.concatenate([e for _, e in parts])
+                err_norm, est = gather_estimates(d_loc, est_loc, group)
                 if not (err_norm <= defect_threshold):
                     info = 1
                 hist_d[-1] = err_norm
@@ -236,10 +249,7 @@ def solve_partitioned(prob: BVProblem, alg: _AbstractMIRK, dt: float = 0.0, abst
                     vals = np.zeros((len(ts), cache.n))
                     if len(ts):
                         B.check(B.lib().mirk_interp(cache._h, ts.ctypes.data_as(B.dp), len(ts), 0, vals.ctypes.data_as(B.dp)))
-                    y_new = np.zeros((len(mesh_new), cache.n))
-                    for ii, vv in _allgather_obj((idx, vals), group):
-                        y_new[ii] = vv
-                    mesh, y = mesh_new, y_new
+                    mesh, y = mesh_new, gather_rows(idx, vals, len(mesh_new), group)
                     continue
             if info != 0:
                 if 2 * (N - 1) > max_sub:

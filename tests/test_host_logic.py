@@ -254,3 +254,50 @@ def test_partitioned_reinterpolation_ownership_follows_the_reference_interval_ru
             iv = np.clip(np.searchsorted(mesh, new[m], side="left") - 1, 0, len(mesh) - 2)
             assert np.all((iv >= lo) & (iv + 1 <= hi))
         assert np.all(owners == 1)
+
+
+_PART_WORKER = r"""
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+import mirk_b200  # noqa
+from boundaryvaluediffeq_jl_b200 import partition
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(5)                                    # same numbers on both ranks
+mesh = np.sort(np.concatenate([[0.0, 2.0], rng.uniform(0, 2, 40)]))
+new = np.sort(np.concatenate([[0.0, 2.0], mesh[5::7], rng.uniform(0, 2, 61)]))
+lo, hi = partition.partition_mesh(len(mesh), world)[rank]
+# the adaptive step of solve_partitioned with a stand-in interpolant u(t) = (t, t^2): local estimates, global selector
+# input, local re-interpolation of the owned nodes, assembled new guess
+est_local = np.abs(np.sin(mesh[lo:hi]))                           # one entry per local interval
+dn, est = partition.gather_estimates(float(est_local.max()), est_local)
+assert est.shape == (len(mesh) - 1,) and np.array_equal(est, np.abs(np.sin(mesh[:-1]))) and dn == est.max()
+dn_nan, _ = partition.gather_estimates(float("nan") if rank == 1 else 1.0, est_local)
+assert dn_nan != dn_nan
+idx = np.nonzero(partition.owned_nodes(mesh, lo, hi, rank, world, new))[0]
+vals = np.stack([new[idx], new[idx] ** 2], axis=1)
+y_new = partition.gather_rows(idx, vals, len(new))
+assert np.array_equal(y_new[:, 0], new) and np.array_equal(y_new[:, 1], new ** 2)
+dist.barrier()
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_two_rank_gloo_partitioned_adaptive_host_logic(tmp_path):
+    """The host side of the mesh-partitioned adaptive loop (partition.gather_estimates / owned_nodes / gather_rows) on
+    two gloo ranks: the gathered estimates are the whole mesh's in rank order, a NaN defect on one rank is a NaN
+    everywhere, and the re-interpolated rows of both ranks assemble into the complete new guess."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "part_worker.py"
+    script.write_text(_PART_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0, err[-2000:]
+        assert "ok" in out
