@@ -70,6 +70,9 @@ def test_reference_ensemble_test_with_prob_func(M, oracle):
     ("lotka", 4, [7.5, 4.0, 8.5, 5.0], [1.0, 2.0], (0.0, 10.0), 0.1, {"node_cap": 1024}),  # big defect
     ("torus", 4, [4.0, 1.0, 0.0, 0.0, 1.0, 2.0], [0.0, 0.0, 1.0, 2.0], (0.0, 1.0), 0.05, {}),  # n = 4
     ("swirling", 4, [0.01], [0.0] * 6, (0.0, 1.0), 0.01, {"abstol": 1e-4}),       # n = 6
+    # singular term (y' = S y / t + f) through the warp kernel's stage-wise Jacobian; fixed mesh (see test_gpu_parity.py)
+    ("lane_emden", 4, [], [1.0, 0.0], (0.0, 1.0), 0.01, {"adaptive": False}),
+    ("lane_emden", 6, [], [1.0, 0.0], (0.0, 1.0), 0.02, {"adaptive": False}),
 ])
 def test_single_trajectory_ensembles_follow_the_single_solve_path(M, oracle, name, order, p, u0, tspan, dt, kw):
     """Each thread runs the same adaptive loop as mirk_solve: compare a few-trajectory ensemble of identical
