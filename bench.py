@@ -552,6 +552,64 @@ def measure_c5(args, which="c5"):
             "workload": f"{c.key}: {c.desc}; mesh partitioned into {world} segment(s)"}
 
 
+# ---- BASELINE config C1: the reference's own benchmark suite (benchmark/simple_pendulum.jl:66-70) -----------------
+def measure_c1(args):
+    """`solve(prob_iip, alg(), dt = 0.05)` for alg in MIRK2 … MIRK6 on the simple pendulum — the five MIRK lines of the
+    reference's benchmark suite, one complete adaptive solve each, through the public API (host wall clock: a solve of 33
+    nodes is launch- and synchronisation-bound, a device-only time would flatter it).  Beside it the CPU restatement on
+    one host core (the problem the reference is built for: n = 2, 33 -> ~50 nodes) and, as an independent solver,
+    scipy.integrate.solve_bvp on the two-point relative of the problem (theta(0) = -pi/2 instead of the interior
+    condition; same 4th-order formula as MIRK4, other mesh refinement)."""
+    import statistics
+
+    import numpy as np
+
+    import mirk_b200 as M
+    from oracle import oracle as O
+
+    u0, tspan, p = [math.pi / 2, math.pi / 2], (0.0, math.pi / 2), [9.81]
+    prob = M.BVProblem("pendulum", u0, tspan, p=p)
+    reps = 15
+    out = {"metric": "bvp_solve_wall_ms", "unit": "ms per solve (median of %d, host wall clock)" % reps, "lower_is_better": True,
+           "workload": "C1: benchmark/simple_pendulum.jl, solve(prob, alg(), dt = 0.05), adaptive, abstol = 1e-6", "algs": {}}
+    for name, order in (("MIRK2", 2), ("MIRK3", 3), ("MIRK4", 4), ("MIRK5", 5), ("MIRK6", 6)):
+        alg = getattr(M, name)()
+        sol = M.solve(prob, alg, dt=0.05)  # warm-up (graph capture, first launches)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            sol = M.solve(prob, alg, dt=0.05)
+            ts.append(time.perf_counter() - t0)
+        ref = O.solve_dt(O.builtin("pendulum"), order, p, u0, tspan, 0.05)
+        tc = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ref = O.solve_dt(O.builtin("pendulum"), order, p, u0, tspan, 0.05)
+            tc.append(time.perf_counter() - t0)
+        same = sol.original["hist_n_mesh"] == ref.hist_N and sol.original["hist_newton"] == ref.hist_newton
+        err = float(np.max(np.abs(sol.u - ref.u)) / np.max(np.abs(ref.u))) if len(sol.t) == len(ref.t) else None
+        out["algs"][name] = {"gpu_ms": 1e3 * statistics.median(ts), "cpu_port_ms": 1e3 * statistics.median(tc), "retcode": int(sol.retcode),
+                             "mesh_history": list(sol.original["hist_n_mesh"]), "newton_history": list(sol.original["hist_newton"]),
+                             "same_histories_as_cpu_port": bool(same), "max_rel_diff_vs_cpu_port": err}
+    try:
+        from scipy.integrate import solve_bvp
+        x = np.linspace(tspan[0], tspan[1], 33)
+        y = np.full((2, 33), math.pi / 2)
+        f = lambda t, u: np.vstack([u[1], -9.81 * np.sin(u[0])])  # noqa: E731
+        bc = lambda ua, ub: np.array([ua[0] + math.pi / 2, ub[0] - math.pi / 2])  # noqa: E731
+        tsp = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = solve_bvp(f, bc, x, y, tol=1e-6)
+            tsp.append(time.perf_counter() - t0)
+        out["scipy_solve_bvp"] = {"ms": 1e3 * statistics.median(tsp), "status": int(r.status), "nodes": int(r.x.size),
+                                  "note": "two-point relative of C1 (theta(0) = -pi/2), independent solver, 1 core"}
+    except Exception as e:  # noqa: BLE001
+        out["scipy_solve_bvp"] = {"error": str(e)[:200]}
+    out["cpu_baseline"] = {"kind": "port", "cores": 1, "sample": "the same 15 solves per method, oracle/mirk_oracle.c orc_solve"}
+    return out
+
+
 def _guarded(fn, *a, **kw):
     """extras must not take the headline line down with them"""
     try:
@@ -610,6 +668,7 @@ def main():
                 extra = {"c3_strong": _guarded(measure_ensemble, args, "strong", True), "c5part": _guarded(measure_c5, args)}
                 if int(os.environ.get("WORLD_SIZE", "1")) == 1:
                     extra["c4"] = _guarded(measure_c5, args, "c4")
+                    extra["c1"] = _guarded(measure_c1, args)
                 dog.cancel()
             if rank == 0:
                 line["extra"] = extra
