@@ -591,6 +591,29 @@ def measure_c1(args):
         out["algs"][name] = {"gpu_ms": 1e3 * statistics.median(ts), "cpu_port_ms": 1e3 * statistics.median(tc), "retcode": int(sol.retcode),
                              "mesh_history": list(sol.original["hist_n_mesh"]), "newton_history": list(sol.original["hist_newton"]),
                              "same_histories_as_cpu_port": bool(same), "max_rel_diff_vs_cpu_port": err}
+    # the same solve as ONE kernel launch: a one-trajectory ensemble (solve(EnsembleProblem(prob), alg; trajectories = 1):
+    # the warp-per-trajectory whole-solve kernel, instantiated for MIRK4 / MIRK6) — parameters in, final mesh and solution out
+    try:
+        from boundaryvaluediffeq_jl_b200 import ensemble as E
+        for name, order in (("MIRK4", 4), ("MIRK6", 6)):
+            h = E.EnsembleHandle(prob, getattr(M, name)(), 1, 0.05)
+            par = np.array([[9.81]])
+            tk = []
+            for i in range(reps + 2):
+                t0 = time.perf_counter()
+                h.set_inputs(par, prob.u0)
+                h.run()
+                res = h.results()
+                mesh, y = h.trajectory(0)
+                if i >= 2:
+                    tk.append(time.perf_counter() - t0)
+            ref = O.solve_dt(O.builtin("pendulum"), order, p, u0, tspan, 0.05)
+            ok = int(res["retcodes"][0]) == 0 and len(mesh) == len(ref.t)
+            out["algs"][name]["gpu_one_kernel_ms"] = 1e3 * statistics.median(tk)
+            out["algs"][name]["one_kernel_max_rel_diff_vs_cpu_port"] = float(np.max(np.abs(y - ref.u)) / np.max(np.abs(ref.u))) if ok else None
+            h.close()
+    except Exception as e:  # noqa: BLE001
+        out["one_kernel_error"] = str(e)[:200]
     try:
         from scipy.integrate import solve_bvp
         x = np.linspace(tspan[0], tspan[1], 33)
