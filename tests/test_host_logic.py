@@ -301,3 +301,22 @@ def test_two_rank_gloo_partitioned_adaptive_host_logic(tmp_path):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_bench_work_model_partitions_the_survey_byte_and_flop_counts():
+    """B = 8 [2 n N + N + 2 * 2 n^2 (N - 1)] bytes and F = F_f + F_J + F_S flops per Newton step.  The per-kernel
+    figures bench.py divides by the measured kernel times must SUM to those totals (C2: 169.1 MB, ~1.43 GF; C4 ~73 GF;
+    C5 ~1.1 TF, 66 GB) — no kernel may be credited traffic the table does not list."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, N, order, B_expect, F_lo, F_hi in ((16, 20000, 6, 169.1e6, 1.35e9, 1.50e9), (128, 4000, 4, 2.10e9, 70e9, 76e9),
+                                              (32, 2000000, 6, 66.6e9, 1.05e12, 1.15e12)):
+        by, fl, B, F = bench.work_model(n, N, order)
+        assert B == 8 * (2 * n * N + N + 2 * 2 * n * n * (N - 1))
+        assert sum(by.values()) == B and abs(B - B_expect) / B_expect < 5e-3
+        assert abs(sum(fl.values()) - F) / F < 1e-12 and F_lo < F < F_hi
+        assert set(by) == set(bench.PHASES) == set(fl)
+        # the dominant kernel (level-0 reduction) is credited the READ of the blocks only
+        assert by["abd_reduce_level0"] == 8 * 2 * n * n * (N - 1)
