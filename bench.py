@@ -132,8 +132,9 @@ def cpu_steps(cfg, steps):
     return it, dt, nrm
 
 
-CPU_NOTE = ("oracle/mirk_oracle.c orc_newton: an untuned C restatement of the reference algorithm (gcc -O3 "
-            "-march=x86-64-v3, FMA contraction off, naive dense products), single thread like the reference's hot "
+CPU_NOTE = ("oracle/mirk_oracle.c orc_newton: a plain C restatement of the reference algorithm (gcc -O3 "
+            "-march=x86-64-v3, FMA contraction off; register-blocked unit-stride dense products, the 6 n^3 products per "
+            "interval MIRK6 needs, sequential row-pivoted ABD elimination), single thread like the reference's hot "
             "path; the Julia reference cannot run in this image, so this is context, not a tuned-CPU comparison")
 
 

@@ -434,12 +434,38 @@ void orc_loss(const orc_problem *P, const orc_tableau *T, const double *p, int N
 /* ------------------------------------------------------------------------------------------ */
 
 static void matmul_nn(int n, const double *A, const double *B, double *C) { /* C = A*B row-major */
-    for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) {
-            double acc = 0.0;
-            for (int k = 0; k < n; k++) acc += A[i * n + k] * B[k * n + j];
-            C[i * n + j] = acc;
+    /* column blocks of 16 / 4 / 1 with the accumulators of a block held in registers across the k loop (unit-stride,
+     * vectorisable).  Every C[i][j] still accumulates its products in ascending k from +0.0, so the result is
+     * bit-identical to the textbook i-j-k loop (no FMA contraction: see the Makefile) */
+    for (int i = 0; i < n; i++) {
+        const double *restrict Ai = A + (size_t)i * n;
+        double *restrict Ci = C + (size_t)i * n;
+        int j0 = 0;
+        for (; j0 + 16 <= n; j0 += 16) {
+            double acc[16];
+            for (int jj = 0; jj < 16; jj++) acc[jj] = 0.0;
+            for (int k = 0; k < n; k++) {
+                const double a = Ai[k];
+                const double *restrict Bk = B + (size_t)k * n + j0;
+                for (int jj = 0; jj < 16; jj++) acc[jj] += a * Bk[jj];
+            }
+            for (int jj = 0; jj < 16; jj++) Ci[j0 + jj] = acc[jj];
         }
+        for (; j0 + 4 <= n; j0 += 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < n; k++) {
+                const double a = Ai[k];
+                const double *restrict Bk = B + (size_t)k * n + j0;
+                for (int jj = 0; jj < 4; jj++) acc[jj] += a * Bk[jj];
+            }
+            for (int jj = 0; jj < 4; jj++) Ci[j0 + jj] = acc[jj];
+        }
+        for (; j0 < n; j0++) {
+            double acc = 0.0;
+            for (int k = 0; k < n; k++) acc += Ai[k] * B[(size_t)k * n + j0];
+            Ci[j0] = acc;
+        }
+    }
 }
 
 void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p, int N,
@@ -451,6 +477,7 @@ void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p,
     double *M = (double *)malloc(sizeof(double) * nn);
     double *A = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_i     */
     double *B = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_{i+1} */
+    int zA[16], zB[16];                                    /* stage derivative structurally zero */
     for (int i = 0; i < N - 1; i++) {
         const double h = mesh[i + 1] - mesh[i];
         const double *yi = y + (size_t)i * n, *yi1 = yi + n;
@@ -469,29 +496,68 @@ void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p,
                 }
                 for (int e = 0; e < nn; e++) J[e] += P->singular_term[e] / tt;
             }
-            /* A_r = J_r [(1-v_r) I + h sum_j x_rj A_j] */
-            for (int e = 0; e < nn; e++) M[e] = 0.0;
-            for (int k = 0; k < n; k++) M[k * n + k] = 1.0 - T->v[r];
-            for (int j = 0; j < r; j++)
-                if (T->x[r][j] != 0.0)
-                    for (int e = 0; e < nn; e++) M[e] += h * T->x[r][j] * A[j * nn + e];
-            matmul_nn(n, J, M, A + r * nn);
+            /* A_r = J_r [(1-v_r) I + h sum_j x_rj A_j];  a stage whose bracket is structurally zero (K_1 does not depend
+             * on y_{i+1}, a stage with v_r = 1 and no coupling not on y_i, ...) is the zero matrix: the product is skipped,
+             * which leaves the same bits as multiplying J_r by zeros */
+            int zero = (1.0 - T->v[r] == 0.0);
+            for (int j = 0; j < r; j++) if (T->x[r][j] != 0.0 && !zA[j]) zero = 0;
+            zA[r] = zero;
+            int coupled = 0;
+            for (int j = 0; j < r; j++) if (T->x[r][j] != 0.0 && !zA[j]) coupled = 1;
+            if (zero) {
+                for (int e = 0; e < nn; e++) A[r * nn + e] = 0.0;
+            } else if (!coupled) {
+                /* bracket = d I: J_r (d I) = d J_r entry by entry; "0.0 +" keeps the +0.0 the product loop leaves */
+                const double d = 1.0 - T->v[r];
+                for (int e = 0; e < nn; e++) A[r * nn + e] = 0.0 + J[e] * d;
+            } else {
+                for (int e = 0; e < nn; e++) M[e] = 0.0;
+                for (int k = 0; k < n; k++) M[k * n + k] = 1.0 - T->v[r];
+                for (int j = 0; j < r; j++)
+                    if (T->x[r][j] != 0.0) {
+                        const double hx = h * T->x[r][j];  /* (h * x) * A: the product order of the plain expression */
+                        const double *restrict Aj = A + (size_t)j * nn;
+                        double *restrict Mw = M;
+                        for (int e = 0; e < nn; e++) Mw[e] += hx * Aj[e];
+                    }
+                matmul_nn(n, J, M, A + r * nn);
+            }
             /* B_r = J_r [v_r I + h sum_j x_rj B_j] */
-            for (int e = 0; e < nn; e++) M[e] = 0.0;
-            for (int k = 0; k < n; k++) M[k * n + k] = T->v[r];
-            for (int j = 0; j < r; j++)
-                if (T->x[r][j] != 0.0)
-                    for (int e = 0; e < nn; e++) M[e] += h * T->x[r][j] * B[j * nn + e];
-            matmul_nn(n, J, M, B + r * nn);
+            zero = (T->v[r] == 0.0);
+            for (int j = 0; j < r; j++) if (T->x[r][j] != 0.0 && !zB[j]) zero = 0;
+            zB[r] = zero;
+            coupled = 0;
+            for (int j = 0; j < r; j++) if (T->x[r][j] != 0.0 && !zB[j]) coupled = 1;
+            if (zero) {
+                for (int e = 0; e < nn; e++) B[r * nn + e] = 0.0;
+            } else if (!coupled) {
+                const double d = T->v[r];
+                for (int e = 0; e < nn; e++) B[r * nn + e] = 0.0 + J[e] * d;
+            } else {
+                for (int e = 0; e < nn; e++) M[e] = 0.0;
+                for (int k = 0; k < n; k++) M[k * n + k] = T->v[r];
+                for (int j = 0; j < r; j++)
+                    if (T->x[r][j] != 0.0) {
+                        const double hx = h * T->x[r][j];
+                        const double *restrict Bj = B + (size_t)j * nn;
+                        double *restrict Mw = M;
+                        for (int e = 0; e < nn; e++) Mw[e] += hx * Bj[e];
+                    }
+                matmul_nn(n, J, M, B + r * nn);
+            }
         }
         double *Li = Lb + (size_t)i * nn, *Ri = Rb + (size_t)i * nn;
         for (int e = 0; e < nn; e++) { Li[e] = 0.0; Ri[e] = 0.0; }
         for (int k = 0; k < n; k++) { Li[k * n + k] = -1.0; Ri[k * n + k] = 1.0; }
-        for (int r = 0; r < s; r++)
+        for (int r = 0; r < s; r++) {
+            const double hb = h * T->b[r];
+            const double *restrict Ar = A + (size_t)r * nn, *restrict Br = B + (size_t)r * nn;
+            double *restrict Lw = Li, *restrict Rw = Ri;
             for (int e = 0; e < nn; e++) {
-                Li[e] -= h * T->b[r] * A[r * nn + e];
-                Ri[e] -= h * T->b[r] * B[r * nn + e];
+                Lw[e] -= hb * Ar[e];
+                Rw[e] -= hb * Br[e];
             }
+        }
     }
     free(tmp); free(K); free(J); free(M); free(A); free(B);
 }
@@ -590,9 +656,9 @@ int orc_abd_solve(int n, int N, int L, const double *Lb, const double *Rb, int m
                     act[(size_t)j * RW + c] = act[(size_t)pr * RW + c];
                     act[(size_t)pr * RW + c] = t;
                 }
-            const double *prow = act + (size_t)j * RW;
+            const double *restrict prow = act + (size_t)j * RW;
             for (int r = j + 1; r < RA; r++) {
-                double *row = act + (size_t)r * RW;
+                double *restrict row = act + (size_t)r * RW;  /* r != j: the rows do not overlap */
                 const double f = row[j] / prow[j];
                 if (f != 0.0) {
                     row[j] = 0.0;
