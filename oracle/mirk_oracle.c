@@ -300,11 +300,18 @@ int orc_interval(const double *mesh, int N, double t) {
 /* collocation residual  (MIRK/collocation.jl:44-72)                      */
 /* ------------------------------------------------------------------------------------------ */
 
-void orc_phi(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
-             const double *y, double *Kd, double *phi) {
+/* Threads over mesh intervals for the two interval-parallel loops (Phi and the Jacobian blocks) — used ONLY by the CPU
+ * baseline of bench.py (`--impl reference`, "all the host threads it can use").  Default 1: the reference's hot path is
+ * single-threaded, and the Python callbacks of the tests' custom problems must not be entered from several threads.
+ * Intervals are independent, so the results do not depend on the thread count. */
+static int g_interval_threads = 1;
+void orc_set_interval_threads(int nthreads) { g_interval_threads = nthreads > 1 ? nthreads : 1; }
+
+static void phi_range(const orc_problem *P, const orc_tableau *T, const double *p, const double *mesh,
+                      const double *y, double *Kd, double *phi, int i0, int i1) {
     const int n = P->n, s = T->s;
     double *tmp = (double *)malloc(sizeof(double) * n);
-    for (int i = 0; i < N - 1; i++) {
+    for (int i = i0; i < i1; i++) {
         const double h = mesh[i + 1] - mesh[i];
         const double *yi = y + (size_t)i * n, *yi1 = yi + n;
         double *K = Kd + (size_t)i * s * n;
@@ -328,6 +335,15 @@ void orc_phi(const orc_problem *P, const orc_tableau *T, const double *p, int N,
             for (int k = 0; k < n; k++) res[k] = -h * K[r * n + k] * T->b[r] + res[k];
     }
     free(tmp);
+}
+
+void orc_phi(const orc_problem *P, const orc_tableau *T, const double *p, int N, const double *mesh,
+             const double *y, double *Kd, double *phi) {
+    const int ni = N - 1, nt = g_interval_threads;
+    if (nt <= 1 || ni < 4 * nt) { phi_range(P, T, p, mesh, y, Kd, phi, 0, ni); return; }
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int c = 0; c < nt; c++)
+        phi_range(P, T, p, mesh, y, Kd, phi, (int)((long long)ni * c / nt), (int)((long long)ni * (c + 1) / nt));
 }
 
 /* interpolation stages (MIRK/interpolation.jl:300-372; Appendix A.3) */
@@ -468,8 +484,8 @@ static void matmul_nn(int n, const double *A, const double *B, double *C) { /* C
     }
 }
 
-void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p, int N,
-                    const double *mesh, const double *y, double *Lb, double *Rb) {
+static void jac_blocks_range(const orc_problem *P, const orc_tableau *T, const double *p,
+                             const double *mesh, const double *y, double *Lb, double *Rb, int i0, int i1) {
     const int n = P->n, s = T->s, nn = n * n;
     double *tmp = (double *)malloc(sizeof(double) * n);
     double *K = (double *)malloc(sizeof(double) * s * n);
@@ -478,7 +494,7 @@ void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p,
     double *A = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_i     */
     double *B = (double *)malloc(sizeof(double) * s * nn); /* dK_r/dy_{i+1} */
     int zA[16], zB[16];                                    /* stage derivative structurally zero */
-    for (int i = 0; i < N - 1; i++) {
+    for (int i = i0; i < i1; i++) {
         const double h = mesh[i + 1] - mesh[i];
         const double *yi = y + (size_t)i * n, *yi1 = yi + n;
         for (int r = 0; r < s; r++) {
@@ -560,6 +576,15 @@ void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p,
         }
     }
     free(tmp); free(K); free(J); free(M); free(A); free(B);
+}
+
+void orc_jac_blocks(const orc_problem *P, const orc_tableau *T, const double *p, int N,
+                    const double *mesh, const double *y, double *Lb, double *Rb) {
+    const int ni = N - 1, nt = g_interval_threads;
+    if (nt <= 1 || ni < 4 * nt) { jac_blocks_range(P, T, p, mesh, y, Lb, Rb, 0, ni); return; }
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int c = 0; c < nt; c++)
+        jac_blocks_range(P, T, p, mesh, y, Lb, Rb, (int)((long long)ni * c / nt), (int)((long long)ni * (c + 1) / nt));
 }
 
 /* BC Jacobian in the reference's pattern (quirk Q2): the interpolant inside loss_bc reads the

@@ -105,6 +105,8 @@ void orc_default_options(orc_options *o);
 #define ORC_MIRK6I 7 /* `order` code of MIRK6I (irrational 6th-order tableau); 2..6 are MIRK2..MIRK6 */
 int orc_convergence_order(int order);
 int orc_tableau_get(int order, orc_tableau *T);
+/* threads over mesh intervals in orc_phi / orc_jac_blocks (bench.py's CPU baseline only; default 1, results unchanged) */
+void orc_set_interval_threads(int nthreads);
 void orc_interp_weights(int order, double tau, double *w, double *wp);
 void orc_mesh_uniform(double t0, double t1, int nint, double *mesh);
 int orc_interval(const double *mesh, int N, double t); /* 0-based interval index */

@@ -77,6 +77,8 @@ def lib():
             build()
         L = C.CDLL(_LIB_PATH)
         L.orc_tableau_get.argtypes = [C.c_int, C.POINTER(Tableau)]
+        L.orc_set_interval_threads.argtypes = [C.c_int]
+        L.orc_set_interval_threads.restype = None
         L.orc_interp_weights.argtypes = [C.c_int, C.c_double, dp, dp]
         L.orc_mesh_uniform.argtypes = [C.c_double, C.c_double, C.c_int, dp]
         L.orc_interval.argtypes = [dp, C.c_int, C.c_double]
@@ -173,6 +175,12 @@ def custom_problem(n, n_p, f, dfdu, bc_times, bc, dbc, problem_type=0, n_bc=None
 
 
 MIRK6I = 7  # `order` code of the irrational 6th-order tableau (ORC_MIRK6I)
+
+
+def set_interval_threads(nthreads: int) -> None:
+    """Threads over mesh intervals in orc_phi / orc_jac_blocks (built-in problems only; bench.py's CPU baseline).  Results do not
+    depend on it; default 1."""
+    lib().orc_set_interval_threads(int(nthreads))
 
 
 def tableau(order) -> Tableau:
