@@ -582,3 +582,26 @@ def test_derivative_boundary_condition_known_answer(oracle):
         ref0 = O.solve_dt(P, order, [0.0, 0.0], [0.0, 1.0], (0.0, math.pi / 2), dt)
         assert ref0.retcode == 0 and ref0.hist_newton[0] == 1
         assert np.max(np.abs(np.asarray(ref0.u)[:, 0] - np.sin(np.asarray(ref0.t)))) < 1e-7
+
+
+def test_interval_threads_do_not_change_the_oracle(oracle):
+    """The CPU arm of bench.py runs the oracle's two interval-parallel loops (Phi, Jacobian blocks) on every host thread.
+    Intervals are independent: residual, blocks and a Newton iterate must be bit-identical for any thread count."""
+    O = oracle
+    import mirk_b200  # noqa: F401  (package alias for configs)
+    from boundaryvaluediffeq_jl_b200 import configs
+    c = configs.c2_chain8(257)
+    out = {}
+    try:
+        for nt in (1, 3, 8):
+            O.set_interval_threads(nt)
+            ws = O.Workspace(O.builtin(c.problem), c.order, c.p, c.mesh, c.y0)
+            r = ws.loss()
+            Lb, Rb = ws.jac_blocks()
+            ws.newton(abstol=0.0, maxiters=2)
+            out[nt] = (r, Lb, Rb, ws.y.copy())
+    finally:
+        O.set_interval_threads(1)
+    for nt in (3, 8):
+        for a, b in zip(out[1], out[nt]):
+            assert np.array_equal(a, b)
