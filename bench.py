@@ -462,6 +462,10 @@ def run_newton(args):
                                         "algorithmic_flops": step_flops, "achieved_tflops": step_flops / step_s * 1e-12,
                                         "fp64_frac": step_flops / step_s * 1e-12 / fp64.value,
                                         "note": "per GPU (per segment when partitioned); the per-kernel algorithmic bytes sum to this"},
+                         "per_phase": {PHASES[i]: {"ms": per_step_ms[i],
+                                                   "hbm_frac": kb[PHASES[i]] / (per_step_ms[i] * 1e-3) * 1e-9 / hbm_peak,
+                                                   "fp64_frac": kf[PHASES[i]] / (per_step_ms[i] * 1e-3) * 1e-12 / fp64.value}
+                                       for i in range(7) if per_step_ms[i] > 0 and (kb[PHASES[i]] or kf[PHASES[i]])},
                          "live_peaks": {"fp64_fma_tflops": fp64.value, "hbm_copy_gbs": hbm_live.value}},
             "phases_ms_per_step": dict(zip(PHASES, per_step_ms)),
             "concurrent_problems": concurrent,
